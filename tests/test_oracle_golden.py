@@ -1,0 +1,112 @@
+"""The CPU oracles against vectors produced by the real reference (oracle/make_golden.py)."""
+
+import numpy as np
+import pytest
+
+from conftest import as_float_pairs, assert_same, golden_tree, load_golden
+from oracle import fast, port
+
+
+@pytest.mark.parametrize("impl", [port, fast], ids=["port", "fast"])
+def test_field_small(impl):
+    g = load_golden("field_small.npz")
+    items, res = impl.run_tree(golden_tree(g), g["labels"], g["pixels"])
+    assert len(items) == int(g["n_items"])
+    a, b = as_float_pairs(res)
+    # fast oracle sums moment_of_inertia / conical_volume over a bbox window instead of the
+    # whole plane (different pairwise-summation tree) -> 1e-12; everything else identical
+    rtol = 0.0 if impl is port else 1e-12
+    assert_same(a, g["values"], rtol, "values")
+    assert_same(b, g["values2"], rtol, "values2")
+
+
+def test_fast_equals_port_bitwise_on_intensity():
+    g = load_golden("field_small.npz")
+    tree = {0: {"max": ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median"]},
+            1: {"add": ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median"]}}
+    _, r_port = port.run_tree(tree, g["labels"], g["pixels"])
+    _, r_fast = fast.run_tree(tree, g["labels"], g["pixels"])
+    assert_same(as_float_pairs(r_fast)[0], as_float_pairs(r_port)[0], 0.0, "intensity")
+
+
+@pytest.mark.parametrize("impl", [port, fast], ids=["port", "fast"])
+def test_tiles_list_and_table(impl):
+    g = load_golden("tiles_list.npz")
+    masks = [m for m in g["labels"]]
+    items, res = impl.run_tree(golden_tree(g), masks, g["pixels"])
+    assert [it[0][0] for it in items] == g["item_tile"].tolist()
+    assert [it[0][1] for it in items] == g["item_label"].tolist()
+    assert_same(as_float_pairs(res)[0], g["values"], 0.0 if impl is port else 1e-12, "values")
+    import json
+
+    wide = port.pivot_wide(items, [float(r) for r in res])
+    assert list(wide) == json.loads(str(g["table_columns"]))
+    assert wide["tile"] == g["table_tile"].tolist()
+    assert wide["label"] == g["table_label"].tolist()
+    got = np.stack([np.asarray(wide[c], dtype=float) for c in list(wide)[2:]], axis=1)
+    assert_same(got, g["table_values"], 0.0 if impl is port else 1e-12, "table")
+
+
+def test_volume_shapes():
+    """tests/extraction/test_volume.py:32-74 — reference outputs on numpy-drawn disks/ellipses."""
+    from oracle.make_golden import numpy_disk, numpy_ellipse
+
+    g = load_golden("volume_shapes.npz")
+    for kind, x, ecc, rot, want in zip(g["kind"], g["x"], g["ecc"], g["rot"], g["out"]):
+        if kind == "disk":
+            m = numpy_disk(int(x))
+        else:
+            y = int(np.round(np.sqrt(x**2 / (1 - ecc**2))))
+            m = numpy_ellipse(int(x), y, int(rot))
+        mn, mj = port.axes_estimate(m)
+        got = [mn, mj, port.m_volume(m), port.m_eccentricity(m), port.m_conical_volume(m)]
+        assert_same(got, want, 0.0, f"{kind} {x} {ecc} {rot}")
+        idx = fast.PlaneIndex(m.astype(np.uint16))
+        got_f = [*fast.shape_metric(idx, 1, "min_maj_approximation"), fast.shape_metric(idx, 1, "volume"),
+                 fast.shape_metric(idx, 1, "eccentricity"), fast.shape_metric(idx, 1, "conical_volume")]
+        assert_same(got_f, want, 1e-12, f"fast {kind} {x} {ecc} {rot}")
+        if kind == "disk":
+            # the reference's own analytic bound (1 %)
+            real_v = 4 * np.pi * x**3 / 3
+            assert abs(got[2] - real_v) / real_v < 0.01
+
+
+@pytest.mark.parametrize("impl", ["port", "fast"])
+def test_degenerate_shapes(impl):
+    g = load_golden("degenerate_shapes.npz")
+    lab = g["labels"]
+    idx = fast.PlaneIndex(lab)
+    for k in range(1, 10):
+        if impl == "port":
+            m = lab == k
+            mn, mj = port.axes_estimate(m)
+            got = [mn, mj, port.m_volume(m), port.m_eccentricity(m), port.m_conical_volume(m), port.m_area(m)]
+        else:
+            got = [*fast.shape_metric(idx, k, "min_maj_approximation"), fast.shape_metric(idx, k, "volume"),
+                   fast.shape_metric(idx, k, "eccentricity"), fast.shape_metric(idx, k, "conical_volume"),
+                   fast.shape_metric(idx, k, "area")]
+        assert_same(got, g["out"][k - 1], 0.0 if impl == "port" else 1e-12, f"label {k}")
+
+
+def test_background():
+    g = load_golden("background.npz")
+    assert port.t_background_median(g["labels"], g["image"]) == float(g["imBackground"])
+    assert port.t_background_max5(g["labels"], g["image"]) == float(g["background_max5"])
+
+
+def test_tile_crop():
+    g = load_golden("tile_crop.npz")
+    frame, centres, drifts = g["frame"], g["centres"], g["drifts"]
+    for tp in (0, 1):
+        for i, c in enumerate(centres):
+            want = g[f"tp{tp}_tile{i}"]
+            got = port.crop_with_padding(frame, port.tile_window(c, (16, 16), drifts, tp))
+            assert got.dtype == want.dtype
+            assert_same(got, want, 0.0, f"tp{tp} tile{i}")
+
+
+def test_invalid_reducer_raises():
+    with pytest.raises(Exception, match="invalid reducer"):
+        port.project_z(np.zeros((2, 3, 3)), port.Z_REDUCERS["mean"])
+    with pytest.raises(Exception, match="invalid reducer"):
+        port.project_z(np.zeros((2, 3, 3)), port.Z_REDUCERS["None"])

@@ -1,0 +1,166 @@
+"""ctypes binding of ``libaliby_b200.so`` (the C-ABI in ``include/aliby_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, :func:`lib` raises with the
+command that builds it.  Importing this module never touches CUDA.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libaliby_b200.so")
+
+# enums of include/aliby_b200.h
+U8, U16, U32, F32 = 0, 1, 2, 3
+RED_MAX, RED_ADD = 0, 1
+
+METRIC = {
+    "area": 0,
+    "centroid_x": 1,
+    "centroid_y": 2,
+    "spherical_volume": 3,
+    "eccentricity": 4,
+    "volume": 5,
+    "conical_volume": 6,
+    "minor_axis": 7,
+    "major_axis": 8,
+    "bbox_rmin": 9,
+    "bbox_rmax": 10,
+    "bbox_cmin": 11,
+    "bbox_cmax": 12,
+    "mean": 16,
+    "total": 17,
+    "total_squared": 18,
+    "std": 19,
+    "median": 20,
+    "max2p5pc": 21,
+    "max5px_median": 22,
+    "moment_of_inertia": 23,
+    "ratio": 24,
+    "max": 25,
+    "min": 26,
+    "imBackground": 27,
+    "background_max5": 28,
+}
+EDT_METRICS = {4, 5, 6, 7, 8}
+
+F_MEDIAN, F_TOP2P5, F_TOP5, F_WRAPSQ, F_MOI = 1, 2, 4, 8, 16
+
+EXPORTS = (
+    "abx_version",
+    "abx_last_error",
+    "abx_extract_workspace_bytes",
+    "abx_extract",
+    "abx_label_scan",
+    "abx_label_max",
+    "abx_crop_tiles",
+    "abx_event_create",
+    "abx_event_destroy",
+    "abx_event_elapsed_ms",
+)
+
+
+class Request(C.Structure):
+    _fields_ = [("channel", C.c_int32), ("reduction", C.c_int32), ("features", C.c_uint32), ("bg_features", C.c_uint32)]
+
+
+class Column(C.Structure):
+    _fields_ = [("request", C.c_int32), ("metric", C.c_int32)]
+
+
+class ObjectRec(C.Structure):
+    _fields_ = [
+        ("sum_row", C.c_uint64),
+        ("sum_col", C.c_uint64),
+        ("n", C.c_uint32),
+        ("rmin", C.c_uint32),
+        ("rmax", C.c_uint32),
+        ("cmin", C.c_uint32),
+        ("cmax", C.c_uint32),
+        ("pad_", C.c_uint32),
+    ]
+
+
+class ExtractArgs(C.Structure):
+    _fields_ = [
+        ("labels", C.c_void_p),
+        ("label_dtype", C.c_int32),
+        ("n_planes", C.c_int32),
+        ("H", C.c_int32),
+        ("W", C.c_int32),
+        ("label_plane_stride", C.c_int64),
+        ("label_row_stride", C.c_int64),
+        ("plane_tile", C.c_void_p),
+        ("plane_base", C.c_void_p),
+        ("n_objects", C.c_int32),
+        ("with_background", C.c_int32),
+        ("pixels", C.c_void_p),
+        ("pixel_dtype", C.c_int32),
+        ("n_tiles", C.c_int32),
+        ("C", C.c_int32),
+        ("Z", C.c_int32),
+        ("tile_offset", C.c_void_p),
+        ("chan_stride", C.c_int64),
+        ("z_stride", C.c_int64),
+        ("row_stride", C.c_int64),
+        ("requests", C.c_void_p),
+        ("n_requests", C.c_int32),
+        ("columns", C.c_void_p),
+        ("n_columns", C.c_int32),
+        ("need_edt", C.c_int32),
+        ("request_feature_union", C.c_int32),
+        ("table", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+        ("stream", C.c_void_p),
+        ("stage_events", C.POINTER(C.c_void_p)),
+    ]
+
+
+class NativeError(RuntimeError):
+    """Non-zero status from the C-ABI."""
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library once; fail loudly if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. aliby_b200 has no CPU fallback: build the CUDA library with "
+            "`python -m aliby_b200.build` (needs nvcc, targets sm_100a)."
+        )
+    handle = C.CDLL(LIB_PATH)
+    handle.abx_version.restype = C.c_int
+    handle.abx_last_error.restype = C.c_char_p
+    handle.abx_extract_workspace_bytes.argtypes = [C.POINTER(ExtractArgs), C.POINTER(C.c_size_t)]
+    handle.abx_extract.argtypes = [C.POINTER(ExtractArgs)]
+    handle.abx_label_scan.argtypes = [C.POINTER(ExtractArgs), C.c_void_p]
+    handle.abx_label_max.argtypes = [
+        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+    ]
+    handle.abx_crop_tiles.argtypes = [
+        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+    ]
+    handle.abx_event_create.argtypes = [C.POINTER(C.c_void_p)]
+    handle.abx_event_destroy.argtypes = [C.c_void_p]
+    handle.abx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    for name in EXPORTS:
+        getattr(handle, name)  # AttributeError if the header and the library drifted apart
+    _lib = handle
+    return handle
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().abx_last_error().decode("utf-8", "replace")
+        if status == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise NativeError(f"{what} failed with status {status}: {msg}")

@@ -1,0 +1,194 @@
+// C-ABI entry points of libaliby_b200 (see include/aliby_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+thread_local char g_error[512] = "";
+
+constexpr size_t kAlign = 256;
+size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+}  // namespace
+
+int abx_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int abx_check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return ABX_OK;
+  return abx_set_error(ABX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int abx_validate(const abx_extract_args* a) {
+  if (!a) return abx_set_error(ABX_ERR_INVALID, "args is NULL");
+  if (a->label_dtype != ABX_U16)
+    return abx_set_error(ABX_ERR_UNSUPPORTED, "label dtype %d has no kernel (uint16 only; ids < 65536)", a->label_dtype);
+  if (a->n_planes < 0 || a->n_objects < 0 || a->n_requests < 0 || a->n_columns < 0)
+    return abx_set_error(ABX_ERR_INVALID, "negative count");
+  if (a->n_planes > 0 && (a->H <= 0 || a->W <= 0 || a->H > 32767 || a->W > 32767))
+    return abx_set_error(ABX_ERR_INVALID, "plane size %d x %d outside [1, 32767]", a->H, a->W);
+  if (a->n_requests > 0) {
+    if (a->pixel_dtype != ABX_U8 && a->pixel_dtype != ABX_U16)
+      return abx_set_error(ABX_ERR_UNSUPPORTED, "pixel dtype %d has no kernel (uint8/uint16); there is no CPU fallback",
+                           a->pixel_dtype);
+    if (a->Z < 1 || a->C < 1) return abx_set_error(ABX_ERR_INVALID, "C and Z must be >= 1");
+    if (a->pixel_dtype == ABX_U16 && a->Z > 65536) return abx_set_error(ABX_ERR_INVALID, "Z too large for 32-bit sums");
+  }
+  return ABX_OK;
+}
+
+int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
+  size_t off = 0;
+  unsigned char* b = static_cast<unsigned char*>(base);
+  const size_t n_rec = (size_t)a->n_objects + (size_t)a->n_planes;
+  ws->recs = reinterpret_cast<abx_object_rec*>(b + off);
+  off = align_up(off + n_rec * sizeof(abx_object_rec));
+  ws->chan = reinterpret_cast<ChanStats*>(b + off);
+  off = align_up(off + n_rec * (size_t)a->n_requests * sizeof(ChanStats));
+  ws->shape = reinterpret_cast<ShapeStats*>(b + off);
+  off = align_up(off + (a->need_edt ? (size_t)a->n_objects * sizeof(ShapeStats) : 0));
+  ws->err = reinterpret_cast<u32*>(b + off);
+  off = align_up(off + sizeof(u32));
+  ws->edt_scratch = b + off;
+  ws->edt_scratch_per_cta = 0;
+  if (a->need_edt) {
+    const size_t plane_px = (size_t)(a->H + 2) * (size_t)(a->W + 2);
+    if (plane_px > (size_t)kEdtSmemWindow) {
+      ws->edt_scratch_per_cta = align_up(plane_px * kEdtBytesPerPixel);
+      off = align_up(off + ws->edt_scratch_per_cta * kEdtLargeCtas);
+    }
+  }
+  ws->total = off;
+  return ABX_OK;
+}
+
+extern "C" int abx_version(void) { return ABX_VERSION; }
+
+extern "C" const char* abx_last_error(void) { return g_error; }
+
+extern "C" int abx_extract_workspace_bytes(const abx_extract_args* args, size_t* bytes) {
+  if (!bytes) return abx_set_error(ABX_ERR_INVALID, "bytes is NULL");
+  int rc = abx_validate(args);
+  if (rc) return rc;
+  Workspace ws;
+  abx_plan_workspace(args, nullptr, &ws);
+  *bytes = ws.total;
+  return ABX_OK;
+}
+
+static int check_pointers(const abx_extract_args* a, const Workspace& ws) {
+  if (a->n_planes > 0 && (!a->labels || !a->plane_tile || !a->plane_base))
+    return abx_set_error(ABX_ERR_INVALID, "labels / plane_tile / plane_base is NULL");
+  if (a->n_requests > 0 && (!a->pixels || !a->tile_offset || !a->requests))
+    return abx_set_error(ABX_ERR_INVALID, "pixels / tile_offset / requests is NULL");
+  if (!a->workspace || a->workspace_bytes < ws.total)
+    return abx_set_error(ABX_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", a->workspace_bytes, ws.total);
+  if ((reinterpret_cast<uintptr_t>(a->workspace) & 15u) != 0)
+    return abx_set_error(ABX_ERR_INVALID, "workspace must be 16-byte aligned");
+  return ABX_OK;
+}
+
+extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* records) {
+  int rc = abx_validate(args);
+  if (rc) return rc;
+  if (!records) return abx_set_error(ABX_ERR_INVALID, "records is NULL");
+  if (!args->workspace || args->workspace_bytes < sizeof(u32))
+    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 4-byte workspace for its error flag");
+  return launch_label_scan(args, records, static_cast<u32*>(args->workspace), static_cast<cudaStream_t>(args->stream));
+}
+
+extern "C" int abx_extract(const abx_extract_args* args) {
+  int rc = abx_validate(args);
+  if (rc) return rc;
+  Workspace ws;
+  abx_plan_workspace(args, args->workspace, &ws);
+  rc = check_pointers(args, ws);
+  if (rc) return rc;
+  if (args->n_objects > 0 && args->n_columns > 0 && (!args->table || !args->columns))
+    return abx_set_error(ABX_ERR_INVALID, "table / columns is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(args->stream);
+  void* const* ev = args->stage_events;
+  auto mark = [&](int i) { if (ev && ev[i]) cudaEventRecord(static_cast<cudaEvent_t>(ev[i]), st); };
+  mark(0);
+  if ((rc = launch_label_scan(args, ws.recs, ws.err, st))) return rc;
+  mark(1);
+  if ((rc = launch_object_stats(args, ws, st))) return rc;
+  mark(2);
+  if ((rc = launch_shape_edt(args, ws, st))) return rc;
+  mark(3);
+  if ((rc = launch_finalize(args, ws, st))) return rc;
+  mark(4);
+  return ABX_OK;
+}
+
+extern "C" int abx_event_create(void** event) {
+  if (!event) return abx_set_error(ABX_ERR_INVALID, "event is NULL");
+  cudaEvent_t e;
+  cudaError_t rc = cudaEventCreate(&e);
+  if (rc != cudaSuccess) return abx_check_cuda(rc, "cudaEventCreate");
+  *event = e;
+  return ABX_OK;
+}
+
+extern "C" int abx_event_destroy(void* event) {
+  return abx_check_cuda(cudaEventDestroy(static_cast<cudaEvent_t>(event)), "cudaEventDestroy");
+}
+
+extern "C" int abx_event_elapsed_ms(void* start, void* end, float* ms) {
+  if (!ms) return abx_set_error(ABX_ERR_INVALID, "ms is NULL");
+  return abx_check_cuda(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(end)),
+                        "cudaEventElapsedTime");
+}
+
+// ---- materialised tile crop -------------------------------------------------------------------
+namespace {
+template <typename T>
+__global__ void crop_tiles_kernel(const T* __restrict__ frame, int C, int Z, i64 chan_stride, i64 z_stride,
+                                  i64 row_stride, const int32_t* __restrict__ origin, int n_tiles, int h, int w,
+                                  T* __restrict__ out) {
+  // grid.y enumerates (tile, c, z, row); threads walk the row
+  const i64 line = blockIdx.x;
+  const int r = (int)(line % h);
+  i64 t = line / h;
+  const int z = (int)(t % Z); t /= Z;
+  const int c = (int)(t % C); t /= C;
+  const int tile = (int)t;
+  const T* src = frame + (i64)c * chan_stride + (i64)z * z_stride + (i64)(origin[2 * tile] + r) * row_stride +
+                 origin[2 * tile + 1];
+  T* dst = out + line * w;
+  for (int x = threadIdx.x; x < w; x += blockDim.x) dst[x] = __ldg(src + x);
+}
+}  // namespace
+
+extern "C" int abx_crop_tiles(const void* frame, int32_t dtype, int32_t C, int32_t Z, int64_t chan_stride,
+                              int64_t z_stride, int64_t row_stride, const int32_t* tile_origin, int32_t n_tiles,
+                              int32_t h, int32_t w, void* out, void* stream) {
+  if (!frame || !tile_origin || !out || C < 1 || Z < 1 || n_tiles < 0 || h < 1 || w < 1)
+    return abx_set_error(ABX_ERR_INVALID, "abx_crop_tiles: bad arguments");
+  const i64 lines = (i64)n_tiles * C * Z * h;
+  if (lines == 0) return ABX_OK;
+  if (lines > 2147483647LL) return abx_set_error(ABX_ERR_INVALID, "abx_crop_tiles: too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = w >= 128 ? 128 : (w >= 64 ? 64 : 32);
+  if (dtype == ABX_U16)
+    crop_tiles_kernel<uint16_t><<<(unsigned)lines, threads, 0, st>>>(static_cast<const uint16_t*>(frame), C, Z,
+                                                                     chan_stride, z_stride, row_stride, tile_origin,
+                                                                     n_tiles, h, w, static_cast<uint16_t*>(out));
+  else if (dtype == ABX_U8)
+    crop_tiles_kernel<uint8_t><<<(unsigned)lines, threads, 0, st>>>(static_cast<const uint8_t*>(frame), C, Z,
+                                                                    chan_stride, z_stride, row_stride, tile_origin,
+                                                                    n_tiles, h, w, static_cast<uint8_t*>(out));
+  else if (dtype == ABX_F32)
+    crop_tiles_kernel<float><<<(unsigned)lines, threads, 0, st>>>(static_cast<const float*>(frame), C, Z, chan_stride,
+                                                                  z_stride, row_stride, tile_origin, n_tiles, h, w,
+                                                                  static_cast<float*>(out));
+  else
+    return abx_set_error(ABX_ERR_UNSUPPORTED, "abx_crop_tiles: dtype %d has no kernel", dtype);
+  return abx_check_cuda(cudaGetLastError(), "crop_tiles");
+}

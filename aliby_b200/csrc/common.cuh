@@ -1,0 +1,68 @@
+// Internal declarations shared by the kernels of libaliby_b200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aliby_b200.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef long long i64;
+
+// Raw per-(object, request) statistics written by object_stats, read by finalize.
+struct ChanStats {
+  u64 sum;         // sum of x
+  u64 sumsq;       // sum of x*x (mod 2^64)
+  u64 wrapsq;      // sum of (x*x mod 2^bits(pixel dtype)) — NumPy's v**2 in the image dtype
+  u64 m10, m01;    // sum x*c', sum x*r' with (r', c') relative to the bbox origin
+  u64 m20, m02;    // sum x*c'^2, sum x*r'^2
+  u64 top2p5_sum;  // sum of the ceil(0.025 n) largest values
+  u64 top5_sum;    // sum of the min(5, n) largest values
+  u32 vmin, vmax;
+  u32 med_lo, med_hi;  // the two middle order statistics (equal for odd n)
+};
+
+// Raw per-object output of the three chained EDTs (cell.py:207-229).
+struct ShapeStats {
+  double sum_nn;   // sum of sqrt(nn^2) over the object   (conical_volume / 4)
+  double sum_top;  // sum of the plateau EDT over the cone top
+  u32 max_nn2;     // max squared distance to the background
+  u32 max_dn2;     // max squared distance to the cone top
+};
+
+struct Workspace {
+  abx_object_rec* recs;  // [n_objects + n_planes]
+  ChanStats* chan;       // [(n_objects + n_planes) * n_requests]
+  ShapeStats* shape;     // [n_objects]
+  unsigned char* edt_scratch;
+  size_t edt_scratch_per_cta;
+  u32* err;
+  size_t total;
+};
+
+int abx_set_error(int code, const char* fmt, ...);
+int abx_check_cuda(cudaError_t e, const char* what);
+int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws);
+int abx_validate(const abx_extract_args* a);
+
+int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, cudaStream_t st);
+int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+
+constexpr int kEdtLargeCtas = 8;           // CTAs that own a whole-plane EDT scratch slot
+constexpr int kEdtSmemWindow = 96 * 96;    // padded window (pixels) that is handled in shared memory
+constexpr int kEdtBytesPerPixel = 8;       // mask(1) + flags(1) + g(2) + d2(4)
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+
+// plane of an object row: largest p with plane_base[p] <= obj
+__device__ __forceinline__ int find_plane(const int32_t* __restrict__ plane_base, int n_planes, int obj) {
+  int lo = 0, hi = n_planes;  // invariant: base[lo] <= obj < base[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (plane_base[mid] <= obj) lo = mid; else hi = mid;
+  }
+  return lo;
+}

@@ -1,0 +1,125 @@
+// Finalisation: raw per-object records -> dense fp64 [objects x columns] table.
+//
+// One thread per table cell.  The arithmetic follows the reference functions to the
+// operation (src/extraction/core/functions/cell.py, trap.py) so that every value that
+// NumPy derives from exact integer sums is reproduced bit-for-bit:
+//   mean = f64(sum) / f64(n)                     cell.py:43-53
+//   median = (lo + hi) / 2                       cell.py:86-96 (np.median on integers)
+//   max2p5pc = f64(top sum) / f64(k)             cell.py:99-116
+//   max5px_median = (top5 / 5) / median          cell.py:119-144 (NaN for n <= 5 or median 0)
+//   centroid = f64(sum(col+1)) / f64(n)          cell.py:282-303
+//   std from exact 128-bit integer variance      cell.py:147-157 (<= 1e-12 from NumPy's two-pass)
+// The dense table replaces the Python long->wide pivot of extract.py:574-598.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double u128_to_double(unsigned __int128 v) {
+  return (double)(u64)(v >> 64) * 18446744073709551616.0 + (double)(u64)v;
+}
+
+__device__ double moment_of_inertia(const ChanStats& c) {
+  // cell.py:232-265 with coordinates relative to the bbox origin (central moments are
+  // translation invariant): mu20 = m20 - m10^2 / m00, eta = mu / m00^2
+  if (c.sum == 0) return nan("");
+  const unsigned __int128 m00 = c.sum;
+  const unsigned __int128 n20 = m00 * c.m20 - (unsigned __int128)c.m10 * c.m10;
+  const unsigned __int128 n02 = m00 * c.m02 - (unsigned __int128)c.m01 * c.m01;
+  const double d = (double)c.sum;
+  const double d3 = d * d * d;
+  return u128_to_double(n20) / d3 + u128_to_double(n02) / d3;
+}
+
+__global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __restrict__ chan,
+                                const ShapeStats* __restrict__ shape, const int32_t* __restrict__ plane_base,
+                                int n_planes, int n_objects, const abx_request* __restrict__ requests,
+                                int n_requests, const abx_column* __restrict__ columns, int n_columns,
+                                double* __restrict__ table) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (i64)n_objects * n_columns) return;
+  const int obj = (int)(idx / n_columns);
+  const int col = (int)(idx - (i64)obj * n_columns);
+  const abx_column cd = columns[col];
+  const abx_object_rec r = recs[obj];
+  const double n = (double)r.n;
+  const double kNaN = nan("");
+  double v = kNaN;
+  if (cd.metric < 16) {
+    double minor = 0, major = 0;
+    if (cd.metric == ABX_M_ECCENTRICITY || cd.metric == ABX_M_VOLUME || cd.metric == ABX_M_MINOR_AXIS ||
+        cd.metric == ABX_M_MAJOR_AXIS) {
+      const ShapeStats s = shape[obj];
+      minor = rint(sqrt((double)s.max_nn2));                       // np.round: half to even
+      major = rint(sqrt((double)s.max_dn2) + s.sum_top / 2.0);
+    }
+    switch (cd.metric) {
+      case ABX_M_AREA: v = n; break;
+      case ABX_M_CENTROID_X: v = (double)r.sum_col / n; break;  // 0/0 -> NaN like NumPy
+      case ABX_M_CENTROID_Y: v = (double)r.sum_row / n; break;
+      case ABX_M_SPHERICAL_VOLUME: {
+        const double rad = sqrt(n / 3.141592653589793);
+        v = (4.0 * 3.141592653589793 * (rad * rad * rad)) / 3.0;
+      } break;
+      case ABX_M_ECCENTRICITY: v = sqrt(major * major - minor * minor) / major; break;
+      case ABX_M_VOLUME: v = (4.0 * 3.141592653589793 * (minor * minor) * major) / 3.0; break;
+      case ABX_M_CONICAL_VOLUME: v = 4.0 * shape[obj].sum_nn; break;
+      case ABX_M_MINOR_AXIS: v = minor; break;
+      case ABX_M_MAJOR_AXIS: v = major; break;
+      case ABX_M_BBOX_RMIN: v = r.n ? (double)r.rmin : kNaN; break;
+      case ABX_M_BBOX_RMAX: v = r.n ? (double)r.rmax : kNaN; break;
+      case ABX_M_BBOX_CMIN: v = r.n ? (double)r.cmin : kNaN; break;
+      case ABX_M_BBOX_CMAX: v = r.n ? (double)r.cmax : kNaN; break;
+      default: break;
+    }
+  } else if (cd.metric == ABX_M_IMBACKGROUND || cd.metric == ABX_M_BACKGROUND_MAX5) {
+    const int p = find_plane(plane_base, n_planes, obj);
+    const u32 nb = recs[n_objects + p].n;
+    const ChanStats c = chan[(i64)(n_objects + p) * n_requests + cd.request];
+    if (nb) {
+      if (cd.metric == ABX_M_IMBACKGROUND) v = ((double)c.med_lo + (double)c.med_hi) / 2.0;
+      else v = (double)c.top5_sum / (double)(nb < 5u ? nb : 5u);  // np.mean(np.sort(bg)[-5:])
+    }
+  } else {
+    const ChanStats c = chan[(i64)obj * n_requests + cd.request];
+    const bool add = requests[cd.request].reduction == ABX_RED_ADD;
+    switch (cd.metric) {
+      case ABX_M_MEAN: v = r.n ? (double)c.sum / n : kNaN; break;
+      case ABX_M_TOTAL: v = (double)c.sum; break;
+      case ABX_M_TOTAL_SQUARED: v = (double)(add ? c.sumsq : c.wrapsq); break;
+      case ABX_M_STD:
+        if (r.n) {
+          const unsigned __int128 num = (unsigned __int128)r.n * c.sumsq - (unsigned __int128)c.sum * c.sum;
+          v = sqrt(u128_to_double(num) / (n * n));
+        }
+        break;
+      case ABX_M_MEDIAN: if (r.n) v = ((double)c.med_lo + (double)c.med_hi) / 2.0; break;
+      case ABX_M_MAX2P5PC:
+        if (r.n) v = (double)c.top2p5_sum / (double)(u32)ceil(n * 0.025);
+        break;
+      case ABX_M_MAX5PX_MEDIAN:
+        if (r.n > 5u) {
+          const double med = ((double)c.med_lo + (double)c.med_hi) / 2.0;
+          if (med != 0.0) v = ((double)c.top5_sum / 5.0) / med;
+        }
+        break;
+      case ABX_M_MOMENT_OF_INERTIA: if (r.n) v = moment_of_inertia(c); break;
+      case ABX_M_MAX: if (r.n) v = (double)c.vmax; break;
+      case ABX_M_MIN: if (r.n) v = (double)c.vmin; break;
+      case ABX_M_RATIO: default: break;  // cell.py:268-279: NaN for any 2-D image
+    }
+  }
+  table[idx] = v;
+}
+
+}  // namespace
+
+int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+  const i64 cells = (i64)a->n_objects * a->n_columns;
+  if (cells == 0) return ABX_OK;
+  const int threads = 256;
+  const i64 blocks = (cells + threads - 1) / threads;
+  finalize_kernel<<<(unsigned)blocks, threads, 0, st>>>(ws.recs, ws.chan, ws.shape, a->plane_base, a->n_planes,
+                                                       a->n_objects, a->requests, a->n_requests, a->columns,
+                                                       a->n_columns, a->table);
+  return abx_check_cuda(cudaGetLastError(), "finalize");
+}

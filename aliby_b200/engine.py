@@ -1,0 +1,279 @@
+"""Host side of the extraction hot path: tree -> plan, plan + device buffers -> dense table.
+
+The plan compiler mirrors how the reference resolves a tree
+(``src/extraction/extract.py:33-74`` flatten/kv, ``extract.py:147-153`` registry lookups,
+``distributors.py:19-24`` reducer check) and reproduces its error behaviour; the engine
+is a thin wrapper over the C-ABI (``abx_extract``).  PyTorch is used for device memory
+and streams only.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from functools import reduce
+from itertools import product
+
+import numpy as np
+
+from . import _native as nat
+
+# REDUCTION_FUNS of loaders.py:110-127: which names exist, which are ufuncs
+REDUCERS = {"max": "ufunc", "add": "ufunc", "div": "ufunc", "mean": "<function mean>", "median": "<function median>", "None": "None"}
+
+# cell.py functions that take the mask only (wrapped by ignore_pixels, loaders.py:56-66,170-171)
+SHAPE_METRICS = {
+    "area": ("area",),
+    "centroid": ("centroid_x", "centroid_y"),
+    "centroid_x": ("centroid_x",),
+    "centroid_y": ("centroid_y",),
+    "conical_volume": ("conical_volume",),
+    "eccentricity": ("eccentricity",),
+    "min_maj_approximation": ("minor_axis", "major_axis"),
+    "spherical_volume": ("spherical_volume",),
+    "volume": ("volume",),
+    # extensions (not in cell.py; cp_measure territory in the reference)
+    "bbox_rmin": ("bbox_rmin",),
+    "bbox_rmax": ("bbox_rmax",),
+    "bbox_cmin": ("bbox_cmin",),
+    "bbox_cmax": ("bbox_cmax",),
+}
+# cell.py functions of (mask, pixels) + extensions max/min + the per-tile background pair of trap.py
+INTENSITY_METRICS = {
+    "mean": 0,
+    "total": nat.F_WRAPSQ * 0,
+    "total_squared": nat.F_WRAPSQ,
+    "std": 0,
+    "median": nat.F_MEDIAN,
+    "max2p5pc": nat.F_TOP2P5,
+    "max5px_median": nat.F_TOP5 | nat.F_MEDIAN,
+    "moment_of_inertia": nat.F_MOI,
+    "ratio": 0,
+    "max": 0,
+    "min": 0,
+}
+BACKGROUND_METRICS = {"imBackground": nat.F_MEDIAN, "background_max5": nat.F_TOP5}
+
+CELL_FUN_NAMES = tuple(
+    sorted(
+        [
+            "area", "centroid", "centroid_x", "centroid_y", "conical_volume", "eccentricity", "max2p5pc",
+            "max5px_median", "mean", "median", "min_maj_approximation", "moment_of_inertia", "ratio",
+            "spherical_volume", "std", "total", "total_squared", "volume",
+        ]
+    )
+)
+EXTENSION_NAMES = ("bbox_cmax", "bbox_cmin", "bbox_rmax", "bbox_rmin", "max", "min")
+TRAP_FUN_NAMES = ("background_max5", "imBackground")
+
+
+def flatten(d: dict, pref=()) -> dict:
+    """Nested dict -> {path tuple: leaf}, insertion order kept (extract.py:33-57)."""
+    return reduce(
+        lambda acc, kv_: ({**acc, **flatten(kv_[1], (*pref, kv_[0]))} if isinstance(kv_[1], dict) else {**acc, (*pref, kv_[0]): kv_[1]}),
+        d.items(),
+        {},
+    )
+
+
+def kv(flat: dict) -> list:
+    """{(ch, red): [metrics]} -> [(ch, red, metric)] (extract.py:60-74)."""
+    return [(*k1, v1) for k, v in flat.items() for k1, v1 in product((k,), v)]
+
+
+@dataclass
+class Plan:
+    """A compiled extraction tree."""
+
+    instructions: list
+    requests: list = field(default_factory=list)  # [(channel, red_enum, features, bg_features)]
+    columns: list = field(default_factory=list)  # [(request_idx, metric_enum)]
+    inst_cols: list = field(default_factory=list)  # per instruction: tuple of dense column indices
+    need_edt: bool = False
+    with_background: bool = False
+    error: Exception | None = None  # raised only when there is at least one object, like the reference
+    _dev: dict = field(default_factory=dict)
+
+    @property
+    def n_columns(self) -> int:
+        return len(self.columns)
+
+    @property
+    def max_channel(self) -> int:
+        return max((r[0] for r in self.requests), default=-1)
+
+    def device_arrays(self, device):
+        """(requests, columns) as device tensors, uploaded once per device."""
+        import torch
+
+        key = str(device)
+        if key not in self._dev:
+            req = np.zeros((max(1, len(self.requests)), 4), dtype=np.int32)
+            for i, r in enumerate(self.requests):
+                req[i] = r
+            col = np.zeros((max(1, len(self.columns)), 2), dtype=np.int32)
+            for i, c in enumerate(self.columns):
+                col[i] = c
+            self._dev[key] = (torch.from_numpy(req).to(device), torch.from_numpy(col).to(device))
+        return self._dev[key]
+
+
+def compile_tree(tree: dict) -> Plan:
+    return compile_instructions(kv(flatten(tree)))
+
+
+def compile_instructions(instructions: list) -> Plan:
+    plan = Plan(instructions=list(instructions))
+    req_index: dict = {}
+    col_index: dict = {}
+
+    def request(ch, red):
+        key = (int(ch), red)
+        if key not in req_index:
+            req_index[key] = len(plan.requests)
+            plan.requests.append([int(ch), nat.RED_MAX if red == "max" else nat.RED_ADD, 0, 0])
+        return req_index[key]
+
+    def column(req, metric_name):
+        key = (req, nat.METRIC[metric_name])
+        if key not in col_index:
+            col_index[key] = len(plan.columns)
+            plan.columns.append(key)
+            if key[1] in nat.EDT_METRICS:
+                plan.need_edt = True
+        return col_index[key]
+
+    for inst in instructions:
+        try:
+            ch, red, metric = inst
+            if red not in REDUCERS:
+                raise KeyError(red)  # REDUCTION_FUNS[red_z], extract.py:151
+            known = metric in SHAPE_METRICS or metric in INTENSITY_METRICS or metric in BACKGROUND_METRICS
+            if not known:
+                raise KeyError(metric)  # CELL_FUNS[metric], extract.py:152
+            has_pixels = not (isinstance(ch, str) and ch == "None")
+            if has_pixels:
+                if REDUCERS[red] != "ufunc":
+                    raise Exception(f"{REDUCERS[red]} is an invalid reducer.")  # distributors.py:24
+                if red == "div":
+                    raise NotImplementedError(
+                        "Z reduction 'div' (np.divide.reduce) has no CUDA kernel in aliby_b200 and there is no CPU fallback"
+                    )
+            if metric in SHAPE_METRICS:
+                cols = tuple(column(-1, m) for m in SHAPE_METRICS[metric])
+            else:
+                if not has_pixels:
+                    raise TypeError(f"metric '{metric}' needs pixels but the channel is 'None'")
+                r = request(ch, red)
+                if metric in BACKGROUND_METRICS:
+                    plan.requests[r][3] |= BACKGROUND_METRICS[metric]
+                    plan.with_background = True
+                else:
+                    plan.requests[r][2] |= INTENSITY_METRICS[metric]
+                cols = (column(r, metric),)
+            plan.inst_cols.append(cols)
+        except Exception as e:  # noqa: BLE001 - deferred, see Plan.error
+            if plan.error is None:
+                plan.error = e
+            plan.inst_cols.append(())
+    return plan
+
+
+_DTYPES = {"uint8": nat.U8, "uint16": nat.U16}
+_workspaces: dict = {}
+
+
+def _workspace(device, nbytes: int):
+    import torch
+
+    key = str(device)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def pixel_dtype_enum(torch_dtype) -> int:
+    name = str(torch_dtype).replace("torch.", "")
+    if name not in _DTYPES:
+        raise NotImplementedError(
+            f"pixel dtype {name} has no CUDA kernel in aliby_b200 (uint8/uint16 only) and there is no CPU fallback"
+        )
+    return _DTYPES[name]
+
+
+def run_planes(
+    plan: Plan,
+    labels,  # torch cuda uint16 (P, H, W), last dim contiguous
+    plane_tile: np.ndarray,
+    n_labels: np.ndarray,
+    pixels,  # torch cuda tensor holding the pixel data (any shape; addressed through offsets/strides)
+    tile_offset: np.ndarray,
+    chan_stride: int,
+    z_stride: int,
+    row_stride: int,
+    n_channels: int,
+    n_z: int,
+    out=None,
+    stage_events=None,
+):
+    """Launch the hot path on the current stream; returns the dense fp64 table (device)."""
+    import torch
+
+    if plan.error is not None and int(np.sum(n_labels)) > 0:
+        raise plan.error
+    lib = nat.lib()
+    device = labels.device
+    P, H, W = labels.shape
+    assert labels.dtype == torch.uint16 and labels.stride(2) == 1
+    n_labels = np.asarray(n_labels, dtype=np.int64)
+    n_objects = int(n_labels.sum())
+    n_cols = plan.n_columns
+    if out is None:
+        out = torch.empty((n_objects, n_cols), dtype=torch.float64, device=device)
+    if n_objects == 0 or n_cols == 0:
+        return out
+    if plan.requests and plan.max_channel >= n_channels:
+        raise IndexError(f"index {plan.max_channel} is out of bounds for axis 1 with size {n_channels}")
+    base = np.zeros(P + 1, dtype=np.int32)
+    np.cumsum(n_labels, out=base[1:])
+    meta = torch.from_numpy(np.concatenate([np.asarray(plane_tile, dtype=np.int32), base])).to(device)
+    offs = torch.from_numpy(np.ascontiguousarray(tile_offset, dtype=np.int64)).to(device)
+    req_t, col_t = plan.device_arrays(device)
+
+    a = nat.ExtractArgs()
+    a.labels = labels.data_ptr()
+    a.label_dtype = nat.U16
+    a.n_planes, a.H, a.W = P, H, W
+    a.label_plane_stride, a.label_row_stride = labels.stride(0), labels.stride(1)
+    a.plane_tile = meta.data_ptr()
+    a.plane_base = meta.data_ptr() + 4 * P
+    a.n_objects = n_objects
+    a.with_background = int(plan.with_background)
+    a.pixels = pixels.data_ptr() if plan.requests else None
+    a.pixel_dtype = pixel_dtype_enum(pixels.dtype) if plan.requests else nat.U16
+    a.n_tiles = len(tile_offset)
+    a.C, a.Z = max(1, n_channels), max(1, n_z)
+    a.tile_offset = offs.data_ptr()
+    a.chan_stride, a.z_stride, a.row_stride = int(chan_stride), int(z_stride), int(row_stride)
+    a.requests = req_t.data_ptr()
+    a.n_requests = len(plan.requests)
+    a.columns = col_t.data_ptr()
+    a.n_columns = n_cols
+    a.need_edt = int(plan.need_edt)
+    a.request_feature_union = 0
+    a.table = out.data_ptr()
+    a.stream = torch.cuda.current_stream(device).cuda_stream
+    if stage_events is not None:  # 5 handles from abx_event_create (bench.py: live per-stage timing)
+        ev = (C.c_void_p * 5)(*stage_events)
+        a.stage_events = C.cast(ev, C.POINTER(C.c_void_p))
+    need = C.c_size_t(0)
+    nat.check(lib.abx_extract_workspace_bytes(C.byref(a), C.byref(need)), "abx_extract_workspace_bytes")
+    ws = _workspace(device, need.value)
+    a.workspace = ws.data_ptr()
+    a.workspace_bytes = ws.numel()
+    with torch.cuda.device(device):
+        nat.check(lib.abx_extract(C.byref(a)), "abx_extract")
+    # meta/offs must outlive the launch: the caching allocator only reuses them stream-ordered
+    return out

@@ -1,0 +1,396 @@
+"""Drop-in for ``src/extraction/extract.py`` of the reference, backed by the CUDA hot path.
+
+Same names, signatures, return structures and error behaviour as the reference's
+functional extraction API, so that ``pipeline["steps"]["extract_*"]`` can be served by
+this module unchanged (see ``aliby_b200.pipe.init_step``):
+
+* :func:`process_tree_masks`, :func:`process_tree_masks_overlap`  (extract.py:240-301, 456-517)
+* :func:`extract_tree`                                            (extract.py:304-375)
+* :func:`format_extraction`                                       (extract.py:520-599)
+* :func:`flatten`, :func:`kv`                                     (extract.py:33-74)
+
+Differences, all deliberate: results are Python ``float`` (the reference returns
+``np.int64``/``np.uint64`` for ``area``/``total`` which its own ``format_extraction``
+rejects); ``ncores``/``progress_bar`` are accepted and ignored (one launch does
+the whole |objects| x |instructions| product); cp_measure features have no kernel and
+raise ``KeyError`` naming the metric.
+"""
+
+from __future__ import annotations
+
+from itertools import product
+
+import numpy as np
+
+from . import engine
+from .engine import flatten, kv  # noqa: F401  (re-exported, same names as the reference)
+from .functions.loaders import load_funs, load_redfuns
+
+CELL_FUNS, TRAP_FUNS, ALL_FUNS = load_funs()
+REDUCTION_FUNS = load_redfuns()
+
+
+class ExtractionResults(list):
+    """``list`` of per-(object, instruction) results that also carries the dense table."""
+
+    dense: np.ndarray | None = None  # (n_objects, n_dense_columns) float64, host
+    plan: engine.Plan | None = None
+    objects: np.ndarray | None = None  # (n_objects, 2|3) int64 object ids
+    items: tuple | None = None
+
+
+_last_items = {"items": None, "objects": None, "plan": None}
+
+
+def _as_mask_list(masks):
+    if not isinstance(masks, list):  # "Hacky fix when tile level is not provided" (extract.py:271-272)
+        masks = [masks]
+    return masks
+
+
+def _to_device_labels(planes: list[np.ndarray], device):
+    """Stack equally-shaped 2-D label planes into one uint16 device tensor."""
+    import torch
+
+    stack = np.stack(planes)
+    if stack.dtype != np.uint16:
+        if stack.size and (stack.min() < 0 or stack.max() > 65535):
+            raise OverflowError("label ids must fit uint16 (segment/dispatch.py:14-19 enforces the same)")
+        stack = stack.astype(np.uint16)
+    return torch.from_numpy(np.ascontiguousarray(stack)).to(device, non_blocking=True)
+
+
+def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
+    """planes: list of (Y, X) arrays; pixels: (tiles, C, Z, Y, X) ndarray / tensor / TileView."""
+    import torch
+
+    from .tile import TileView
+
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    n_objects = int(np.sum(n_labels))
+    if n_objects == 0:
+        return np.zeros((0, plan.n_columns))
+    if plan.error is not None:
+        raise plan.error
+    labels_dev = _to_device_labels(planes, device)
+    if isinstance(pixels, TileView):
+        px_dev, offs, cs, zs, rs, C_, Z_ = pixels.addressing(device)
+    else:
+        if isinstance(pixels, np.ndarray):
+            if plan.requests:
+                if pixels.dtype not in (np.uint8, np.uint16):
+                    raise NotImplementedError(
+                        f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200 (uint8/uint16 only) "
+                        "and there is no CPU fallback"
+                    )
+                px_dev = torch.from_numpy(np.ascontiguousarray(pixels)).to(device, non_blocking=True)
+            else:
+                px_dev = torch.empty(0, dtype=torch.uint16, device=device)
+        else:
+            px_dev = pixels.to(device).contiguous()
+        T, C_, Z_, Y, X = pixels.shape
+        offs = np.arange(T, dtype=np.int64) * (C_ * Z_ * Y * X)
+        cs, zs, rs = Z_ * Y * X, Y * X, X
+    table = engine.run_planes(plan, labels_dev, plane_tile, n_labels, px_dev, offs, cs, zs, rs, C_, Z_)
+    return table.cpu().numpy()
+
+
+class ExtractionTable:
+    """Dense result of :func:`extract_table`: one row per object, one column per feature."""
+
+    def __init__(self, objects: np.ndarray, names: list[str], values: np.ndarray):
+        self.objects = objects  # (n, 2) int64: tile, label
+        self.names = names  # reference column names "{ch}/{red}/{metric}/{metric}"
+        self.values = values  # (n, len(names)) float64, host
+
+    def to_arrow(self):
+        """Same table as ``format_extraction`` builds (tile, label, sorted feature columns)."""
+        import pyarrow as pa
+
+        data = {"tile": pa.array(self.objects[:, 0], pa.int64()), "label": pa.array(self.objects[:, 1], pa.int64())}
+        for j in np.argsort(np.asarray(self.names, dtype=object), kind="stable") if self.names else []:
+            data[self.names[j]] = pa.array(np.ascontiguousarray(self.values[:, j]), pa.float64())
+        return pa.table(data)
+
+
+def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | None = None) -> ExtractionTable:
+    """Fast public entry point: tree + host (or device) arrays in, dense per-object table out.
+
+    Does what ``process_tree_masks`` + ``extract_tree`` + the pivot of ``format_extraction`` do
+    (extract.py:240-375, 574-598) without materialising the |objects| x |instructions| Python
+    lists: labels and pixels are uploaded once, the per-plane label maxima are found on the
+    device (the reference's ``masks.max()``, extract.py:279), one ``abx_extract`` call fills the
+    table and a single device-to-host copy returns it."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native as nat
+
+    masks = _as_mask_list(masks)
+    plan = plan or engine.compile_tree(tree)
+    if any(len(c) != 1 for c in plan.inst_cols if c):
+        raise Exception("tuple-valued metrics (centroid, min_maj_approximation) cannot be table columns")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    keep = [i for i, m in enumerate(masks) if len(m)]
+    names = ["/".join(str(x) for x in inst) + f"/{inst[-1]}" for inst in plan.instructions]
+    if not keep:
+        return ExtractionTable(np.zeros((0, 2), np.int64), names, np.zeros((0, len(names))))
+    if isinstance(masks[keep[0]], torch.Tensor):
+        labels_dev = torch.stack([masks[i] for i in keep]).to(device)
+    else:
+        labels_dev = _to_device_labels([np.asarray(masks[i]) for i in keep], device)
+    P, H, W = labels_dev.shape
+    nmax = torch.empty(P, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        nat.check(
+            nat.lib().abx_label_max(
+                labels_dev.data_ptr(), nat.U16, P, H, W, labels_dev.stride(0), labels_dev.stride(1), nmax.data_ptr(),
+                C.c_void_p(torch.cuda.current_stream(device).cuda_stream),
+            ),
+            "abx_label_max",
+        )
+    from .tile import TileView
+
+    if isinstance(pixels, TileView):
+        px_dev, offs, cs, zs, rs, C_, Z_ = pixels.addressing(device)
+    else:
+        if isinstance(pixels, np.ndarray):
+            if pixels.dtype not in (np.uint8, np.uint16):
+                raise NotImplementedError(f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200")
+            px_dev = torch.from_numpy(pixels).to(device, non_blocking=True)
+        else:
+            px_dev = pixels.to(device)
+        px_dev = px_dev.contiguous()
+        T, C_, Z_, Y, X = px_dev.shape
+        offs = np.arange(T, dtype=np.int64) * (C_ * Z_ * Y * X)
+        cs, zs, rs = Z_ * Y * X, Y * X, X
+    n_labels = nmax.cpu().numpy().astype(np.int64)  # small D2H: the row count has to reach the host
+    table = engine.run_planes(plan, labels_dev, np.asarray(keep, dtype=np.int32), n_labels, px_dev, offs, cs, zs, rs, C_, Z_)
+    values = table.cpu().numpy()
+    cols = np.fromiter((c[0] for c in plan.inst_cols), dtype=np.int64, count=len(plan.inst_cols))
+    objects = np.stack(
+        [np.repeat(np.asarray(keep, dtype=np.int64), n_labels), np.concatenate([np.arange(1, k + 1) for k in n_labels])],
+        axis=1,
+    ) if n_labels.sum() else np.zeros((0, 2), np.int64)
+    return ExtractionTable(objects, names, values[:, cols] if len(cols) else values[:, :0])
+
+
+def _results_from_dense(plan, dense, row_of_item, inst_of_item):
+    """Flat python list in item order; tuple-valued metrics become tuples."""
+    single = all(len(c) == 1 for c in plan.inst_cols)
+    if single and len(row_of_item):
+        cols = np.fromiter((c[0] for c in plan.inst_cols), dtype=np.int64)
+        return dense[row_of_item, cols[inst_of_item]].tolist()
+    out = []
+    for r, i in zip(row_of_item, inst_of_item):
+        c = plan.inst_cols[i]
+        out.append(float(dense[r, c[0]]) if len(c) == 1 else tuple(float(dense[r, k]) for k in c))
+    return out
+
+
+def process_tree_masks(
+    tree: dict,
+    masks,
+    pixels: np.ndarray,
+    measure_fn,
+    ncores=None,
+    progress_bar: bool = False,
+    cp_measure_kwargs=None,
+):
+    """Same contract as the reference (extract.py:240-301): ``(tileid_instructions, results)``
+    with ``tileid_instructions = product(objects, instructions)``, object-major; objects are
+    every id ``1..max`` of every non-empty tile, absent ids included."""
+    masks = _as_mask_list(masks)
+    instructions = kv(flatten(tree))
+    ind_masks = []
+    for tile_i, masks_in_tile in enumerate(masks):
+        if len(masks_in_tile):
+            for mask_i in range(1, int(masks_in_tile.max()) + 1):
+                ind_masks.append((tile_i, mask_i))
+    tileid_instructions = tuple(product(ind_masks, instructions))
+    _last_items.update(items=tileid_instructions, objects=ind_masks, plan=engine.compile_instructions(instructions))
+    extra = {}
+    if cp_measure_kwargs is not None:
+        extra["cp_measure_kwargs"] = cp_measure_kwargs
+    result = measure_fn(tileid_instructions, masks, pixels, ncores=ncores, progress_bar=progress_bar, **extra)
+    return tileid_instructions, result
+
+
+def process_tree_masks_overlap(
+    tree: dict,
+    masks,
+    pixels: np.ndarray,
+    measure_fn,
+    ncores=None,
+    progress_bar: bool = False,
+    overlap: bool = True,
+    cp_measure_kwargs=None,
+):
+    """BABY-style ``(tile, stack, label)`` enumeration (extract.py:456-517).
+
+    Like the live reference path, the ids enumerated for a stack are ``1..k`` with ``k`` the
+    number of distinct non-zero labels in that stack (``relabel_sequential`` ids), while the
+    measurement reads the plane of the *original* id; for
+    sequential labels — the supported case — both coincide."""
+    masks = _as_mask_list(masks)
+    instructions = kv(flatten(tree))
+    tile_stack_mask = []
+    for tile_i, masks_in_tile in enumerate(masks):
+        for stack_i, stack_pixels in enumerate(masks_in_tile):
+            k = int(np.count_nonzero(np.unique(stack_pixels)))
+            tile_stack_mask.extend((tile_i, stack_i, mask_i) for mask_i in range(1, k + 1))
+    tileid_instructions = tuple(product(tile_stack_mask, instructions))
+    _last_items.update(items=tileid_instructions, objects=tile_stack_mask, plan=engine.compile_instructions(instructions))
+    extra = {}
+    if cp_measure_kwargs is not None:
+        extra["cp_measure_kwargs"] = cp_measure_kwargs
+    result = measure_fn(tileid_instructions, masks, pixels, ncores=ncores, progress_bar=progress_bar, **extra)
+    return tileid_instructions, result
+
+
+def extract_tree(
+    tileid_instructions,
+    masks,
+    pixels,
+    ncores=False,
+    progress_bar: bool = False,
+    overlap: bool = False,
+    cp_measure_kwargs=None,
+):
+    """All measurements of ``tileid_instructions`` in one pass on the GPU (extract.py:304-375).
+
+    ``tileid_instructions`` may be any subset/order of ``((tile, label), (ch, red, metric))``
+    items (``(tile, stack, label)`` with ``overlap=True``)."""
+    results = ExtractionResults()
+    if not len(tileid_instructions):
+        return results
+    masks = _as_mask_list(masks)
+    if tileid_instructions is _last_items["items"]:
+        plan, objects = _last_items["plan"], _last_items["objects"]
+        n_inst = len(plan.instructions)
+        row_of_item = inst_of_item = None  # object-major product: implicit
+    else:
+        inst_index: dict = {}
+        obj_index: dict = {}
+        row_of_item = np.empty(len(tileid_instructions), dtype=np.int64)
+        inst_of_item = np.empty(len(tileid_instructions), dtype=np.int64)
+        for k, (obj, inst) in enumerate(tileid_instructions):
+            row_of_item[k] = obj_index.setdefault(tuple(obj), len(obj_index))
+            inst_of_item[k] = inst_index.setdefault(tuple(inst), len(inst_index))
+        plan = engine.compile_instructions(list(inst_index))
+        objects = list(obj_index)
+        n_inst = len(inst_index)
+
+    # label planes: one per tile, or one per (tile, stack) for overlapping masks
+    planes, plane_tile, n_labels, plane_of = [], [], [], {}
+    for tile_i, m in enumerate(masks):
+        if not len(m):
+            continue
+        stacks = list(m) if overlap else [m]
+        for stack_i, plane in enumerate(stacks):
+            plane = np.asarray(plane)
+            plane_of[(tile_i, stack_i) if overlap else (tile_i,)] = len(planes)
+            planes.append(plane)
+            plane_tile.append(tile_i)
+            if overlap:  # ids 1..k, k = number of distinct labels of the stack (see docstring above)
+                n_labels.append(int(np.count_nonzero(np.unique(plane))))
+            else:
+                n_labels.append(int(plane.max()) if plane.size else 0)
+    n_labels = np.asarray(n_labels, dtype=np.int64)
+    base = np.concatenate([[0], np.cumsum(n_labels)])
+    dense = _run_dense(plan, planes, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels)
+
+    obj_rows = np.empty(len(objects), dtype=np.int64)
+    for k, obj in enumerate(objects):
+        p = plane_of[tuple(obj[:-1])]
+        if not (1 <= obj[-1] <= n_labels[p]):
+            raise IndexError(f"index {obj[-1] - 1} is out of bounds for axis 0 with size {n_labels[p]}")
+        obj_rows[k] = base[p] + obj[-1] - 1
+    if row_of_item is None:
+        row_of_item = np.repeat(obj_rows, n_inst)
+        inst_of_item = np.tile(np.arange(n_inst), len(objects))
+    else:
+        row_of_item = obj_rows[row_of_item]
+    results.extend(_results_from_dense(plan, dense, row_of_item, inst_of_item))
+    results.dense, results.plan, results.items = dense, plan, tileid_instructions
+    results.objects = np.asarray(objects, dtype=np.int64).reshape(len(objects), -1)
+    results.obj_rows = obj_rows
+    return results
+
+
+def format_extraction(instructions_result):
+    """Long -> wide ``pyarrow.Table`` with the reference's naming (extract.py:520-599):
+    scalar results land in ``"{ch}/{red}/{metric}/{metric}"``, dict results in
+    ``"{ch}/{red}/{metric}/{key}"``, ndarrays (embedders) in ``X_{c}``; columns are
+    ``tile, label, <sorted metric names>``; missing cells are null."""
+    import pyarrow as pa
+
+    instructions, results = instructions_result
+    if isinstance(results, ExtractionResults) and results.items is instructions and results.dense is not None:
+        table = _format_dense(results, pa)
+        if table is not None:
+            return table
+    names = ("tile", "label", "metric", "value")
+    formatted = {k: [] for k in names}
+    for inst, metrics in zip(instructions, results, strict=True):
+        tileid = inst[0][0]
+        label = inst[0][-1]
+        branch = "/".join(str(x) for x in inst[1])
+        if isinstance(metrics, (int, float)):
+            formatted["tile"].append(tileid)
+            formatted["label"].append(label)
+            formatted["metric"].append(f"{branch}/{inst[1][-1]}")
+            formatted["value"].append(metrics)
+        elif isinstance(metrics, dict):
+            for k, values in metrics.items():
+                for value in values:
+                    formatted["value"].append(value)
+                    formatted["tile"].append(tileid)
+                    formatted["label"].append(label)
+                    formatted["metric"].append(f"{branch}/{k}")
+        elif isinstance(metrics, np.ndarray):
+            for (r, c), value in np.ndenumerate(metrics):
+                formatted["tile"].append(r)
+                formatted["label"].append(0)
+                formatted["metric"].append(f"X_{c}")
+                formatted["value"].append(value)
+        else:
+            raise Exception(
+                f"the metrics are in an invalid value: {type(metrics)}. Valid values are int/float, dict or numpy array."
+            )
+    pivoted: dict = {}
+    for t, lbl, m, v in zip(formatted["tile"], formatted["label"], formatted["metric"], formatted["value"], strict=True):
+        pivoted.setdefault((t, lbl), {"tile": t, "label": lbl})[m] = v
+    metrics_list = sorted(set(formatted["metric"]))
+    wide = {"tile": [], "label": []}
+    wide.update({m: [] for m in metrics_list})
+    for row in pivoted.values():
+        wide["tile"].append(row["tile"])
+        wide["label"].append(row["label"])
+        for m in metrics_list:
+            wide[m].append(row.get(m, None))
+    return pa.Table.from_pydict(wide)
+
+
+def _format_dense(results: ExtractionResults, pa):
+    """Arrow table straight from the dense block (no per-value Python work)."""
+    plan = results.plan
+    if any(len(c) != 1 for c in plan.inst_cols):
+        return None  # tuple-valued metric: let the generic path raise like the reference
+    objs = results.objects
+    keys = objs[:, [0, -1]]
+    # the reference keys rows by (tile, label): a later object with the same key overwrites
+    _, first = np.unique(keys, axis=0, return_index=True)
+    if len(first) != len(keys):
+        return None
+    names = {}
+    for inst, cols in zip(plan.instructions, plan.inst_cols):
+        names["/".join(str(x) for x in inst) + f"/{inst[-1]}"] = cols[0]
+    data = {"tile": pa.array(keys[:, 0], pa.int64()), "label": pa.array(keys[:, 1], pa.int64())}
+    block = results.dense[results.obj_rows]
+    for name in sorted(names):
+        data[name] = pa.array(np.ascontiguousarray(block[:, names[name]]), pa.float64())
+    return pa.table(data)

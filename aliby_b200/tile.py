@@ -1,0 +1,129 @@
+"""Fused tile crop: tile windows addressed inside the full frame instead of copied out of it.
+
+The reference's Tiler (``src/aliby/tile/tiler.py:309-366``) loads each channel of a time
+point and slices one ``(Z, h, w)`` window per tile (``tiles.py:109-166`` gives the window:
+``start = int(centre - sum(drifts[:tp+1])) - size // 2`` on each axis), stacking them into a
+``(tiles, C, Z, h, w)`` copy.  Here the frame is uploaded once and a :class:`TileView`
+records only the per-tile origins; the extraction kernels read the windows in place (each
+pixel leaves HBM once), and :meth:`TileView.materialize` produces the reference's dense
+array on the device for consumers that want it (a segmenter).
+
+Out-of-bounds windows (median padding / NaN tiles of ``tiler.py:601-650``) have no CUDA
+kernel: the reference filters edge tiles at time point 0 (``tiler.py:685-690``) and its
+drift is pinned to zero in this fork, so they do not occur on the pipeline
+path; asking for one raises ``NotImplementedError`` (there is no CPU fallback).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+
+def tile_origins(centres, size, drifts=(), tp: int = 0) -> np.ndarray:
+    """First/second-axis start of every tile window at time ``tp`` (tiles.py:109-166)."""
+    size = (size, size) if isinstance(size, int) else tuple(size)
+    centres = np.asarray(centres)
+    shift = np.sum(np.asarray(drifts, dtype=float).reshape(-1, 2)[: tp + 1], axis=0) if len(drifts) else np.zeros(2)
+    at_tp = (centres - shift).astype(int)  # truncation toward zero, like Tile.centre_at_time
+    half = np.array([size[0] // 2, size[1] // 2])
+    return (at_tp - half).astype(np.int64)
+
+
+class TileView:
+    """Lazy ``(tiles, C, Z, h, w)`` view of windows inside one ``(C, Z, H, W)`` frame."""
+
+    def __init__(self, frame, origins, size):
+        self.frame = frame  # numpy array or torch tensor (host or device)
+        self.origins = np.asarray(origins, dtype=np.int64).reshape(-1, 2)
+        self.size = (size, size) if isinstance(size, int) else tuple(size)
+        C_, Z_, H, W = frame.shape
+        h, w = self.size
+        bad = (
+            (self.origins[:, 0] < 0) | (self.origins[:, 1] < 0) | (self.origins[:, 0] + h > H) | (self.origins[:, 1] + w > W)
+        )
+        if bad.any():
+            raise NotImplementedError(
+                f"tile windows {np.flatnonzero(bad).tolist()} leave the {H}x{W} frame: the median/NaN padding of "
+                "tiler.py:601-650 has no CUDA kernel and there is no CPU fallback"
+            )
+        self._dev = None
+
+    @property
+    def shape(self):
+        C_, Z_, _, _ = self.frame.shape
+        return (len(self.origins), C_, Z_, *self.size)
+
+    @property
+    def dtype(self):
+        return self.frame.dtype
+
+    def __len__(self):
+        return len(self.origins)
+
+    def device_frame(self, device=None):
+        import torch
+
+        if self._dev is None or (device is not None and self._dev.device != torch.device(device)):
+            if device is None:
+                device = torch.device("cuda", torch.cuda.current_device())
+            f = self.frame
+            if isinstance(f, np.ndarray):
+                if f.dtype not in (np.uint8, np.uint16):
+                    raise NotImplementedError(f"pixel dtype {f.dtype} has no CUDA kernel in aliby_b200")
+                f = torch.from_numpy(np.ascontiguousarray(f))
+            self._dev = f.to(device, non_blocking=True).contiguous()
+        return self._dev
+
+    def addressing(self, device=None):
+        """(device frame, tile element offsets, chan/z/row strides, C, Z) for the kernels."""
+        f = self.device_frame(device)
+        C_, Z_, H, W = f.shape
+        offs = self.origins[:, 0] * W + self.origins[:, 1]
+        return f, offs.astype(np.int64), Z_ * H * W, H * W, W, C_, Z_
+
+    def materialize(self, device=None):
+        """Dense ``(tiles, C, Z, h, w)`` device tensor (what ``Tiler.get_fczyx`` returns)."""
+        import torch
+
+        f = self.device_frame(device)
+        C_, Z_, H, W = f.shape
+        h, w = self.size
+        out = torch.empty((len(self.origins), C_, Z_, h, w), dtype=f.dtype, device=f.device)
+        if len(self.origins) == 0:
+            return out
+        org = torch.from_numpy(self.origins.astype(np.int32)).to(f.device)
+        dt = {torch.uint8: nat.U8, torch.uint16: nat.U16, torch.float32: nat.F32}[f.dtype]
+        with torch.cuda.device(f.device):
+            nat.check(
+                nat.lib().abx_crop_tiles(
+                    f.data_ptr(), dt, C_, Z_, Z_ * H * W, H * W, W, org.data_ptr(), len(self.origins), h, w,
+                    out.data_ptr(), C.c_void_p(torch.cuda.current_stream(f.device).cuda_stream),
+                ),
+                "abx_crop_tiles",
+            )
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialize().cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
+class FusedTiler:
+    """Step object with the reference Tiler's ``run_tp`` contract (tiler.py:393-448) for
+    pre-located tiles: returns ``{"drift": [0.0, 0.0], "pixels": TileView}``."""
+
+    def __init__(self, pixels_tczyx, centres, tile_size):
+        self.pixels = pixels_tczyx
+        self.centres = np.asarray(centres)
+        self.tile_size = tile_size
+
+    def run_tp(self, tp: int):
+        frame = self.pixels[tp]
+        if hasattr(frame, "compute"):
+            frame = frame.compute(scheduler="synchronous")
+        view = TileView(np.asarray(frame), tile_origins(self.centres, self.tile_size), self.tile_size)
+        return {"drift": [0.0, 0.0], "pixels": view}

@@ -1,0 +1,186 @@
+/*
+ * aliby_b200 — C-ABI of the B200 (sm_100a) per-object feature-extraction library.
+ *
+ * This is the drop-in boundary for ALIBY's extraction hot path.  The reference
+ * (afermg/aliby) is pure Python and has no FFI of its own; each entry point below
+ * names the reference code it replaces (paths relative to the reference root):
+ *
+ *   abx_label_scan     src/agora/utils/masks.py:35-37 (one-hot expansion, deleted) +
+ *                      src/extraction/core/functions/cell.py:18-27,282-303 (area, centroid)
+ *   abx_object_stats   src/extraction/extract.py:77-153 (measure/measure_mono loop),
+ *                      src/extraction/core/functions/distributors.py:6-24 (Z reduction, fused),
+ *                      src/extraction/core/functions/cell.py:43-157,232-265 (mean, total,
+ *                      total_squared, median, max2p5pc, max5px_median, std, moment_of_inertia),
+ *                      src/extraction/core/functions/trap.py:6-43 (background = label 0),
+ *                      src/aliby/tile/tiler.py:309-366 (tile crop, fused through tile offsets)
+ *   abx_shape_edt      src/extraction/core/functions/cell.py:30-40,160-229 (eccentricity,
+ *                      volume, conical_volume, min_maj_approximation: three chained EDTs)
+ *   abx_finalize       the scalar arithmetic of the functions above + the dense
+ *                      [objects x columns] table that replaces the long->wide pivot of
+ *                      src/extraction/extract.py:574-598
+ *   abx_extract        all four, stream-ordered (one call per extract step and timepoint,
+ *                      i.e. what src/aliby/pipe_core.py:217 invokes)
+ *   abx_crop_tiles     src/aliby/tile/tiler.py:309-366 materialised (tiles, C, Z, h, w)
+ *
+ * Conventions: plain C, no exceptions; every call returns 0 on success or a negative
+ * abx_status, with a thread-local message behind abx_last_error().  The caller owns
+ * every buffer (device memory unless stated otherwise); nothing is allocated on the
+ * hot call — size the scratch with abx_extract_workspace_bytes().  All strides and
+ * offsets are in ELEMENTS of the addressed array.  Calls are re-entrant across
+ * streams and devices; the only global state is the thread-local error string.
+ */
+#ifndef ALIBY_B200_H
+#define ALIBY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABX_VERSION 1
+
+typedef enum abx_status {
+  ABX_OK = 0,
+  ABX_ERR_INVALID = -1,   /* bad argument (message says which) */
+  ABX_ERR_UNSUPPORTED = -2, /* dtype / reduction without a kernel: no CPU fallback exists */
+  ABX_ERR_CUDA = -3,      /* CUDA runtime error */
+  ABX_ERR_WORKSPACE = -4  /* workspace too small */
+} abx_status;
+
+typedef enum abx_dtype { ABX_U8 = 0, ABX_U16 = 1, ABX_U32 = 2, ABX_F32 = 3 } abx_dtype;
+
+/* Z reductions of REDUCTION_FUNS (loaders.py:110-127) that are legal ufuncs. */
+typedef enum abx_reduction { ABX_RED_MAX = 0, ABX_RED_ADD = 1 } abx_reduction;
+
+/* Dense-table column kinds. 0-15 need only the label plane, 16+ a pixel request. */
+typedef enum abx_metric {
+  ABX_M_AREA = 0,
+  ABX_M_CENTROID_X = 1,
+  ABX_M_CENTROID_Y = 2,
+  ABX_M_SPHERICAL_VOLUME = 3,
+  ABX_M_ECCENTRICITY = 4,
+  ABX_M_VOLUME = 5,
+  ABX_M_CONICAL_VOLUME = 6,
+  ABX_M_MINOR_AXIS = 7,
+  ABX_M_MAJOR_AXIS = 8,
+  ABX_M_BBOX_RMIN = 9,
+  ABX_M_BBOX_RMAX = 10,
+  ABX_M_BBOX_CMIN = 11,
+  ABX_M_BBOX_CMAX = 12,
+  ABX_M_MEAN = 16,
+  ABX_M_TOTAL = 17,
+  ABX_M_TOTAL_SQUARED = 18,
+  ABX_M_STD = 19,
+  ABX_M_MEDIAN = 20,
+  ABX_M_MAX2P5PC = 21,
+  ABX_M_MAX5PX_MEDIAN = 22,
+  ABX_M_MOMENT_OF_INERTIA = 23,
+  ABX_M_RATIO = 24,
+  ABX_M_MAX = 25,
+  ABX_M_MIN = 26,
+  ABX_M_IMBACKGROUND = 27,
+  ABX_M_BACKGROUND_MAX5 = 28
+} abx_metric;
+
+/* What a pixel request has to compute (bit mask). Sums/min/max are always produced. */
+#define ABX_F_MEDIAN 1u
+#define ABX_F_TOP2P5 2u
+#define ABX_F_TOP5 4u
+#define ABX_F_WRAPSQ 8u   /* total_squared with the square wrapped in the pixel dtype */
+#define ABX_F_MOI 16u
+
+/* One (channel, Z-reduction) pair of the extraction tree. */
+typedef struct abx_request {
+  int32_t channel;
+  int32_t reduction;   /* abx_reduction */
+  uint32_t features;   /* ABX_F_* needed for cell objects */
+  uint32_t bg_features; /* ABX_F_* needed for the per-plane background object (0 = none) */
+} abx_request;
+
+/* One column of the dense output table. */
+typedef struct abx_column {
+  int32_t request; /* index into requests[], -1 for label-only metrics */
+  int32_t metric;  /* abx_metric */
+} abx_column;
+
+/* Per-object record produced by abx_label_scan (also usable on its own). */
+typedef struct abx_object_rec {
+  uint64_t sum_row; /* sum of (row + 1) over the object's pixels */
+  uint64_t sum_col; /* sum of (col + 1) */
+  uint32_t n;       /* area in pixels */
+  uint32_t rmin, rmax, cmin, cmax; /* inclusive bbox, plane coordinates */
+  uint32_t pad_;
+} abx_object_rec;
+
+typedef struct abx_extract_args {
+  /* label planes: [n_planes][H][W] */
+  const void* labels;
+  int32_t label_dtype; /* ABX_U16 (segment/dispatch.py:14-19 guarantees ids < 65536) */
+  int32_t n_planes;
+  int32_t H, W;
+  int64_t label_plane_stride, label_row_stride;
+  const int32_t* plane_tile; /* [n_planes] pixel tile read by each plane */
+  const int32_t* plane_base; /* [n_planes + 1] exclusive prefix of max label per plane */
+  int32_t n_objects;         /* == plane_base[n_planes] (host value) */
+  int32_t with_background;   /* also reduce label 0 of every plane (per-tile background) */
+  /* pixels: element (tile, ch, z, r, c) lives at
+   *   pixels[tile_offset[tile] + ch*chan_stride + z*z_stride + r*row_stride + c]
+   * which covers a dense (tiles,C,Z,h,w) array and a tile crop fused straight out of
+   * full frames (tile_offset = frame base + row0*row_stride + col0). */
+  const void* pixels;
+  int32_t pixel_dtype; /* ABX_U8 | ABX_U16 */
+  int32_t n_tiles;
+  int32_t C, Z;
+  const int64_t* tile_offset; /* [n_tiles] */
+  int64_t chan_stride, z_stride, row_stride;
+  /* plan */
+  const abx_request* requests; /* device, [n_requests] */
+  int32_t n_requests;
+  const abx_column* columns;   /* device, [n_columns] */
+  int32_t n_columns;
+  int32_t need_edt;            /* any of ECCENTRICITY/VOLUME/CONICAL_VOLUME/MINOR/MAJOR requested */
+  int32_t request_feature_union; /* OR of features|bg_features over requests (host copy) */
+  /* output: [n_objects][n_columns] float64, row-major */
+  double* table;
+  /* scratch */
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream; /* cudaStream_t */
+  /* optional: 5 events made by abx_event_create, recorded on `stream` before the label scan and
+   * after the label scan / object statistics / EDT shape metrics / finalisation */
+  void* const* stage_events;
+} abx_extract_args;
+
+int abx_version(void);
+const char* abx_last_error(void);
+
+/* Bytes of scratch abx_extract needs for these shapes (labels/pixels pointers are not read). */
+int abx_extract_workspace_bytes(const abx_extract_args* args, size_t* bytes);
+
+/* Whole hot path: label scan -> per-object statistics -> EDT shape metrics -> dense table. */
+int abx_extract(const abx_extract_args* args);
+
+/* Stages, callable on their own (records: [n_objects + n_planes], background records last). */
+int abx_label_scan(const abx_extract_args* args, abx_object_rec* records);
+
+/* Per-plane maximum label (what masks.max() is to extract.py:279), out: device int32 [n_planes]. */
+int abx_label_max(const void* labels, int32_t label_dtype, int32_t n_planes, int32_t H, int32_t W,
+                  int64_t plane_stride, int64_t row_stride, int32_t* out_max, void* stream);
+
+/* Materialised tile crop (tiler.py:309-366) for in-bounds windows:
+ * out[(t, c, z, r, x)] = frame[c*chan_stride + z*z_stride + (row0[t]+r)*row_stride + col0[t]+x]. */
+int abx_crop_tiles(const void* frame, int32_t dtype, int32_t C, int32_t Z, int64_t chan_stride,
+                   int64_t z_stride, int64_t row_stride, const int32_t* tile_origin /* [n_tiles][2] */,
+                   int32_t n_tiles, int32_t h, int32_t w, void* out, void* stream);
+
+/* Timing events for abx_extract_args.stage_events (thin wrappers over cudaEvent_t). */
+int abx_event_create(void** event);
+int abx_event_destroy(void* event);
+int abx_event_elapsed_ms(void* start, void* end, float* ms); /* both events must have completed */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALIBY_B200_H */

@@ -173,7 +173,7 @@ def run_tree(tree: dict, masks, pixels: np.ndarray):
         index = PlaneIndex(np.asarray(lab_plane))
         projected: dict = {}
         for j, (ch, red, metric) in enumerate(instructions):
-            if metric not in port.CELL_METRICS and metric not in ("max", "min") | BACKGROUND_METRICS:
+            if metric not in port.CELL_METRICS and metric not in {"max", "min"} | BACKGROUND_METRICS:
                 raise KeyError(metric)
             img = None
             if ch != "None":

@@ -1,0 +1,300 @@
+"""Parity of the CUDA hot path (through the C-ABI) with the reference-pinned oracle.
+
+Integer-derived outputs (area, total, total_squared, median, max2p5pc, max5px_median, mean,
+centroid, bbox, max/min, minor/major axis, volume, eccentricity) must be bit-exact; the
+fp64 outputs whose summation order differs from NumPy's (std, moment_of_inertia,
+conical_volume, spherical_volume) must agree within the north star's 1e-6 relative — the
+tests ask for 1e-9.
+"""
+
+import json
+
+import numpy as np
+import pytest
+
+from conftest import as_float_pairs, assert_same, golden_tree, load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOOSE = {"std", "moment_of_inertia", "conical_volume", "spherical_volume"}
+RTOL_LOOSE = 1e-9
+
+SHAPE = ["area", "centroid", "centroid_x", "centroid_y", "conical_volume", "eccentricity",
+         "min_maj_approximation", "spherical_volume", "volume"]
+INTENSITY = ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median",
+             "moment_of_inertia", "ratio"]
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from aliby_b200 import extract
+
+    return extract
+
+
+def check_items(items, got, want_a, want_b=None):
+    ga, gb = as_float_pairs(got)
+    metrics = np.array([it[1][2] for it in items])
+    loose = np.isin(metrics, list(LOOSE))
+    assert_same(ga[~loose], np.asarray(want_a)[~loose], 0.0, "exact metrics")
+    assert_same(ga[loose], np.asarray(want_a)[loose], RTOL_LOOSE, "fp64 metrics")
+    if want_b is not None:
+        assert_same(gb, want_b, 0.0, "tuple second slot")
+
+
+def against_oracle(ab, tree, masks, pixels, oracle=None):
+    from oracle import fast
+
+    oracle = oracle or fast
+    items, got = ab.process_tree_masks(tree, masks, pixels, ab.extract_tree)
+    o_items, want = oracle.run_tree(tree, masks, pixels)
+    assert len(items) == len(o_items)
+    assert all(a[0] == tuple(b[0]) and tuple(a[1]) == tuple(b[1]) for a, b in zip(items[:200], o_items[:200]))
+    wa, wb = as_float_pairs(want)
+    check_items(items, got, wa, wb)
+    return items, got
+
+
+# ---------------------------------------------------------------- golden vectors (real reference)
+def test_golden_field_small(ab):
+    g = load_golden("field_small.npz")
+    items, got = ab.process_tree_masks(golden_tree(g), g["labels"], g["pixels"], ab.extract_tree)
+    assert len(items) == int(g["n_items"])
+    check_items(items, got, g["values"], g["values2"])
+
+
+def test_golden_tiles_list_and_table(ab):
+    g = load_golden("tiles_list.npz")
+    masks = [m for m in g["labels"]]
+    items, got = ab.process_tree_masks(golden_tree(g), masks, g["pixels"], ab.extract_tree)
+    assert [it[0][0] for it in items] == g["item_tile"].tolist()
+    assert [it[0][1] for it in items] == g["item_label"].tolist()
+    check_items(items, got, g["values"])
+    table = ab.format_extraction((items, got))
+    assert table.column_names == json.loads(str(g["table_columns"]))
+    assert [str(t) for t in table.schema.types] == json.loads(str(g["table_types"]))
+    assert table.column("tile").to_pylist() == g["table_tile"].tolist()
+    assert table.column("label").to_pylist() == g["table_label"].tolist()
+    vals = np.stack([np.asarray(table.column(c).to_pylist(), dtype=float) for c in table.column_names[2:]], axis=1)
+    loose_cols = np.array([c.split("/")[-1] in LOOSE for c in table.column_names[2:]])
+    assert_same(vals[:, ~loose_cols], g["table_values"][:, ~loose_cols], 0.0, "table exact")
+    assert_same(vals[:, loose_cols], g["table_values"][:, loose_cols], RTOL_LOOSE, "table fp64")
+    # the generic (non-dense) formatter must build the same table from plain python lists
+    table2 = ab.format_extraction((items, list(got)))
+    assert table2.schema.equals(table.schema) and table2.num_rows == table.num_rows
+    for c in table.column_names:
+        assert_same(table2.column(c).to_pylist(), table.column(c).to_pylist(), 0.0, c)
+
+
+def test_golden_volume_shapes(ab):
+    """Reference outputs for the analytic shapes of tests/extraction/test_volume.py."""
+    from oracle.make_golden import numpy_disk, numpy_ellipse
+
+    g = load_golden("volume_shapes.npz")
+    tree = {"None": {"None": ["min_maj_approximation", "volume", "eccentricity", "conical_volume"]}}
+    for kind, x, ecc, rot, want in zip(g["kind"], g["x"], g["ecc"], g["rot"], g["out"]):
+        if kind == "disk":
+            m = numpy_disk(int(x))
+        else:
+            y = int(np.round(np.sqrt(x**2 / (1 - ecc**2))))
+            m = numpy_ellipse(int(x), y, int(rot))
+        _, got = ab.process_tree_masks(tree, m.astype(np.uint16), np.zeros((1, 1, 1, *m.shape), np.uint16), ab.extract_tree)
+        assert got[0] == (want[0], want[1]), (kind, x, ecc, rot, got[0], want[:2])
+        assert got[1] == want[2] and got[2] == want[3]
+        assert abs(got[3] - want[4]) <= RTOL_LOOSE * abs(want[4])
+        if kind == "disk":  # the reference's own analytic 1 % bound
+            real_v = 4 * np.pi * float(x) ** 3 / 3
+            assert abs(got[1] - real_v) / real_v < 0.01
+
+
+def test_golden_degenerate_shapes(ab):
+    g = load_golden("degenerate_shapes.npz")
+    tree = {"None": {"None": ["min_maj_approximation", "volume", "eccentricity", "conical_volume", "area"]}}
+    lab = g["labels"]
+    items, got = ab.process_tree_masks(tree, lab, np.zeros((1, 1, 1, *lab.shape), np.uint16), ab.extract_tree)
+    got = np.array([[*got[5 * k][:2], got[5 * k + 1], got[5 * k + 2], got[5 * k + 3], got[5 * k + 4]] for k in range(9)])
+    assert_same(got, g["out"], 0.0, "degenerate shapes")
+
+
+def test_golden_background(ab):
+    g = load_golden("background.npz")
+    tree = {0: {"max": ["imBackground", "background_max5"]}}
+    items, got = ab.process_tree_masks(tree, g["labels"], g["image"][None, None, None], ab.extract_tree)
+    assert got[0] == float(g["imBackground"]) and got[1] == float(g["background_max5"])
+    # registry view with the reference's (Y, X, N) calling convention (trap.py:6-43)
+    lab = g["labels"]
+    stack = np.stack([lab == k for k in range(1, int(lab.max()) + 1)], axis=2)
+    assert ab.TRAP_FUNS["imBackground"](stack, g["image"]) == float(g["imBackground"])
+    assert ab.TRAP_FUNS["background_max5"](stack, g["image"]) == float(g["background_max5"])
+
+
+def test_golden_overlap(ab):
+    from functools import partial
+
+    g = load_golden("overlap.npz")
+    masks = [m for m in g["masks"]]
+    items, got = ab.process_tree_masks_overlap(golden_tree(g), masks, g["pixels"], partial(ab.extract_tree, overlap=True))
+    assert np.array_equal(np.array([list(it[0]) for it in items]), g["item_ids"])
+    assert_same(got, g["values"], 0.0, "overlap")
+
+
+# ---------------------------------------------------------------- oracle comparisons on synthetic fields
+def test_config_c1(ab):
+    """BASELINE.json configs[0]: 2 channels x 1080^2, ~300 objects, intensity + sizeshape."""
+    from aliby_b200 import synth
+
+    pixels, labels = synth.make_field(synth.CONFIG_SEEDS["C1"], (1080, 1080), 2, 300)
+    tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume"]},
+            0: {"max": ["mean", "std", "median", "total", "max2p5pc", "max5px_median", "max", "min"]},
+            1: {"max": ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median", "moment_of_inertia"]}}
+    items, got = against_oracle(ab, tree, labels, pixels)
+    assert len(items) == int(labels.max()) * 22
+
+
+def test_config_c2_full_size(ab):
+    """BASELINE.json configs[1]: 5 channels x 2160^2, ~2k cells, full cell-function set."""
+    from aliby_b200 import synth
+
+    pixels, labels = synth.make_field(synth.CONFIG_SEEDS["C2"], (2160, 2160), 5, 2000)
+    tree = {"None": {"None": SHAPE}}
+    for ch in range(5):
+        tree[ch] = {"max": INTENSITY + ["max", "min"]}
+    items, got = against_oracle(ab, tree, labels, pixels)
+    # size-independent properties
+    a, _ = as_float_pairs(got)
+    metrics = np.array([it[1][2] for it in items])
+    chans = np.array([str(it[1][0]) for it in items])
+    assert a[metrics == "area"].sum() == np.count_nonzero(labels)
+    for ch in range(5):
+        tot = a[(metrics == "total") & (chans == str(ch))].sum()
+        assert tot == pixels[0, ch, 0][labels > 0].astype(np.int64).sum()
+
+
+def test_z_stack_max_and_add(ab):
+    """configs[3] shape at a reduced size: Z = 16, reductions max and add fused into the load."""
+    from aliby_b200 import synth
+
+    pixels, labels = synth.make_field(1004, (256, 320), 3, 40, n_z=16)
+    tree = {0: {"max": INTENSITY}, 1: {"add": INTENSITY}, 2: {"add": ["mean", "median"], "max": ["median", "max2p5pc"]}}
+    against_oracle(ab, tree, labels, pixels)
+
+
+def test_uint8_pixels_and_odd_width(ab):
+    rng = np.random.default_rng(3)
+    from aliby_b200 import synth
+
+    labels = synth.ellipse_labels(rng, (101, 203), 25, semi_axes=(4, 14))
+    pixels = rng.integers(0, 256, size=(1, 2, 2, 101, 203)).astype(np.uint8)
+    tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity"]},
+            0: {"max": INTENSITY}, 1: {"add": INTENSITY}}
+    against_oracle(ab, tree, labels, pixels)
+
+
+def test_wide_value_range_needs_refinement(ab):
+    """Objects whose values span the whole uint16 range force the multi-level radix select."""
+    rng = np.random.default_rng(9)
+    labels = np.zeros((200, 300), np.uint16)
+    labels[10:90, 10:140] = 1     # 10 400 px  (> shared-memory capacity: window re-scan path)
+    labels[100:150, 20:60] = 2    # 2 000 px
+    labels[160:163, 5:9] = 3
+    labels[100:190, 200:290] = 5  # id 4 absent
+    pixels = rng.integers(0, 65536, size=(1, 2, 3, 200, 300)).astype(np.uint16)
+    pixels[0, 0, :, 160:163, 5:9] = 77  # constant object
+    tree = {0: {"max": INTENSITY}, 1: {"add": INTENSITY, "max": ["median", "max2p5pc", "max5px_median"]}}
+    against_oracle(ab, tree, labels, pixels)
+
+
+def test_whole_plane_object_and_large_edt(ab):
+    """One label covering almost the whole plane: non-compacted statistics + global-scratch EDT."""
+    rng = np.random.default_rng(4)
+    labels = np.ones((150, 180), np.uint16)
+    labels[0, :] = 0
+    labels[40:60, 50:90] = 2
+    pixels = rng.integers(0, 5000, size=(1, 1, 1, 150, 180)).astype(np.uint16)
+    tree = {"None": {"None": SHAPE}, 0: {"max": INTENSITY + ["imBackground", "background_max5"]}}
+    against_oracle(ab, tree, labels, pixels)
+
+
+def test_empty_inputs(ab):
+    tree = {"None": {"None": ["area"]}, 0: {"max": ["mean"]}}
+    px = np.zeros((1, 1, 1, 32, 32), np.uint16)
+    items, got = ab.process_tree_masks(tree, np.zeros((32, 32), np.uint16), px, ab.extract_tree)
+    assert items == () and list(got) == []
+    items, got = ab.process_tree_masks(tree, [np.zeros((0,), np.uint16)], px, ab.extract_tree)
+    assert items == () and list(got) == []
+    table = ab.format_extraction((items, got))
+    assert table.num_rows == 0 and table.column_names == ["tile", "label"]
+
+
+def test_error_behaviour(ab):
+    px = np.zeros((1, 1, 2, 16, 16), np.uint16)
+    lab = np.zeros((16, 16), np.uint16)
+    lab[2:5, 2:5] = 1
+    with pytest.raises(KeyError):
+        ab.process_tree_masks({0: {"max": ["not_a_metric"]}}, lab, px, ab.extract_tree)
+    with pytest.raises(KeyError):
+        ab.process_tree_masks({0: {"nope": ["mean"]}}, lab, px, ab.extract_tree)
+    with pytest.raises(Exception, match="invalid reducer"):
+        ab.process_tree_masks({0: {"mean": ["mean"]}}, lab, px, ab.extract_tree)
+    with pytest.raises(Exception, match="invalid reducer"):
+        ab.process_tree_masks({0: {"None": ["mean"]}}, lab, px, ab.extract_tree)
+    with pytest.raises(NotImplementedError):
+        ab.process_tree_masks({0: {"max": ["mean"]}}, lab, px.astype(np.float32), ab.extract_tree)
+    # no objects -> the reference never reaches the lookups, neither do we
+    items, got = ab.process_tree_masks({0: {"max": ["not_a_metric"]}}, np.zeros_like(lab), px, ab.extract_tree)
+    assert items == ()
+
+
+def test_extract_tree_arbitrary_subset(ab):
+    """extract_tree called directly with a shuffled subset of items (extract.py:304-375 contract)."""
+    from oracle import fast
+
+    g = load_golden("tiles_list.npz")
+    masks = [m for m in g["labels"]]
+    tree = golden_tree(g)
+    o_items, o_res = fast.run_tree(tree, masks, g["pixels"])
+    rng = np.random.default_rng(0)
+    pick = rng.permutation(len(o_items))[:97]
+    sub = tuple(o_items[i] for i in pick)
+    got = ab.extract_tree(sub, masks, g["pixels"], ncores=None)
+    check_items(sub, got, as_float_pairs([o_res[i] for i in pick])[0])
+
+
+def test_registry_single_mask_calls(ab):
+    """CELL_FUNS[name](mask, pixels) — the registry contract of loaders.py:28-79."""
+    from oracle import port
+
+    rng = np.random.default_rng(2)
+    yy, xx = np.mgrid[0:40, 0:50]
+    mask = ((yy - 18) ** 2 / 90.0 + (xx - 22) ** 2 / 200.0) <= 1.0
+    img = rng.integers(100, 3000, size=(40, 50)).astype(np.uint16)
+    for name in ["area", "mean", "median", "max2p5pc", "max5px_median", "total", "centroid_x", "centroid_y",
+                 "volume", "eccentricity", "total_squared"]:
+        want = port.CELL_METRICS[name](mask, img.copy())
+        assert ab.CELL_FUNS[name](mask, img) == float(want), name
+    assert ab.CELL_FUNS["centroid"](mask, None) == tuple(float(v) for v in port.m_centroid(mask))
+    assert set(port.CELL_METRICS) <= set(ab.CELL_FUNS)
+
+
+def test_fused_tile_crop_matches_reference_crop(ab):
+    """configs[2] (yeast traps): extraction straight out of the frame == crop (tiler.py) then extract."""
+    from aliby_b200 import synth
+    from aliby_b200.tile import TileView, tile_origins
+    from oracle import fast, port
+
+    frames, centres, labels = synth.make_trap_position(1003, n_tp=2, n_channels=3, frame=(600, 640), n_tiles=12, tile_size=96)
+    tree = {"None": {"None": ["area", "volume", "eccentricity", "centroid_x", "centroid_y"]},
+            0: {"max": ["mean", "median", "std", "max5px_median", "imBackground"]},
+            2: {"max": ["median", "background_max5"]}}
+    for tp in range(2):
+        masks = [m for m in labels[tp]]
+        crop = port.crop_tiles(frames[tp], centres, (96, 96), (), tp)  # the reference's materialised tiles
+        view = TileView(frames[tp], tile_origins(centres, 96), 96)
+        assert np.array_equal(np.asarray(view), crop)  # abx_crop_tiles == tiler.py crop
+        items, got = ab.process_tree_masks(tree, masks, view, ab.extract_tree)
+        o_items, want = fast.run_tree(tree, masks, crop)
+        check_items(items, got, as_float_pairs(want)[0])

@@ -45,6 +45,7 @@ METRIC = {
     "background_max5": 28,
 }
 EDT_METRICS = {4, 5, 6, 7, 8}
+CONICAL_METRIC = 6
 
 F_MEDIAN, F_TOP2P5, F_TOP5, F_WRAPSQ, F_MOI = 1, 2, 4, 8, 16
 
@@ -74,12 +75,12 @@ class ObjectRec(C.Structure):
     _fields_ = [
         ("sum_row", C.c_uint64),
         ("sum_col", C.c_uint64),
-        ("n", C.c_uint32),
         ("rmin", C.c_uint32),
         ("rmax", C.c_uint32),
         ("cmin", C.c_uint32),
         ("cmax", C.c_uint32),
-        ("pad_", C.c_uint32),
+        ("n", C.c_uint32),
+        ("pad_", C.c_uint32 * 3),
     ]
 
 

@@ -54,7 +54,12 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   ws->shape = reinterpret_cast<ShapeStats*>(b + off);
   off = align_up(off + (a->need_edt ? (size_t)a->n_objects * sizeof(ShapeStats) : 0));
   ws->err = reinterpret_cast<u32*>(b + off);
-  off = align_up(off + sizeof(u32));
+  ws->list_counts = ws->err + 1;
+  off = align_up(off + 4 * sizeof(u32));
+  ws->stats_list = reinterpret_cast<int*>(b + off);
+  off = align_up(off + n_rec * sizeof(int));
+  ws->edt_list = reinterpret_cast<int*>(b + off);
+  off = align_up(off + n_rec * sizeof(int));
   ws->edt_scratch = b + off;
   ws->edt_scratch_per_cta = 0;
   if (a->need_edt) {
@@ -98,8 +103,8 @@ extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* reco
   int rc = abx_validate(args);
   if (rc) return rc;
   if (!records) return abx_set_error(ABX_ERR_INVALID, "records is NULL");
-  if (!args->workspace || args->workspace_bytes < sizeof(u32))
-    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 4-byte workspace for its error flag");
+  if (!args->workspace || args->workspace_bytes < 4 * sizeof(u32))
+    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 16-byte workspace for its flags");
   return launch_label_scan(args, records, static_cast<u32*>(args->workspace), static_cast<cudaStream_t>(args->stream));
 }
 
@@ -118,8 +123,9 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   mark(0);
   if ((rc = launch_label_scan(args, ws.recs, ws.err, st))) return rc;
   mark(1);
-  if ((rc = launch_object_stats(args, ws, st))) return rc;
+  if ((rc = launch_object_warp(args, ws, st))) return rc;   // objects with a window <= 64 x 64
   mark(2);
+  if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
   if ((rc = launch_shape_edt(args, ws, st))) return rc;
   mark(3);
   if ((rc = launch_finalize(args, ws, st))) return rc;

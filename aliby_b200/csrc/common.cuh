@@ -37,7 +37,10 @@ struct Workspace {
   ShapeStats* shape;     // [n_objects]
   unsigned char* edt_scratch;
   size_t edt_scratch_per_cta;
-  u32* err;
+  u32* err;          // [0] error flags, [1] stats_list length, [2] edt_list length
+  int* stats_list;   // objects the warp kernel handed to the CTA statistics kernel
+  int* edt_list;     // objects the warp kernel handed to the CTA EDT kernel
+  u32* list_counts;  // = err + 1
   size_t total;
 };
 
@@ -46,7 +49,8 @@ int abx_check_cuda(cudaError_t e, const char* what);
 int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws);
 int abx_validate(const abx_extract_args* a);
 
-int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, cudaStream_t st);
+int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err /* [3] */, cudaStream_t st);
+int launch_object_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);

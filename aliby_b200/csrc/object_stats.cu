@@ -147,12 +147,15 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
                     int n_objects, int n_total, const PX* __restrict__ pixels,
                     const i64* __restrict__ tile_offset, i64 chan_stride, i64 z_stride, i64 px_row_stride, int Z,
                     const abx_request* __restrict__ requests, int n_requests,
-                    const abx_object_rec* __restrict__ recs, ChanStats* __restrict__ out) {
+                    const abx_object_rec* __restrict__ recs, ChanStats* __restrict__ out,
+                    const int* __restrict__ work_list, const u32* __restrict__ work_count) {
   __shared__ Smem s;
   const u32 lane = lane_id(), warp = threadIdx.x >> 5;
   constexpr u32 kWrapMask = (sizeof(PX) == 1) ? 0xFFu : 0xFFFFu;
 
-  for (int obj = blockIdx.x; obj < n_total; obj += gridDim.x) {
+  const u32 n_work = *work_count;  // objects handed over by the warp-per-object kernel
+  for (u32 wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int obj = work_list[wi];
     __syncthreads();  // previous object's smem is dead
     if (threadIdx.x == 0) {
       const bool bg = obj >= n_objects;
@@ -341,13 +344,13 @@ int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStre
   if (a->n_requests == 0) return ABX_OK;
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0) return ABX_OK;
-  const int grid = n_total < 148 * 64 ? n_total : 148 * 64;
+  const int grid = n_total < 148 * 8 ? n_total : 148 * 8;
 #define ABX_LAUNCH_OS(PX)                                                                                          \
   object_stats_kernel<PX><<<grid, kThreads, 0, st>>>(                                                             \
       static_cast<const uint16_t*>(a->labels), a->label_plane_stride, a->label_row_stride, a->plane_tile,         \
       a->plane_base, a->n_planes, a->n_objects, n_total, static_cast<const PX*>(a->pixels),                       \
       reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride, a->row_stride, a->Z, a->requests, \
-      a->n_requests, ws.recs, ws.chan)
+      a->n_requests, ws.recs, ws.chan, ws.stats_list, ws.list_counts)
   if (a->pixel_dtype == ABX_U16) ABX_LAUNCH_OS(uint16_t);
   else if (a->pixel_dtype == ABX_U8) ABX_LAUNCH_OS(uint8_t);
   else return abx_set_error(ABX_ERR_UNSUPPORTED, "object_stats: pixel dtype %d has no kernel", a->pixel_dtype);

@@ -103,14 +103,17 @@ __global__ void __launch_bounds__(kThreads)
 shape_edt_kernel(const uint16_t* __restrict__ labels, i64 plane_stride, i64 row_stride,
                  const int32_t* __restrict__ plane_base, int n_planes, int n_objects,
                  const abx_object_rec* __restrict__ recs, ShapeStats* __restrict__ out, int large_mode,
-                 unsigned char* scratch, size_t scratch_per_cta) {
+                 unsigned char* scratch, size_t scratch_per_cta, const int* __restrict__ work_list,
+                 const u32* __restrict__ work_count) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ Red red;
   __shared__ abx_object_rec rec;
   __shared__ int s_plane;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int obj = blockIdx.x; obj < n_objects; obj += gridDim.x) {
+  const u32 n_work = *work_count;  // objects handed over by the warp-per-object kernel
+  for (u32 wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int obj = work_list[wi];
     __syncthreads();
     if (threadIdx.x == 0) { rec = recs[obj]; s_plane = find_plane(plane_base, n_planes, obj); }
     __syncthreads();
@@ -206,15 +209,16 @@ int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_
     if (e != cudaSuccess) return abx_check_cuda(e, "shape_edt smem attribute");
     attr_done[dev] = true;
   }
-  const int grid = a->n_objects < 148 * 32 ? a->n_objects : 148 * 32;
+  const int grid = a->n_objects < 148 * 3 ? a->n_objects : 148 * 3;
   shape_edt_kernel<<<grid, kThreads, smem, st>>>(static_cast<const uint16_t*>(a->labels), a->label_plane_stride,
                                                  a->label_row_stride, a->plane_base, a->n_planes, a->n_objects,
-                                                 ws.recs, ws.shape, 0, nullptr, 0);
+                                                 ws.recs, ws.shape, 0, nullptr, 0, ws.edt_list, ws.list_counts + 1);
   if (ws.edt_scratch_per_cta) {
     shape_edt_kernel<<<kEdtLargeCtas, kThreads, 0, st>>>(static_cast<const uint16_t*>(a->labels),
                                                          a->label_plane_stride, a->label_row_stride, a->plane_base,
                                                          a->n_planes, a->n_objects, ws.recs, ws.shape, 1,
-                                                         ws.edt_scratch, ws.edt_scratch_per_cta);
+                                                         ws.edt_scratch, ws.edt_scratch_per_cta, ws.edt_list,
+                                                         ws.list_counts + 1);
   }
   return abx_check_cuda(cudaGetLastError(), "shape_edt");
 }

@@ -89,7 +89,7 @@ class Plan:
     requests: list = field(default_factory=list)  # [(channel, red_enum, features, bg_features)]
     columns: list = field(default_factory=list)  # [(request_idx, metric_enum)]
     inst_cols: list = field(default_factory=list)  # per instruction: tuple of dense column indices
-    need_edt: bool = False
+    need_edt: int = 0  # bit 0: axes (eccentricity/volume/min/maj), bit 1: conical_volume
     with_background: bool = False
     error: Exception | None = None  # raised only when there is at least one object, like the reference
     _dev: dict = field(default_factory=dict)
@@ -140,7 +140,7 @@ def compile_instructions(instructions: list) -> Plan:
             col_index[key] = len(plan.columns)
             plan.columns.append(key)
             if key[1] in nat.EDT_METRICS:
-                plan.need_edt = True
+                plan.need_edt |= 2 if key[1] == nat.CONICAL_METRIC else 1
         return col_index[key]
 
     for inst in instructions:

@@ -375,7 +375,7 @@ def ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        names = ["label_scan", "object_stats", "shape_edt", "finalize"]
+        names = ["label_scan", "object_warp", "large_objects", "finalize"]
         dom = int(np.argmax(stage_ms))
         achieved = (algo_bytes / 1e9) / (stage_ms[dom] / 1e3)
         prof = profiled_traffic() or {}
@@ -416,7 +416,7 @@ def ours(args):
                 "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "api": "aliby_b200.extract.extract_table(tree, masks, pixels) with pinned host arrays",
             },
-            "gpu_launches": args.steps * 6,  # init_records, label_scan, object_stats, shape_edt x2, finalize
+            "gpu_launches": args.steps * 8,  # init_records, label_scan, object_warp, object_stats, shape_edt x2, finalize
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

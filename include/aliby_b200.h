@@ -109,10 +109,10 @@ typedef struct abx_column {
 typedef struct abx_object_rec {
   uint64_t sum_row; /* sum of (row + 1) over the object's pixels */
   uint64_t sum_col; /* sum of (col + 1) */
+  uint32_t rmin, rmax, cmin, cmax; /* inclusive bbox, plane coordinates (16-byte aligned) */
   uint32_t n;       /* area in pixels */
-  uint32_t rmin, rmax, cmin, cmax; /* inclusive bbox, plane coordinates */
-  uint32_t pad_;
-} abx_object_rec;
+  uint32_t pad_[3];
+} abx_object_rec; /* 48 bytes */
 
 typedef struct abx_extract_args {
   /* label planes: [n_planes][H][W] */
@@ -140,7 +140,7 @@ typedef struct abx_extract_args {
   int32_t n_requests;
   const abx_column* columns;   /* device, [n_columns] */
   int32_t n_columns;
-  int32_t need_edt;            /* any of ECCENTRICITY/VOLUME/CONICAL_VOLUME/MINOR/MAJOR requested */
+  int32_t need_edt;            /* bit 0: ECCENTRICITY/VOLUME/MINOR/MAJOR requested, bit 1: CONICAL_VOLUME */
   int32_t request_feature_union; /* OR of features|bg_features over requests (host copy) */
   /* output: [n_objects][n_columns] float64, row-major */
   double* table;
@@ -149,7 +149,7 @@ typedef struct abx_extract_args {
   size_t workspace_bytes;
   void* stream; /* cudaStream_t */
   /* optional: 5 events made by abx_event_create, recorded on `stream` before the label scan and
-   * after the label scan / object statistics / EDT shape metrics / finalisation */
+   * after the label scan / warp-per-object kernel / large-object kernels / finalisation */
   void* const* stage_events;
 } abx_extract_args;
 

@@ -38,6 +38,8 @@ int abx_validate(const abx_extract_args* a) {
       return abx_set_error(ABX_ERR_UNSUPPORTED, "pixel dtype %d has no kernel (uint8/uint16); there is no CPU fallback",
                            a->pixel_dtype);
     if (a->Z < 1 || a->C < 1) return abx_set_error(ABX_ERR_INVALID, "C and Z must be >= 1");
+    if (a->row_stride < 1 || a->row_stride >= (1LL << 25))
+      return abx_set_error(ABX_ERR_INVALID, "pixel row stride %lld outside [1, 2^25)", (long long)a->row_stride);
     if (a->pixel_dtype == ABX_U16 && a->Z > 65536) return abx_set_error(ABX_ERR_INVALID, "Z too large for 32-bit sums");
   }
   return ABX_OK;

@@ -138,31 +138,82 @@ __device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* 
   const u32 n = o.n;
 
   // ---- pass 1: moments and extrema; stage values ----
-  u64 a_sum = 0, a_sq = 0, a_wrap = 0, a_m10 = 0, a_m01 = 0, a_m20 = 0, a_m02 = 0;
-  u32 a_min = 0xFFFFFFFFu, a_max = 0;
-  for_each_px(o, s, [&](u32 r, u32 c, u32 i) {
-    const u32 x = load_reduced(px + (i64)r * px_rs + c, Z, z_stride, rq.reduction);
-    a_sum += x;
-    const u64 xx = (u64)x * (u64)x;
-    a_sq += xx;
-    a_wrap += add ? xx : (u64)((u32)xx & kWrapMask);
-    a_min = min(a_min, x);
-    a_max = max(a_max, x);
-    if (want_moi) {
-      a_m10 += (u64)x * c; a_m01 += (u64)x * r;
-      a_m20 += (u64)x * c * c; a_m02 += (u64)x * r * r;
-    }
-    if (staged) s.vals[i] = (unsigned short)x;
-  });
   ChanStats cs;
-  cs.sum = warp_sum64(a_sum);
-  cs.sumsq = warp_sum64(a_sq);
-  cs.wrapsq = warp_sum64(a_wrap);
-  if (want_moi) {
-    cs.m10 = warp_sum64(a_m10); cs.m01 = warp_sum64(a_m01);
-    cs.m20 = warp_sum64(a_m20); cs.m02 = warp_sum64(a_m02);
+  u32 a_min = 0xFFFFFFFFu, a_max = 0;
+  if (staged) {
+    // Fast path: at most kCap / 32 = 64 values per lane, each < 2^16, so 32-bit partial sums of
+    // x, x*c, x*r and (x*x mod 2^16) are exact and the squares go through one IMAD.WIDE each.
+    // Gathers are issued in batches of kBatch per lane so that their round trips overlap.
+    constexpr int kBatch = 8;
+    u32 f_sum = 0, f_wrap = 0, f_m10 = 0, f_m01 = 0;
+    u64 f_sq = 0, f_m20 = 0, f_m02 = 0;
+    const u32 rs = (u32)px_rs;
+    for (u32 i0 = lane; i0 < n; i0 += 32 * kBatch) {
+      u32 k[kBatch], x[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const u32 i = i0 + 32u * u;
+        k[u] = (i < n) ? (u32)s.offs[i] : 0xFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        x[u] = 0;
+        if (k[u] != 0xFFFFu) {
+          const PX* q = px + ((k[u] >> 6) * rs + (k[u] & 63u));
+          x[u] = (Z == 1) ? (u32)__ldg(q) : load_reduced(q, Z, z_stride, rq.reduction);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const bool ok = k[u] != 0xFFFFu;
+        const u32 v = x[u];
+        f_sum += v;
+        f_sq += (u64)v * (u64)v;
+        f_wrap += (v * v) & kWrapMask;
+        a_min = min(a_min, ok ? v : 0xFFFFFFFFu);
+        a_max = max(a_max, v);
+        if (want_moi) {
+          const u32 c = k[u] & 63u, r = (k[u] >> 6) & 63u;
+          const u32 xc = v * c, xr = v * r;
+          f_m10 += xc; f_m01 += xr;
+          f_m20 += (u64)xc * (u64)c; f_m02 += (u64)xr * (u64)r;
+        }
+        if (ok) s.vals[i0 + 32u * u] = (unsigned short)v;
+      }
+    }
+    cs.sum = (u64)__reduce_add_sync(0xFFFFFFFFu, f_sum);      // n * 65535 < 2^27
+    cs.wrapsq = (u64)__reduce_add_sync(0xFFFFFFFFu, f_wrap);
+    cs.sumsq = warp_sum64(f_sq);
+    if (want_moi) {
+      cs.m10 = warp_sum64((u64)f_m10); cs.m01 = warp_sum64((u64)f_m01);
+      cs.m20 = warp_sum64(f_m20); cs.m02 = warp_sum64(f_m02);
+    } else {
+      cs.m10 = cs.m01 = cs.m20 = cs.m02 = 0;
+    }
   } else {
-    cs.m10 = cs.m01 = cs.m20 = cs.m02 = 0;
+    u64 a_sum = 0, a_sq = 0, a_wrap = 0, a_m10 = 0, a_m01 = 0, a_m20 = 0, a_m02 = 0;
+    for_each_px(o, s, [&](u32 r, u32 c, u32) {
+      const u32 x = load_reduced(px + (i64)r * px_rs + c, Z, z_stride, rq.reduction);
+      a_sum += x;
+      const u64 xx = (u64)x * (u64)x;
+      a_sq += xx;
+      a_wrap += add ? xx : (u64)((u32)xx & kWrapMask);
+      a_min = min(a_min, x);
+      a_max = max(a_max, x);
+      if (want_moi) {
+        a_m10 += (u64)x * c; a_m01 += (u64)x * r;
+        a_m20 += (u64)x * c * c; a_m02 += (u64)x * r * r;
+      }
+    });
+    cs.sum = warp_sum64(a_sum);
+    cs.sumsq = warp_sum64(a_sq);
+    cs.wrapsq = warp_sum64(a_wrap);
+    if (want_moi) {
+      cs.m10 = warp_sum64(a_m10); cs.m01 = warp_sum64(a_m01);
+      cs.m20 = warp_sum64(a_m20); cs.m02 = warp_sum64(a_m02);
+    } else {
+      cs.m10 = cs.m01 = cs.m20 = cs.m02 = 0;
+    }
   }
   const u32 vmin = __reduce_min_sync(0xFFFFFFFFu, a_min);
   const u32 vmax = __reduce_max_sync(0xFFFFFFFFu, a_max);
@@ -273,14 +324,16 @@ __device__ __forceinline__ u32 nearest_bit_sq(u64 m, u32 c) {
 __device__ __forceinline__ void shape_edt_warp(const Obj& o, WSmem& s, u32 rmin, u32 cmin, bool want_conical,
                                                ShapeStats* __restrict__ dst) {
   const u32 lane = lane_id();
-  unsigned char* g = reinterpret_cast<unsigned char*>(s.vals);  // [64][64], 4096 B
-  u64* topmask = reinterpret_cast<u64*>(s.hist);               // [64]
+  // g: row distances with one all-zero frame row above and below the window: [66][64] bytes,
+  // i.e. vals[] plus the first 128 bytes of hist[]; the cone-top mask sits further into hist[]
+  unsigned char* g = reinterpret_cast<unsigned char*>(s.vals);
+  u64* topmask = reinterpret_cast<u64*>(s.hist + 256);         // [64]
   const int h = o.h, w = o.w;
   __syncwarp();
   // zero g (non-object pixels have row distance 0) and the cone-top mask
   {
     uint4* g4 = reinterpret_cast<uint4*>(g);
-    for (int k = lane; k < (kSide * kSide) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
+    for (int k = lane; k < ((kSide + 2) * kSide) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
     topmask[lane] = 0; topmask[lane + 32] = 0;
   }
   __syncwarp();
@@ -293,19 +346,21 @@ __device__ __forceinline__ void shape_edt_warp(const Obj& o, WSmem& s, u32 rmin,
     const u32 dl = le ? (c - (63u - (u32)__clzll((long long)le))) : (c + 1u);
     const u64 ge = z >> c;
     const u32 dr = ge ? ((u32)__ffsll((long long)ge) - 1u) : (64u - c);
-    g[(r << 6) | c] = (unsigned char)min(dl, dr);
+    g[((r + 1u) << 6) | c] = (unsigned char)min(dl, dr);
   });
   __syncwarp();
   // ---- EDT 1: column pass with early exit; frame rows (-1 and h) have g = 0 ----
+  // The frame rows make bounds checks unnecessary: the walk stops at the latest when it reaches
+  // a frame row (candidate d^2 with g = 0), i.e. before it could leave the buffer.
   auto col_min = [&](u32 r, u32 c) -> u32 {
-    const u32 k = (r << 6) | c;
+    const u32 k = ((r + 1u) << 6) | c;
     const u32 g0 = g[k];
     u32 best = g0 * g0;
-    for (u32 d = 1; d * d < best; ++d) {
-      const u32 up = (d <= r) ? (u32)g[k - (d << 6)] : 0u;
-      const u32 dn = (r + d < (u32)h) ? (u32)g[k + (d << 6)] : 0u;
-      const u32 m2 = min(up, dn);
-      best = min(best, m2 * m2 + d * d);
+    u32 d64 = 64, dd = 1, step = 3;  // d * 64, d * d, 2 d + 1
+    while (dd < best) {
+      const u32 m2 = min((u32)g[k - d64], (u32)g[k + d64]);
+      best = min(best, m2 * m2 + dd);
+      dd += step; step += 2; d64 += 64;
     }
     return best;
   };
@@ -323,7 +378,7 @@ __device__ __forceinline__ void shape_edt_warp(const Obj& o, WSmem& s, u32 rmin,
   }
   // ---- cone top: pixels with nn2 == max (only pixels with g^2 >= max can qualify) ----
   for_each_px(o, s, [&](u32 r, u32 c, u32) {
-    const u32 g0 = g[(r << 6) | c];
+    const u32 g0 = g[((r + 1u) << 6) | c];
     if (g0 * g0 >= max_nn2 && col_min(r, c) == max_nn2) atomicOr(reinterpret_cast<unsigned long long*>(&topmask[r]), 1ull << c);
   });
   __syncwarp();
@@ -454,10 +509,13 @@ object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i6
   extern __shared__ __align__(16) unsigned char dyn[];
   WSmem& s = reinterpret_cast<WSmem*>(dyn)[threadIdx.x >> 5];
   const u32 lane = lane_id();
-  const int gwarp = blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * kWarps;
 
-  for (int obj = gwarp; obj < n_total; obj += nwarps) {
+  for (;;) {
+    // dynamic work distribution: one atomic per object (objects differ 100x in cost)
+    int obj = 0;
+    if (lane == 0) obj = (int)atomicAdd(&list_counts[2], 1u);
+    obj = __shfl_sync(0xFFFFFFFFu, obj, 0);
+    if (obj >= n_total) break;
     const abx_object_rec rec = recs[obj];
     const bool is_bg = obj >= n_objects;
     if (rec.n == 0) {
@@ -493,19 +551,31 @@ object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i6
     __syncwarp();
     {
       u32 base = 0;
-      for (int r = 0; r < h; ++r) {
-        const uint16_t* lrow = o.lab + (i64)r * o.lab_rs;
-        const bool hit0 = (lane < (u32)w) && ((u32)__ldg(lrow + lane) == o.label);
-        const bool hit1 = (lane + 32 < (u32)w) && ((u32)__ldg(lrow + lane + 32) == o.label);
-        const u32 b0 = __ballot_sync(0xFFFFFFFFu, hit0);
-        const u32 b1 = __ballot_sync(0xFFFFFFFFu, hit1);
-        if (lane == 0) { s.rowmask[r] = (u64)b0 | ((u64)b1 << 32); s.rowbase[r] = (unsigned short)base; }
-        if (o.listed) {
-          const u32 lt = (1u << lane) - 1u;
-          if (hit0) s.offs[base + __popc(b0 & lt)] = (unsigned short)((r << 6) | lane);
-          if (hit1) s.offs[base + __popc(b0) + __popc(b1 & lt)] = (unsigned short)((r << 6) | (lane + 32));
+      constexpr int kRows = 4;
+      for (int r0 = 0; r0 < h; r0 += kRows) {
+        u32 l0[kRows], l1[kRows];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {  // all loads of the row group first
+          const uint16_t* lrow = o.lab + (i64)(r0 + u) * o.lab_rs;
+          const bool in = r0 + u < h;
+          l0[u] = (in && lane < (u32)w) ? (u32)__ldg(lrow + lane) : 0xFFFFFFFFu;
+          l1[u] = (in && lane + 32 < (u32)w) ? (u32)__ldg(lrow + lane + 32) : 0xFFFFFFFFu;
         }
-        base += __popc(b0) + __popc(b1);
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+          const int r = r0 + u;
+          if (r >= h) break;
+          const bool hit0 = l0[u] == o.label, hit1 = l1[u] == o.label;
+          const u32 b0 = __ballot_sync(0xFFFFFFFFu, hit0);
+          const u32 b1 = __ballot_sync(0xFFFFFFFFu, hit1);
+          if (lane == 0) { s.rowmask[r] = (u64)b0 | ((u64)b1 << 32); s.rowbase[r] = (unsigned short)base; }
+          if (o.listed) {
+            const u32 lt = (1u << lane) - 1u;
+            if (hit0) s.offs[base + __popc(b0 & lt)] = (unsigned short)((r << 6) | lane);
+            if (hit1) s.offs[base + __popc(b0) + __popc(b1 & lt)] = (unsigned short)((r << 6) | (lane + 32));
+          }
+          base += __popc(b0) + __popc(b1);
+        }
       }
       if (lane >= (u32)h) s.rowmask[lane] = 0;  // rows beyond the window read as empty
       if (lane + 32 >= (u32)h) s.rowmask[lane + 32] = 0;
@@ -536,7 +606,7 @@ int launch_object_warp(const abx_extract_args* a, const Workspace& ws, cudaStrea
   if (n_total == 0 || (a->n_requests == 0 && !a->need_edt)) return ABX_OK;
   const size_t smem = object_warp_smem_bytes();
   int grid = (n_total + kWarps - 1) / kWarps;
-  if (grid > 148 * 2 * 8) grid = 148 * 2 * 8;
+  if (grid > 148 * 2) grid = 148 * 2;  // persistent: 2 CTAs per SM, warps pull objects from a counter
   const int want_conical = (a->need_edt & 2) != 0;
 #define ABX_LAUNCH_OW(PX)                                                                                           \
   do {                                                                                                              \

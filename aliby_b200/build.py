@@ -53,6 +53,8 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = find_nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("ABX_PHASE_TIMING"):
+        extra.append("-DABX_PHASE_TIMING")
     objs = []
     jobs = []
     for src in SOURCES:

@@ -57,7 +57,7 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   off = align_up(off + (a->need_edt ? (size_t)a->n_objects * sizeof(ShapeStats) : 0));
   ws->err = reinterpret_cast<u32*>(b + off);
   ws->list_counts = ws->err + 1;
-  off = align_up(off + 4 * sizeof(u32));
+  off = align_up(off + 8 * sizeof(u32));
   ws->stats_list = reinterpret_cast<int*>(b + off);
   off = align_up(off + n_rec * sizeof(int));
   ws->edt_list = reinterpret_cast<int*>(b + off);
@@ -105,8 +105,8 @@ extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* reco
   int rc = abx_validate(args);
   if (rc) return rc;
   if (!records) return abx_set_error(ABX_ERR_INVALID, "records is NULL");
-  if (!args->workspace || args->workspace_bytes < 4 * sizeof(u32))
-    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 16-byte workspace for its flags");
+  if (!args->workspace || args->workspace_bytes < 8 * sizeof(u32))
+    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 32-byte workspace for its flags");
   return launch_label_scan(args, records, static_cast<u32*>(args->workspace), static_cast<cudaStream_t>(args->stream));
 }
 

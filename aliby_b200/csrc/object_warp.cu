@@ -19,22 +19,40 @@
 // kernels (object_stats.cu, shape_edt.cu) consume.
 #include "common.cuh"
 
+// Optional per-phase cycle counters (debug builds: -DABX_PHASE_TIMING): lane 0 of every warp adds its
+// clock64() deltas; read back through abx_debug_phase_cycles().
+#ifdef ABX_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define PHASE_T0() long long _pt = clock64()
+#define PHASE_ADD(i)                                                                      \
+  do {                                                                                    \
+    const long long _n = clock64();                                                       \
+    if (lane_id() == 0) atomicAdd(&g_phase_cycles[i], (unsigned long long)(_n - _pt));    \
+    _pt = _n;                                                                             \
+  } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(i) do {} while (0)
+#endif
+
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
 constexpr int kSide = 64;    // maximum window side
-constexpr int kCap = 2048;   // pixels of one object kept as a compact list
-constexpr int kBins = 512;   // level-0 histogram bins (4 x 128 during refinement)
+// Two size classes share the code: <= 2048 pixels (8 warps per CTA) and 2049..4096 pixels (4 warps
+// per CTA, twice the shared memory per warp), so that every object with a window <= 64 x 64 is
+// handled through the compact pixel list.
+constexpr int kCapSmall = 2048, kWarpsSmall = 8;
+constexpr int kCapLarge = 4096, kWarpsLarge = 4;
+constexpr int kBins = 1024;  // level-0 histogram bins, 16-bit counters packed in pairs (4 x 128 during refinement)
 
-struct __align__(16) WSmem {
+template <int CAP>
+struct __align__(16) WSmemT {
   u64 rowmask[kSide];            // bit c of rowmask[r]: window pixel (r, c) belongs to the object
   unsigned short rowbase[kSide]; // number of object pixels in rows < r
-  unsigned short offs[kCap];     // compact list: (r << 6) | c
-  unsigned short vals[kCap];     // staged values of the current request; u8 g[64][64] in phase E
-  u32 hist[kBins];               // histogram; u64 topmask[64] in phase E
-  u32 t_key[4], t_rank[4], t_cnt[4];
-  u64 t_sum[4];
+  unsigned short offs[CAP];      // compact list: (r << 6) | c
+  unsigned short vals[CAP];      // staged values of the current request; u8 g[66][64] in phase E
+  u32 hist[kBins / 2];           // 1024 packed 16-bit counters; g overflow + u64 topmask[64] in phase E
+  u32 t_key[4], t_rank[4], t_cnt[4], t_cb[4];
 };
 
 struct Obj {
@@ -42,15 +60,15 @@ struct Obj {
   i64 lab_rs;
   u32 label, n;
   int h, w;
-  bool listed;          // compact offset list valid (n <= kCap)
+  bool listed;          // compact offset list valid (n <= CAP of the size class)
 };
 
 __device__ __forceinline__ u64 lanemask_lt64(u32 c) { return (c == 0) ? 0ull : (~0ull >> (64 - c)); }
 
 // f(r, c, i): every object pixel once; i = compact index.  Warp-uniform control flow around f is
 // NOT guaranteed (lanes without a pixel skip f).
-template <class F>
-__device__ __forceinline__ void for_each_px(const Obj& o, const WSmem& s, F&& f) {
+template <class S, class F>
+__device__ __forceinline__ void for_each_px(const Obj& o, const S& s, F&& f) {
   const u32 lane = lane_id();
   if (o.listed) {
     for (u32 i = lane; i < o.n; i += 32) {
@@ -74,40 +92,83 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
   return v;
 }
 
-// rank search in hist[0, nb): `per` consecutive bins per lane (see object_stats.cu)
-__device__ __forceinline__ void find_ranks(const u32* hist, u32 nb, u32 vbase, const u32* ranks, int n_ranks,
-                                           u32* out_key, u32* out_rank, u32* out_cnt, u64* out_sum) {
+// ---- histogram with packed 16-bit counters (counts <= 4096 per object) ------------------------
+__device__ __forceinline__ void hist_zero(u32* hist) {  // 1024 bins = 128 x uint4
+  uint4* h4 = reinterpret_cast<uint4*>(hist);
+#pragma unroll
+  for (int k = 0; k < kBins / 8 / 32; ++k) h4[lane_id() + 32 * k] = make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void hist_add(u32* hist, u32 bin) {
+  atomicAdd(&hist[bin >> 1], (bin & 1u) ? 0x10000u : 1u);
+}
+
+// Locate up to four ranks in the 16-bit histogram h16[0, nb): each lane owns `per` consecutive
+// bins (a multiple of 8, read as uint4).  For rank t: key = its bin, rank = t - (count below the
+// bin), cnt = count below the bin, cb = sum over the bins below of count * bin index.
+__device__ __forceinline__ void find_ranks16(const unsigned short* h16, u32 nb, const u32* ranks, int n_ranks,
+                                             u32* out_key, u32* out_rank, u32* out_cnt, u32* out_cb) {
   const u32 lane = lane_id();
-  const u32 per = (nb + 31) / 32;
-  const u32 b0 = lane * per, b1 = min(b0 + per, nb);
-  u32 cnt = 0;
-  u64 wsum = 0;
-  for (u32 b = b0; b < b1; ++b) {
-    const u32 c = hist[b];
-    cnt += c;
-    wsum += (u64)c * (u64)(vbase + b);
+  const u32 per = (((nb + 31u) >> 5) + 7u) & ~7u;  // 8, 16, 24 or 32
+  const u32 b0 = lane * per;
+  u32 cnt = 0, cb = 0;
+  for (u32 k = 0; k < per; k += 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(h16 + b0 + k);
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const u32 lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
+      cnt += lo + hi;
+      cb += lo * (b0 + k + 2 * j) + hi * (b0 + k + 2 * j + 1);
+    }
   }
-  u32 icnt = cnt;
-  u64 iw = wsum;
+  u32 icnt = cnt, icb = cb;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const u32 c = __shfl_up_sync(0xFFFFFFFFu, icnt, o);
-    const u64 q = __shfl_up_sync(0xFFFFFFFFu, iw, o);
-    if (lane >= (u32)o) { icnt += c; iw += q; }
+    const u32 q = __shfl_up_sync(0xFFFFFFFFu, icb, o);
+    if (lane >= (u32)o) { icnt += c; icb += q; }
   }
-  const u32 ecnt = icnt - cnt;
-  const u64 ew = iw - wsum;
+  const u32 ecnt = icnt - cnt, ecb = icb - cb;
   for (int j = 0; j < n_ranks; ++j) {
     const u32 t = ranks[j];
     if (t >= ecnt && t < ecnt + cnt) {
-      u32 acc = ecnt;
-      u64 ws = ew;
-      for (u32 b = b0; b < b1; ++b) {
-        const u32 c = hist[b];
-        if (t < acc + c) { out_key[j] = b; out_rank[j] = t - acc; out_cnt[j] = acc; out_sum[j] = ws; break; }
+      u32 acc = ecnt, accb = ecb;
+      for (u32 bq = b0; bq < b0 + per; ++bq) {
+        const u32 c = h16[bq];
+        if (t < acc + c) { out_key[j] = bq; out_rank[j] = t - acc; out_cnt[j] = acc; out_cb[j] = accb; break; }
         acc += c;
-        ws += (u64)c * (u64)(vbase + b);
+        accb += c * bq;
       }
+    }
+  }
+}
+
+// Four independent rank searches at once: eight lanes per 128-bin sub-histogram (refinement).
+__device__ __forceinline__ void find_ranks16_x4(const unsigned short* h16, const u32* ranks, u32* out_key, u32* out_rank) {
+  const u32 lane = lane_id();
+  const u32 grp = lane >> 3, sub = lane & 7u;
+  const u32 b0 = grp * 128u + sub * 16u;
+  u32 cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(h16 + b0 + k);
+    cnt += (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) +
+           (v.w & 0xFFFFu) + (v.w >> 16);
+  }
+  u32 icnt = cnt;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const u32 c = __shfl_up_sync(0xFFFFFFFFu, icnt, o, 8);
+    if (sub >= (u32)o) icnt += c;
+  }
+  const u32 ecnt = icnt - cnt;
+  const u32 t = ranks[grp];
+  if (t >= ecnt && t < ecnt + cnt) {
+    u32 acc = ecnt;
+    for (u32 bq = b0; bq < b0 + 16u; ++bq) {
+      const u32 c = h16[bq];
+      if (t < acc + c) { out_key[grp] = bq - grp * 128u; out_rank[grp] = t - acc; break; }
+      acc += c;
     }
   }
 }
@@ -126,8 +187,8 @@ __device__ __forceinline__ u32 load_reduced(const PX* __restrict__ p, int Z, i64
 // ------------------------------------------------------------------------------------------------
 // phase S: one (channel, reduction) request
 // ------------------------------------------------------------------------------------------------
-template <typename PX>
-__device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* __restrict__ px, i64 px_rs,
+template <typename PX, class S>
+__device__ __forceinline__ void request_stats(const Obj& o, S& s, const PX* __restrict__ px, i64 px_rs,
                                               i64 z_stride, int Z, const abx_request rq, u32 feats,
                                               ChanStats* __restrict__ dst) {
   const u32 lane = lane_id();
@@ -138,10 +199,11 @@ __device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* 
   const u32 n = o.n;
 
   // ---- pass 1: moments and extrema; stage values ----
+  PHASE_T0();
   ChanStats cs;
   u32 a_min = 0xFFFFFFFFu, a_max = 0;
   if (staged) {
-    // Fast path: at most kCap / 32 = 64 values per lane, each < 2^16, so 32-bit partial sums of
+    // Fast path: at most CAP / 32 <= 128 values per lane, each < 2^16, so 32-bit partial sums of
     // x, x*c, x*r and (x*x mod 2^16) are exact and the squares go through one IMAD.WIDE each.
     // Gathers are issued in batches of kBatch per lane so that their round trips overlap.
     constexpr int kBatch = 8;
@@ -217,6 +279,7 @@ __device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* 
   }
   const u32 vmin = __reduce_min_sync(0xFFFFFFFFu, a_min);
   const u32 vmax = __reduce_max_sync(0xFFFFFFFFu, a_max);
+  PHASE_ADD(1);
   cs.vmin = vmin; cs.vmax = vmax;
   cs.med_lo = cs.med_hi = 0;
   cs.top2p5_sum = cs.top5_sum = 0;
@@ -230,30 +293,44 @@ __device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* 
         for_each_px(o, s, [&](u32 r, u32 c, u32) { f(load_reduced(px + (i64)r * px_rs + c, Z, z_stride, rq.reduction)); });
       }
     };
-    // ---- pass 2: range-adaptive histogram ----
+    // ---- pass 2: range-adaptive histogram, 1024 bins of packed 16-bit counters ----
+    const unsigned short* h16 = reinterpret_cast<const unsigned short*>(s.hist);
     const u32 range = vmax - vmin;
     int s0 = 0;
     while ((range >> s0) >= (u32)kBins) ++s0;
     const u32 nb = (range >> s0) + 1;
     __syncwarp();
-    for (u32 b = lane; b < nb; b += 32) s.hist[b] = 0;
+    hist_zero(s.hist);
     __syncwarp();
-    for_each_value([&](u32 x) { atomicAdd(&s.hist[(x - vmin) >> s0], 1u); });
+    if (staged) {
+      u32 i = lane;
+      for (; i + 96 < n; i += 128) {  // four independent atomics in flight
+        const u32 x0 = s.vals[i], x1 = s.vals[i + 32], x2 = s.vals[i + 64], x3 = s.vals[i + 96];
+        hist_add(s.hist, (x0 - vmin) >> s0); hist_add(s.hist, (x1 - vmin) >> s0);
+        hist_add(s.hist, (x2 - vmin) >> s0); hist_add(s.hist, (x3 - vmin) >> s0);
+      }
+      for (; i < n; i += 32) hist_add(s.hist, ((u32)s.vals[i] - vmin) >> s0);
+    } else {
+      for_each_value([&](u32 x) { hist_add(s.hist, (x - vmin) >> s0); });
+    }
     __syncwarp();
+    PHASE_ADD(2);
     const u32 k2p5 = (u32)ceil((double)n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
     const u32 k5 = min(n, 5u);
     const u32 ranks[4] = {(n - 1) / 2, n / 2, n - k2p5, n - k5};
-    find_ranks(s.hist, nb, vmin, ranks, 4, s.t_key, s.t_rank, s.t_cnt, s.t_sum);
+    find_ranks16(h16, nb, ranks, 4, s.t_key, s.t_rank, s.t_cnt, s.t_cb);
     __syncwarp();
+    PHASE_ADD(3);
     u32 value[4];
     u64 below[2];
     if (s0 == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) value[j] = vmin + s.t_key[j];
-      below[0] = s.t_sum[2] + (u64)s.t_rank[2] * value[2];
-      below[1] = s.t_sum[3] + (u64)s.t_rank[3] * value[3];
+      // sum of the t smallest values = vmin * cnt + sum(count * bin) over the bins below + rank * value
+      below[0] = (u64)vmin * s.t_cnt[2] + s.t_cb[2] + (u64)s.t_rank[2] * value[2];
+      below[1] = (u64)vmin * s.t_cnt[3] + s.t_cb[3] + (u64)s.t_rank[3] * value[3];
     } else {
-      // ---- refinement: 7 more bits per sweep inside the four target bins ----
+      // ---- refinement: 7 more bits per sweep inside the four target bins, searched in parallel ----
       int cur = s0;
       u32 key[4], rnk[4];
 #pragma unroll
@@ -262,7 +339,7 @@ __device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* 
         const int nxt = cur > 7 ? cur - 7 : 0;
         const u32 nsub = 1u << (cur - nxt);
         __syncwarp();
-        for (u32 b = lane; b < (u32)kBins; b += 32) s.hist[b] = 0;
+        hist_zero(s.hist);
         __syncwarp();
         for_each_value([&](u32 x) {
           const u32 d = x - vmin;
@@ -270,13 +347,10 @@ __device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* 
           const u32 sb = (d >> nxt) & (nsub - 1u);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (hi == key[j]) atomicAdd(&s.hist[128 * j + sb], 1u);
+            if (hi == key[j]) hist_add(s.hist, 128u * j + sb);
         });
         __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          find_ranks(s.hist + 128 * j, nsub, 0u, &rnk[j], 1, &s.t_key[j], &s.t_rank[j], &s.t_cnt[j], &s.t_sum[j]);
-        }
+        find_ranks16_x4(h16, rnk, s.t_key, s.t_rank);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) { key[j] = (key[j] << (cur - nxt)) | s.t_key[j]; rnk[j] = s.t_rank[j]; }
@@ -299,6 +373,7 @@ __device__ __forceinline__ void request_stats(const Obj& o, WSmem& s, const PX* 
         below[1] = sb3 + (u64)(ranks[3] - cb3) * (u64)v3;
       }
     }
+    PHASE_ADD(4);
     cs.med_lo = value[0]; cs.med_hi = value[1];
     cs.top2p5_sum = cs.sum - below[0];
     cs.top5_sum = cs.sum - below[1];
@@ -321,7 +396,8 @@ __device__ __forceinline__ u32 nearest_bit_sq(u64 m, u32 c) {
   return d * d;
 }
 
-__device__ __forceinline__ void shape_edt_warp(const Obj& o, WSmem& s, u32 rmin, u32 cmin, bool want_conical,
+template <class S, bool kLaneMask>
+__device__ __forceinline__ void shape_edt_warp(const Obj& o, S& s, u32 rmin, u32 cmin, bool want_conical,
                                                ShapeStats* __restrict__ dst) {
   const u32 lane = lane_id();
   // g: row distances with one all-zero frame row above and below the window: [66][64] bytes,
@@ -364,26 +440,52 @@ __device__ __forceinline__ void shape_edt_warp(const Obj& o, WSmem& s, u32 rmin,
     }
     return best;
   };
+  PHASE_T0();
   u32 lmax = 0;
   double s_nn = 0.0;
-  for_each_px(o, s, [&](u32 r, u32 c, u32) {
-    const u32 d2 = col_min(r, c);
-    lmax = max(lmax, d2);
-    if (want_conical) s_nn += sqrt((double)d2);
-  });
+  u64 at_max = 0;  // bit j <-> the lane's j-th pixel (i = lane + 32 j) attains lmax (<= 64 pixels per lane)
+  if (kLaneMask && o.listed) {
+    u32 j = 0;
+    for (u32 i = lane; i < o.n; i += 32, ++j) {
+      const u32 k = s.offs[i];
+      const u32 d2 = col_min(k >> 6, k & 63u);
+      if (d2 > lmax) { lmax = d2; at_max = 1ull << j; }
+      else if (d2 == lmax) at_max |= 1ull << j;
+      if (want_conical) s_nn += sqrt((double)d2);
+    }
+  } else {
+    for_each_px(o, s, [&](u32 r, u32 c, u32) {
+      const u32 d2 = col_min(r, c);
+      lmax = max(lmax, d2);
+      if (want_conical) s_nn += sqrt((double)d2);
+    });
+  }
   const u32 max_nn2 = __reduce_max_sync(0xFFFFFFFFu, lmax);
+  PHASE_ADD(6);
   if (want_conical) {
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) s_nn += __shfl_xor_sync(0xFFFFFFFFu, s_nn, k);
   }
-  // ---- cone top: pixels with nn2 == max (only pixels with g^2 >= max can qualify) ----
-  for_each_px(o, s, [&](u32 r, u32 c, u32) {
-    const u32 g0 = g[((r + 1u) << 6) | c];
-    if (g0 * g0 >= max_nn2 && col_min(r, c) == max_nn2) atomicOr(reinterpret_cast<unsigned long long*>(&topmask[r]), 1ull << c);
-  });
+  // ---- cone top: pixels with nn2 == max ----
+  if (kLaneMask && o.listed) {
+    if (lmax == max_nn2) {
+      while (at_max) {
+        const u32 j = (u32)__ffsll((long long)at_max) - 1u;
+        at_max &= at_max - 1;
+        const u32 k = s.offs[lane + 32u * j];
+        atomicOr(reinterpret_cast<unsigned long long*>(&topmask[k >> 6]), 1ull << (k & 63u));
+      }
+    }
+  } else {  // only pixels with g^2 >= max can qualify: recompute those
+    for_each_px(o, s, [&](u32 r, u32 c, u32) {
+      const u32 g0 = g[((r + 1u) << 6) | c];
+      if (g0 * g0 >= max_nn2 && col_min(r, c) == max_nn2) atomicOr(reinterpret_cast<unsigned long long*>(&topmask[r]), 1ull << c);
+    });
+  }
   __syncwarp();
   const u64 tm0 = topmask[lane], tm1 = topmask[lane + 32];
   const u32 n_top = __reduce_add_sync(0xFFFFFFFFu, (u32)(__popcll(tm0) + __popcll(tm1)));
+  PHASE_ADD(7);
   // ---- EDT 2: distance of every object pixel to the nearest cone-top pixel ----
   u32 lmax2 = 0;
   if (n_top <= 32) {
@@ -497,8 +599,8 @@ __device__ __forceinline__ void shape_edt_warp(const Obj& o, WSmem& s, u32 rmin,
 }
 
 // ------------------------------------------------------------------------------------------------
-template <typename PX>
-__global__ void __launch_bounds__(kThreads, 2)
+template <typename PX, int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
 object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i64 lab_row_stride,
                    const int32_t* __restrict__ plane_tile, const int32_t* __restrict__ plane_base, int n_planes,
                    int n_objects, int n_total, const PX* __restrict__ pixels, const i64* __restrict__ tile_offset,
@@ -507,17 +609,52 @@ object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i6
                    const abx_object_rec* __restrict__ recs, ChanStats* __restrict__ chan, ShapeStats* __restrict__ shape,
                    int* __restrict__ stats_list, int* __restrict__ edt_list, u32* __restrict__ list_counts) {
   extern __shared__ __align__(16) unsigned char dyn[];
-  WSmem& s = reinterpret_cast<WSmem*>(dyn)[threadIdx.x >> 5];
+  using S = WSmemT<CAP>;
+  constexpr bool kPrimary = CAP == kCapSmall;  // the small class also zero-fills empty objects and builds the work lists
+  constexpr u32 kLo = kPrimary ? 0u : (u32)kCapSmall;
+  S& s = reinterpret_cast<S*>(dyn)[threadIdx.x >> 5];
   const u32 lane = lane_id();
 
-  for (;;) {
-    // dynamic work distribution: one atomic per object (objects differ 100x in cost)
-    int obj = 0;
-    if (lane == 0) obj = (int)atomicAdd(&list_counts[2], 1u);
-    obj = __shfl_sync(0xFFFFFFFFu, obj, 0);
-    if (obj >= n_total) break;
+  // dynamic work distribution: one atomic per object (objects differ 100x in cost); the warp always
+  // holds the NEXT object too and prefetches its label / pixel windows into L2 while it works.
+  auto fetch = [&]() -> int {
+    int v = 0;
+    if (lane == 0) v = (int)atomicAdd(&list_counts[kPrimary ? 2 : 3], 1u);
+    return __shfl_sync(0xFFFFFFFFu, v, 0);
+  };
+  auto prefetch_object = [&](int nobj) {
+    if (nobj >= n_objects) return;  // background objects go to the CTA kernels
+    const abx_object_rec nr = recs[nobj];
+    const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
+    if (nr.n <= kLo || nr.n > (u32)CAP || nh > kSide || nw > kSide) return;
+    const int np = find_plane(plane_base, n_planes, nobj);
+    const i64 tail = (i64)nw - 1;
+    for (int r = lane; r < nh; r += 32) {
+      const uint16_t* lr = labels + (i64)np * lab_plane_stride + (i64)(nr.rmin + r) * lab_row_stride + nr.cmin;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lr));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(lr + tail));
+    }
+    if (n_requests > 0) {
+      const PX* base = pixels + tile_offset[plane_tile[np]] + (i64)nr.rmin * px_row_stride + nr.cmin;
+      const int zmax = Z < 16 ? Z : 16;
+      for (int q = 0; q < n_requests; ++q) {
+        const PX* cb = base + (i64)requests[q].channel * chan_stride;
+        for (int z = 0; z < zmax; ++z)
+          for (int r = lane; r < nh; r += 32) {
+            const PX* pr = cb + (i64)z * z_stride + (i64)r * px_row_stride;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + tail));
+          }
+      }
+    }
+  };
+  int obj = fetch();
+  int nxt = obj < n_total ? fetch() : n_total;
+  for (; obj < n_total; obj = nxt, nxt = fetch()) {
+    if (nxt < n_total) prefetch_object(nxt);
     const abx_object_rec rec = recs[obj];
     const bool is_bg = obj >= n_objects;
+    if (!kPrimary && (rec.n <= kLo || rec.n > (u32)CAP)) continue;
     if (rec.n == 0) {
       for (int q = lane; q < n_requests; q += 32) {
         ChanStats z;
@@ -533,7 +670,7 @@ object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i6
     }
     const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
     if (is_bg || h > kSide || w > kSide) {  // hand over to the CTA-per-object kernels
-      if (lane == 0) {
+      if (kPrimary && lane == 0) {
         if (n_requests > 0) stats_list[atomicAdd(&list_counts[0], 1u)] = obj;
         if (!is_bg && need_edt) edt_list[atomicAdd(&list_counts[1], 1u)] = obj;
       }
@@ -545,9 +682,11 @@ object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i6
     o.n = rec.n; o.h = h; o.w = w;
     o.lab_rs = lab_row_stride;
     o.lab = labels + (i64)p * lab_plane_stride + (i64)rec.rmin * lab_row_stride + rec.cmin;
-    o.listed = rec.n <= (u32)kCap;
+    if (kPrimary && rec.n > (u32)CAP) continue;  // the large size class takes it
+    o.listed = true;
 
     // ---- phase M: row bitmasks, row bases, compact offset list ----
+    PHASE_T0();
     __syncwarp();
     {
       u32 base = 0;
@@ -581,6 +720,7 @@ object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i6
       if (lane + 32 >= (u32)h) s.rowmask[lane + 32] = 0;
     }
     __syncwarp();
+    PHASE_ADD(0);
 
     // ---- phase S ----
     if (n_requests > 0) {
@@ -593,42 +733,61 @@ object_warp_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i6
       }
     }
     // ---- phase E ----
-    if (need_edt) shape_edt_warp(o, s, rec.rmin, rec.cmin, want_conical != 0, shape + obj);
+#ifdef ABX_PHASE_TIMING
+    _pt = clock64();
+#endif
+    if (need_edt) shape_edt_warp<S, (CAP <= 2048)>(o, s, rec.rmin, rec.cmin, want_conical != 0, shape + obj);
+    PHASE_ADD(5);
   }
 }
 
 }  // namespace
 
-size_t object_warp_smem_bytes() { return sizeof(WSmem) * kWarps; }
+#ifdef ABX_PHASE_TIMING
+extern "C" int abx_debug_phase_cycles(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_phase_cycles, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
+template <typename PX, int CAP, int WARPS>
+static int launch_class(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, int n_total) {
+  const size_t smem = sizeof(WSmemT<CAP>) * WARPS;
+  static thread_local bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(object_warp_kernel<PX, CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return abx_check_cuda(e, "object_warp smem attribute");
+    done[dev] = true;
+  }
+  int grid = (n_total + WARPS - 1) / WARPS;
+  if (grid > 148 * 2) grid = 148 * 2;  // persistent: 2 CTAs per SM, warps pull objects from a counter
+  object_warp_kernel<PX, CAP, WARPS><<<grid, WARPS * 32, smem, st>>>(
+      static_cast<const uint16_t*>(a->labels), a->label_plane_stride, a->label_row_stride, a->plane_tile, a->plane_base,
+      a->n_planes, a->n_objects, n_total, static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset),
+      a->chan_stride, a->z_stride, a->row_stride, a->Z, a->requests, a->n_requests, a->need_edt, (a->need_edt & 2) != 0,
+      ws.recs, ws.chan, ws.shape, ws.stats_list, ws.edt_list, ws.list_counts);
+  return abx_check_cuda(cudaGetLastError(), "object_warp");
+}
+
+template <typename PX>
+static int launch_both(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, int n_total) {
+  int rc = launch_class<PX, kCapSmall, kWarpsSmall>(a, ws, st, n_total);
+  if (rc) return rc;
+  return launch_class<PX, kCapLarge, kWarpsLarge>(a, ws, st, n_total);
+}
 
 int launch_object_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0 || (a->n_requests == 0 && !a->need_edt)) return ABX_OK;
-  const size_t smem = object_warp_smem_bytes();
-  int grid = (n_total + kWarps - 1) / kWarps;
-  if (grid > 148 * 2) grid = 148 * 2;  // persistent: 2 CTAs per SM, warps pull objects from a counter
-  const int want_conical = (a->need_edt & 2) != 0;
-#define ABX_LAUNCH_OW(PX)                                                                                           \
-  do {                                                                                                              \
-    static thread_local bool done[64] = {false};                                                                    \
-    int dev = 0;                                                                                                    \
-    cudaGetDevice(&dev);                                                                                            \
-    if (dev < 64 && !done[dev]) {                                                                                   \
-      cudaError_t e = cudaFuncSetAttribute(object_warp_kernel<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                           (int)smem);                                                              \
-      if (e != cudaSuccess) return abx_check_cuda(e, "object_warp smem attribute");                                 \
-      done[dev] = true;                                                                                             \
-    }                                                                                                               \
-    object_warp_kernel<PX><<<grid, kThreads, smem, st>>>(                                                          \
-        static_cast<const uint16_t*>(a->labels), a->label_plane_stride, a->label_row_stride, a->plane_tile,        \
-        a->plane_base, a->n_planes, a->n_objects, n_total, static_cast<const PX*>(a->pixels),                      \
-        reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride, a->row_stride, a->Z,            \
-        a->requests, a->n_requests, a->need_edt, want_conical, ws.recs, ws.chan, ws.shape, ws.stats_list,          \
-        ws.edt_list, ws.list_counts);                                                                              \
-  } while (0)
-  if (a->n_requests == 0 || a->pixel_dtype == ABX_U16) ABX_LAUNCH_OW(uint16_t);
-  else if (a->pixel_dtype == ABX_U8) ABX_LAUNCH_OW(uint8_t);
-  else return abx_set_error(ABX_ERR_UNSUPPORTED, "object_warp: pixel dtype %d has no kernel", a->pixel_dtype);
-#undef ABX_LAUNCH_OW
-  return abx_check_cuda(cudaGetLastError(), "object_warp");
+  if (a->n_requests == 0 || a->pixel_dtype == ABX_U16) return launch_both<uint16_t>(a, ws, st, n_total);
+  if (a->pixel_dtype == ABX_U8) return launch_both<uint8_t>(a, ws, st, n_total);
+  return abx_set_error(ABX_ERR_UNSUPPORTED, "object_warp: pixel dtype %d has no kernel", a->pixel_dtype);
 }

@@ -114,19 +114,112 @@ class ExtractionTable:
         return pa.table(data)
 
 
-def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | None = None) -> ExtractionTable:
-    """Fast public entry point: tree + host (or device) arrays in, dense per-object table out.
-
-    Does what ``process_tree_masks`` + ``extract_tree`` + the pivot of ``format_extraction`` do
-    (extract.py:240-375, 574-598) without materialising the |objects| x |instructions| Python
-    lists: labels and pixels are uploaded once, the per-plane label maxima are found on the
-    device (the reference's ``masks.max()``, extract.py:279), one ``abx_extract`` call fills the
-    table and a single device-to-host copy returns it."""
+def _label_max(labels_dev, device):
+    """Per-plane maximum label on the device (the reference's ``masks.max()``, extract.py:279)."""
     import ctypes as C
 
     import torch
 
     from . import _native as nat
+
+    P, H, W = labels_dev.shape
+    nmax = torch.empty(P, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        nat.check(
+            nat.lib().abx_label_max(
+                labels_dev.data_ptr(), nat.U16, P, H, W, labels_dev.stride(0), labels_dev.stride(1), nmax.data_ptr(),
+                C.c_void_p(torch.cuda.current_stream(device).cuda_stream),
+            ),
+            "abx_label_max",
+        )
+    return nmax
+
+
+_copy_streams: dict = {}
+
+
+def _copy_stream(device):
+    import torch
+
+    key = str(device)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
+def _host_u16(plane) -> "np.ndarray":
+    plane = np.asarray(plane)
+    if plane.dtype != np.uint16:
+        if plane.size and (plane.min() < 0 or plane.max() > 65535):
+            raise OverflowError("label ids must fit uint16 (segment/dispatch.py:14-19 enforces the same)")
+        plane = plane.astype(np.uint16)
+    return np.ascontiguousarray(plane)
+
+
+def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
+    """Host arrays in, host table out, with the uploads of later tiles overlapping the kernels of
+    earlier ones: all H2D copies are queued on a copy stream (asynchronous when the arrays are
+    pinned), each chunk of tiles is extracted as soon as its copy has landed, and its table goes
+    back with an asynchronous D2H copy.  Returns ``(values (n, dense columns), n_labels per kept tile)``."""
+    import torch
+
+    T, C_, Z_, Y, X = pixels.shape
+    tile_bytes = C_ * Z_ * Y * X * pixels.dtype.itemsize
+    per_chunk = max(1, int(chunk_bytes // max(1, tile_bytes)))
+    chunks = [keep[i : i + per_chunk] for i in range(0, len(keep), per_chunk)]
+    cur = torch.cuda.current_stream(device)
+    cps = _copy_stream(device)
+    cps.wait_stream(cur)  # buffers handed out by the caching allocator may still be in use on `cur`
+    staged = []
+    with torch.cuda.stream(cps):
+        for tiles in chunks:
+            lab = torch.empty((len(tiles), Y, X), dtype=torch.uint16, device=device)
+            for j, t in enumerate(tiles):
+                lab[j].copy_(torch.from_numpy(_host_u16(masks[t])), non_blocking=True)
+            if plan.requests:
+                consecutive = tiles == list(range(tiles[0], tiles[0] + len(tiles)))
+                src = pixels[tiles[0] : tiles[0] + len(tiles)] if consecutive else pixels[tiles]
+                px = torch.empty(src.shape, dtype=getattr(torch, str(src.dtype)), device=device)
+                px.copy_(torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
+            else:
+                px = torch.empty(0, dtype=torch.uint16, device=device)
+            ev = torch.cuda.Event()
+            ev.record(cps)
+            staged.append((tiles, lab, px, ev))
+    outs, n_all = [], []
+    for tiles, lab, px, ev in staged:
+        cur.wait_event(ev)
+        nmax_host = torch.empty(len(tiles), dtype=torch.int32, pin_memory=True)
+        nmax_host.copy_(_label_max(lab, device), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        done.synchronize()  # the row count has to reach the host; later uploads keep running meanwhile
+        n_labels = nmax_host.numpy().astype(np.int64)
+        n_all.append(n_labels)
+        offs = np.arange(len(tiles), dtype=np.int64) * (C_ * Z_ * Y * X)
+        table = engine.run_planes(plan, lab, np.arange(len(tiles), dtype=np.int32), n_labels, px, offs,
+                                  Z_ * Y * X, Y * X, X, C_, Z_)
+        host = torch.empty(table.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(table, non_blocking=True)
+        outs.append((host, table))
+    cur.synchronize()
+    values = np.concatenate([h.numpy() for h, _ in outs]) if outs else np.zeros((0, plan.n_columns))
+    return values, np.concatenate(n_all) if n_all else np.zeros(0, np.int64)
+
+
+def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | None = None,
+                  chunk_bytes: int = 48 << 20) -> ExtractionTable:
+    """Fast public entry point: tree + host (or device) arrays in, dense per-object table out.
+
+    Does what ``process_tree_masks`` + ``extract_tree`` + the pivot of ``format_extraction`` do
+    (extract.py:240-375, 574-598) without materialising the |objects| x |instructions| Python
+    lists.  Host inputs are uploaded in chunks of tiles on a copy stream while earlier chunks are
+    being extracted (pinned arrays make the copies asynchronous); the per-plane label maxima are
+    found on the device (the reference's ``masks.max()``, extract.py:279), one ``abx_extract`` call
+    per chunk fills the table and an asynchronous device-to-host copy returns it."""
+    import torch
+
+    from .tile import TileView
 
     masks = _as_mask_list(masks)
     plan = plan or engine.compile_tree(tree)
@@ -138,38 +231,29 @@ def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | No
     names = ["/".join(str(x) for x in inst) + f"/{inst[-1]}" for inst in plan.instructions]
     if not keep:
         return ExtractionTable(np.zeros((0, 2), np.int64), names, np.zeros((0, len(names))))
-    if isinstance(masks[keep[0]], torch.Tensor):
-        labels_dev = torch.stack([masks[i] for i in keep]).to(device)
+    host_inputs = isinstance(pixels, np.ndarray) and not isinstance(masks[keep[0]], torch.Tensor)
+    if host_inputs:
+        if plan.requests and pixels.dtype not in (np.uint8, np.uint16):
+            raise NotImplementedError(
+                f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200 (uint8/uint16 only) and there is no CPU fallback"
+            )
+        values, n_labels = _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes)
     else:
-        labels_dev = _to_device_labels([np.asarray(masks[i]) for i in keep], device)
-    P, H, W = labels_dev.shape
-    nmax = torch.empty(P, dtype=torch.int32, device=device)
-    with torch.cuda.device(device):
-        nat.check(
-            nat.lib().abx_label_max(
-                labels_dev.data_ptr(), nat.U16, P, H, W, labels_dev.stride(0), labels_dev.stride(1), nmax.data_ptr(),
-                C.c_void_p(torch.cuda.current_stream(device).cuda_stream),
-            ),
-            "abx_label_max",
-        )
-    from .tile import TileView
-
-    if isinstance(pixels, TileView):
-        px_dev, offs, cs, zs, rs, C_, Z_ = pixels.addressing(device)
-    else:
-        if isinstance(pixels, np.ndarray):
-            if pixels.dtype not in (np.uint8, np.uint16):
-                raise NotImplementedError(f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200")
-            px_dev = torch.from_numpy(pixels).to(device, non_blocking=True)
+        if isinstance(masks[keep[0]], torch.Tensor):
+            labels_dev = torch.stack([masks[i] for i in keep]).to(device)
         else:
-            px_dev = pixels.to(device)
-        px_dev = px_dev.contiguous()
-        T, C_, Z_, Y, X = px_dev.shape
-        offs = np.arange(T, dtype=np.int64) * (C_ * Z_ * Y * X)
-        cs, zs, rs = Z_ * Y * X, Y * X, X
-    n_labels = nmax.cpu().numpy().astype(np.int64)  # small D2H: the row count has to reach the host
-    table = engine.run_planes(plan, labels_dev, np.asarray(keep, dtype=np.int32), n_labels, px_dev, offs, cs, zs, rs, C_, Z_)
-    values = table.cpu().numpy()
+            labels_dev = _to_device_labels([np.asarray(masks[i]) for i in keep], device)
+        nmax = _label_max(labels_dev, device)
+        if isinstance(pixels, TileView):
+            px_dev, offs, cs, zs, rs, C_, Z_ = pixels.addressing(device)
+        else:
+            px_dev = pixels.to(device).contiguous()
+            T, C_, Z_, Y, X = px_dev.shape
+            offs = np.arange(T, dtype=np.int64) * (C_ * Z_ * Y * X)
+            cs, zs, rs = Z_ * Y * X, Y * X, X
+        n_labels = nmax.cpu().numpy().astype(np.int64)  # small D2H: the row count has to reach the host
+        table = engine.run_planes(plan, labels_dev, np.asarray(keep, dtype=np.int32), n_labels, px_dev, offs, cs, zs, rs, C_, Z_)
+        values = table.cpu().numpy()
     cols = np.fromiter((c[0] for c in plan.inst_cols), dtype=np.int64, count=len(plan.inst_cols))
     objects = np.stack(
         [np.repeat(np.asarray(keep, dtype=np.int64), n_labels), np.concatenate([np.arange(1, k + 1) for k in n_labels])],

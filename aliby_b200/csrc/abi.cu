@@ -58,6 +58,8 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   ws->err = reinterpret_cast<u32*>(b + off);
   ws->list_counts = ws->err + 1;
   off = align_up(off + 8 * sizeof(u32));
+  ws->sqrt_tab = reinterpret_cast<double*>(b + off);
+  off = align_up(off + (a->need_edt ? (size_t)abx_sqrt_table_entries() * sizeof(double) : 0));
   ws->stats_list = reinterpret_cast<int*>(b + off);
   off = align_up(off + n_rec * sizeof(int));
   ws->edt_list = reinterpret_cast<int*>(b + off);

@@ -40,7 +40,8 @@ struct Workspace {
   u32* err;          // [0] error flags, [1] stats_list length, [2] edt_list length
   int* stats_list;   // objects the warp kernel handed to the CTA statistics kernel
   int* edt_list;     // objects the warp kernel handed to the CTA EDT kernel
-  u32* list_counts;  // = err + 1
+  u32* list_counts;  // = err + 1: [0] stats_list length, [1] edt_list length, [2..3] / [4..5] work counters
+  double* sqrt_tab;  // sqrt(d2) of every squared distance the warp EDT can produce
   size_t total;
 };
 
@@ -54,6 +55,7 @@ int launch_object_warp(const abx_extract_args* a, const Workspace& ws, cudaStrea
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int abx_sqrt_table_entries();
 
 constexpr int kEdtLargeCtas = 8;           // CTAs that own a whole-plane EDT scratch slot
 constexpr int kEdtSmemWindow = 96 * 96;    // padded window (pixels) that is handled in shared memory

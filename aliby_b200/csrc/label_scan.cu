@@ -4,12 +4,11 @@
 // Replaces the one-hot expansion of src/agora/utils/masks.py:35-37 (L*Y*X bytes) and
 // the full-plane products of cell.py:18-27 (area) and cell.py:282-303 (centroid).
 //
-// Mapping: a warp owns a 256-pixel row chunk per iteration.  The chunk is staged in shared
-// memory with one 128-bit load per lane, then read back with a stride-32 mapping so that the
-// eight ballots of "this pixel starts a run" form a 256-bit mask in pixel order.  The lane
-// that owns a run start finds the run end with bit scans and issues the atomics: one lane
-// per label run, no shuffles.  Bounding-box atomics are skipped when one 128-bit read of the
-// record (possibly stale, hence conservative) shows they cannot change it.
+// Mapping: see label_scan_kernel — lanes walk down 8-pixel column strips with 128-bit coalesced
+// loads and keep the object they are inside of in registers; one set of global atomics per
+// (strip, band, object).  The first version (one warp per 256-pixel row chunk, one set of atomics
+// per row run) executed 2.35 warp instructions per pixel and ran at 0.6 TB/s
+// (profiles/r01e_summary.md).
 #include "common.cuh"
 
 namespace {
@@ -33,90 +32,154 @@ __global__ void init_records_kernel(abx_object_rec* recs, int n_objects, int n_p
   }
 }
 
-__device__ __forceinline__ void emit_run(abx_object_rec* __restrict__ recs, int base, u32 n_labels, u32 label,
-                                         u32 row, u32 cs, u32 ce, u32* err) {
-  if (label > n_labels) { atomicOr(err, 1u); return; }
-  abx_object_rec* rec = recs + base + (label - 1);
-  const u32 count = ce - cs + 1;
-  atomicAdd(&rec->n, count);
-  atomicAdd(reinterpret_cast<u64*>(&rec->sum_row), (u64)count * (u64)(row + 1));
-  atomicAdd(reinterpret_cast<u64*>(&rec->sum_col), ((u64)(cs + 1) + (u64)(ce + 1)) * (u64)count / 2);
-  // bbox: the fields are monotone, so a stale read can only cause a redundant atomic
-  const uint4 bb = __ldcg(reinterpret_cast<const uint4*>(&rec->rmin));  // rmin, rmax, cmin, cmax
-  if (row < bb.x) atomicMin(&rec->rmin, row);
-  if (row > bb.y) atomicMax(&rec->rmax, row);
-  if (cs < bb.z) atomicMin(&rec->cmin, cs);
-  if (ce > bb.w) atomicMax(&rec->cmax, ce);
+// One object piece found by a lane: `n` pixels, coordinate sums and bounding box in plane coordinates.
+struct Piece {
+  u32 label, n, sum_row, sum_col;  // sums of (row + 1) and (col + 1)
+  u32 rmin, rmax, cmask;           // cmask: bit j <-> column c0 + j holds a pixel of the piece
+};
+
+__device__ __forceinline__ void emit_piece(abx_object_rec* __restrict__ recs, int base, u32 n_labels, const Piece& p,
+                                           u32 c0, u32* err) {
+  if (p.label > n_labels) { atomicOr(err, 1u); return; }
+  abx_object_rec* rec = recs + base + (p.label - 1);
+  atomicAdd(&rec->n, p.n);
+  atomicAdd(reinterpret_cast<u64*>(&rec->sum_row), (u64)p.sum_row);
+  atomicAdd(reinterpret_cast<u64*>(&rec->sum_col), (u64)p.sum_col);
+  atomicMin(&rec->rmin, p.rmin);
+  atomicMax(&rec->rmax, p.rmax);
+  atomicMin(&rec->cmin, c0 + (u32)__ffs(p.cmask) - 1u);
+  atomicMax(&rec->cmax, c0 + 31u - (u32)__clz(p.cmask));
 }
+
+// bit j of the result <-> halfword j of (w0..w3) equals `label`
+__device__ __forceinline__ u32 eq_mask8(const u32 (&w)[4], u32 label) {
+  const u32 pair = label | (label << 16);
+  u32 m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u32 x = w[j] ^ pair;
+    m |= ((x & 0xFFFFu) == 0u ? 1u : 0u) << (2 * j);
+    m |= ((x >> 16) == 0u ? 2u : 0u) << (2 * j);
+  }
+  return m;
+}
+
+__device__ __forceinline__ u32 bitpos_sum8(u32 m) {  // sum of the positions of the set bits of an 8-bit mask
+  return (u32)__popc(m & 0xAAu) + 2u * (u32)__popc(m & 0xCCu) + 4u * (u32)__popc(m & 0xF0u);
+}
+
+// Column-strip walker.  A warp owns a band of kBandRows rows x 256 columns; lane l walks DOWN the
+// 8-pixel strip [c0, c0 + 8) with one 128-bit load per row (the 32 lanes of a row form one coalesced
+// 512-byte request), keeping the object it is inside of in registers: a row whose 8 labels all equal
+// the current label costs a handful of instructions, and an object is flushed to its global record
+// with one set of atomics per (strip, band) instead of one per row run.
+constexpr int kBandRows = 32;
+constexpr int kRowBatch = 8;  // rows whose loads are in flight together
 
 __global__ void __launch_bounds__(kScanThreads)
 label_scan_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int W, i64 plane_stride, i64 row_stride,
                   const int32_t* __restrict__ plane_base, abx_object_rec* __restrict__ recs, int n_objects,
-                  int with_bg, int vec_ok, u32* err) {
-  __shared__ __align__(16) uint16_t stage_all[kScanWarps][256];
-  uint16_t* stage = stage_all[threadIdx.x >> 5];
+                  int vec_ok, u32* err) {
   const u32 lane = lane_id();
   const i64 gwarp = (i64)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
   const i64 nwarps = (i64)gridDim.x * kScanWarps;
-  const int chunks_per_row = (W + 255) >> 8;
-  const i64 total = (i64)n_planes * H * chunks_per_row;
-  u32 bg_count = 0;  // warp-uniform
-  int bg_plane = -1;
+  const int col_groups = (W + 255) >> 8;
+  const int bands = (H + kBandRows - 1) / kBandRows;
+  const i64 total = (i64)n_planes * bands * col_groups;
 
-  for (i64 chunk = gwarp; chunk < total; chunk += nwarps) {
-    const int cx = (int)(chunk % chunks_per_row);
-    const i64 t = chunk / chunks_per_row;
-    const u32 row = (u32)(t % H);
-    const int p = (int)(t / H);
-    if (with_bg && p != bg_plane) {  // flush the background count of the previous plane
-      if (lane == 0 && bg_plane >= 0 && bg_count) atomicAdd(&recs[n_objects + bg_plane].n, bg_count);
-      bg_count = 0;
-      bg_plane = p;
-    }
-    const u32 cbase = (u32)cx * 256u;
-    const int len = min(256, W - (int)cbase);  // valid pixels of this chunk
-    const uint16_t* src = labels + (i64)p * plane_stride + (i64)row * row_stride + cbase;
-    __syncwarp();
-    {
-      const int o = (int)lane * 8;
-      if (vec_ok && o + 8 <= len) {
-        *reinterpret_cast<uint4*>(stage + o) = __ldg(reinterpret_cast<const uint4*>(src + o));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (o + i < len) stage[o + i] = __ldg(src + o + i);
-      }
-    }
-    __syncwarp();
-    // run starts in pixel order: bit `lane` of sflag[k] <-> pixel 32 k + lane
-    u32 sflag[8], mine[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int q = 32 * k + (int)lane;
-      const bool valid = q < len;
-      const u32 cur = valid ? (u32)stage[q] : 0u;
-      const u32 prev = (valid && q > 0) ? (u32)stage[q - 1] : 0xFFFFFFFFu;
-      mine[k] = cur;
-      sflag[k] = __ballot_sync(0xFFFFFFFFu, valid && cur != prev);
-      if (with_bg) bg_count += __popc(__ballot_sync(0xFFFFFFFFu, valid && cur == 0u));
-    }
+  for (i64 unit = gwarp; unit < total; unit += nwarps) {
+    const int cg = (int)(unit % col_groups);
+    const i64 t = unit / col_groups;
+    const int band = (int)(t % bands);
+    const int p = (int)(t / bands);
+    const u32 c0 = (u32)cg * 256u + lane * 8u;
+    if (c0 >= (u32)W) continue;
+    const bool full = vec_ok && c0 + 8u <= (u32)W;  // aligned 128-bit loads are legal for this strip
+    const int r_begin = band * kBandRows, r_end = min(H, r_begin + kBandRows);
+    const uint16_t* src = labels + (i64)p * plane_stride + c0;
     const int base = plane_base[p];
     const u32 n_labels = (u32)(plane_base[p + 1] - base);
+
+    Piece cur;
+    cur.label = 0; cur.n = 0; cur.sum_row = 0; cur.sum_col = 0; cur.rmin = 0; cur.rmax = 0; cur.cmask = 0;
+    for (int r0 = r_begin; r0 < r_end; r0 += kRowBatch) {
+      uint4 q[kRowBatch];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (!((sflag[k] >> lane) & 1u) || mine[k] == 0u) continue;
-      // run end = next start - 1 (or the end of the chunk)
-      u32 nxt = (lane == 31) ? 0u : (sflag[k] & ~((2u << lane) - 1u));
-      int endq = -1;
-      if (nxt) endq = 32 * k + __ffs(nxt) - 1;
+      for (int u = 0; u < kRowBatch; ++u) {
+        const int r = r0 + u;
+        q[u] = make_uint4(0, 0, 0, 0);
+        if (r < r_end) {
+          const uint16_t* row = src + (i64)r * row_stride;
+          if (full) {
+            q[u] = __ldg(reinterpret_cast<const uint4*>(row));
+          } else {  // ragged right edge or unaligned rows: element loads, zero beyond the plane
+            u32 e[8];
 #pragma unroll
-      for (int kk = 1; kk < 8; ++kk)
-        if (k + kk < 8 && endq < 0 && sflag[(k + kk) & 7]) endq = 32 * (k + kk) + __ffs(sflag[(k + kk) & 7]) - 1;
-      if (endq < 0 || endq > len) endq = len;
-      emit_run(recs, base, n_labels, mine[k], row, cbase + 32u * k + lane, cbase + (u32)endq - 1u, err);
+            for (int j = 0; j < 8; ++j) e[j] = (c0 + j < (u32)W) ? (u32)__ldg(row + j) : 0u;
+            q[u] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRowBatch; ++u) {
+        const u32 r = (u32)(r0 + u);
+        if ((int)r >= r_end) break;
+        const u32 w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        const u32 pair = cur.label | (cur.label << 16);
+        if (((w[0] ^ pair) | (w[1] ^ pair) | (w[2] ^ pair) | (w[3] ^ pair)) == 0u) {  // all 8 == current label
+          if (cur.label) {
+            cur.n += 8u; cur.sum_row += 8u * (r + 1u); cur.sum_col += 8u * c0 + 36u;
+            cur.cmask = 0xFFu; cur.rmax = r;
+          }
+          continue;
+        }
+        u32 rest = 0xFFu & ~eq_mask8(w, 0u);  // labelled pixels of this row
+        if (cur.label) {
+          const u32 m = eq_mask8(w, cur.label);
+          if (m) {
+            const u32 k = (u32)__popc(m);
+            cur.n += k; cur.sum_row += k * (r + 1u); cur.sum_col += k * (c0 + 1u) + bitpos_sum8(m);
+            cur.cmask |= m; cur.rmax = r;
+            rest &= ~m;
+          } else {  // the object ended above this row
+            emit_piece(recs, base, n_labels, cur, c0, err);
+            cur.label = 0;
+          }
+        }
+        while (rest) {  // other labels inside the 8 pixels
+          const u32 pos = (u32)__ffs(rest) - 1u;
+          const u32 wsel = pos < 4u ? (pos < 2u ? w[0] : w[1]) : (pos < 6u ? w[2] : w[3]);
+          const u32 lbl = (wsel >> ((pos & 1u) << 4)) & 0xFFFFu;
+          const u32 m = eq_mask8(w, lbl);
+          const u32 k = (u32)__popc(m);
+          Piece np;
+          np.label = lbl; np.n = k; np.sum_row = k * (r + 1u); np.sum_col = k * (c0 + 1u) + bitpos_sum8(m);
+          np.rmin = r; np.rmax = r; np.cmask = m;
+          if (cur.label == 0) cur = np;                           // becomes the tracked object
+          else emit_piece(recs, base, n_labels, np, c0, err);     // second object in the strip: per-row piece
+          rest &= ~m;
+        }
+      }
     }
+    if (cur.label) emit_piece(recs, base, n_labels, cur, c0, err);
   }
-  if (with_bg && lane == 0 && bg_plane >= 0 && bg_count) atomicAdd(&recs[n_objects + bg_plane].n, bg_count);
+}
+
+// background pixel count of every plane = H * W - labelled pixels (label 0 is never accumulated)
+__global__ void background_count_kernel(abx_object_rec* __restrict__ recs, const int32_t* __restrict__ plane_base,
+                                        int n_objects, int H, int W) {
+  __shared__ u32 part[8];
+  const int p = blockIdx.x;
+  u32 s = 0;
+  for (int i = plane_base[p] + threadIdx.x; i < plane_base[p + 1]; i += blockDim.x) s += recs[i].n;
+  s = __reduce_add_sync(0xFFFFFFFFu, s);
+  if (lane_id() == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 tot = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += part[k];
+    recs[n_objects + p].n = (u32)H * (u32)W - tot;
+  }
 }
 
 __global__ void label_max_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int W, i64 plane_stride,
@@ -138,17 +201,18 @@ __global__ void label_max_kernel(const uint16_t* __restrict__ labels, int n_plan
 int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, cudaStream_t st) {
   const int n_rec = a->n_objects + a->n_planes;
   init_records_kernel<<<(n_rec + 255) / 256, 256, 0, st>>>(recs, a->n_objects, a->n_planes, a->H, a->W, err);
-  const i64 chunks = (i64)a->n_planes * a->H * ((a->W + 255) / 256);
-  if (chunks == 0) return abx_check_cuda(cudaGetLastError(), "init_records");
-  const int warps_per_block = kScanWarps;
-  i64 blocks = (chunks + warps_per_block - 1) / warps_per_block;
-  const i64 cap = 148 * 8 * 4;  // a few waves of 8 resident CTAs per SM
+  const i64 units = (i64)a->n_planes * ((a->H + kBandRows - 1) / kBandRows) * ((a->W + 255) / 256);
+  if (units == 0) return abx_check_cuda(cudaGetLastError(), "init_records");
+  i64 blocks = (units + kScanWarps - 1) / kScanWarps;
+  const i64 cap = 148 * 8;  // 8 CTAs of 8 warps per SM; more units than that are walked in a grid-stride loop
   if (blocks > cap) blocks = cap;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(a->labels) & 15u) == 0) && (a->label_row_stride % 8 == 0) &&
                      (a->label_plane_stride % 8 == 0);
   label_scan_kernel<<<(int)blocks, kScanThreads, 0, st>>>(
       static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,
-      a->plane_base, recs, a->n_objects, a->with_background, vec_ok, err);
+      a->plane_base, recs, a->n_objects, vec_ok, err);
+  if (a->with_background)
+    background_count_kernel<<<a->n_planes, 256, 0, st>>>(recs, a->plane_base, a->n_objects, a->H, a->W);
   return abx_check_cuda(cudaGetLastError(), "label_scan");
 }
 

@@ -78,18 +78,19 @@ __device__ __noinline__ void build_list(const Obj& o, unsigned short* __restrict
   const u32 lt = (1u << lane) - 1u;
   const bool two = o.w > 32;
   u32 base = 0;
+  constexpr int kRows = 8;  // label rows in flight per iteration (16 loads per lane)
 #pragma unroll 1
-  for (int r0 = 0; r0 < o.h; r0 += 4) {
-    u32 l0[4], l1[4];
+  for (int r0 = 0; r0 < o.h; r0 += kRows) {
+    u32 l0[kRows], l1[kRows];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {  // all loads of the row group first
+    for (int u = 0; u < kRows; ++u) {  // all loads of the row group first
       const uint16_t* lrow = o.lab + (i64)(r0 + u) * o.lab_rs;
       const bool in = r0 + u < o.h;
       l0[u] = (in && lane < (u32)o.w) ? (u32)__ldg(lrow + lane) : kFull;
       l1[u] = (in && two && lane + 32 < (u32)o.w) ? (u32)__ldg(lrow + lane + 32) : kFull;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kRows; ++u) {
       const int r = r0 + u;
       if (r >= o.h) break;
       const bool hit0 = l0[u] == o.label, hit1 = l1[u] == o.label;
@@ -238,56 +239,71 @@ struct ValueSource {  // value i of the current request
 };
 
 // pass 1: moments and extrema of one request; values staged when they fit 16 bits (kWide = false).
-// kWide (Z reduction "add"): 64-bit accumulators, nothing staged.
+// kWide (Z reduction "add"): 64-bit accumulators, nothing staged.  The gather is software-pipelined:
+// the loads of batch b + 1 are in flight while batch b is accumulated.
 template <typename PX, bool kWide>
-__device__ __noinline__ void moments_pass(u32 n, const unsigned short* __restrict__ offs, unsigned short* __restrict__ vals,
+__device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __restrict__ offs, unsigned short* __restrict__ vals,
                                              const PX* __restrict__ px, u32 rs, i64 z_stride, int Z, int red,
                                              bool want_moi, ChanStats& cs) {
   using Acc = typename std::conditional<kWide, u64, u32>::type;
   constexpr u32 kWrapMask = (sizeof(PX) == 1) ? 0xFFu : 0xFFFFu;
   constexpr int kBatch = 8;
+  constexpr u32 kNone = 0xFFFFu;
   const u32 lane = lane_id();
   Acc f_sum = 0, f_wrap = 0, f_m10 = 0, f_m01 = 0;
   u64 f_sq = 0, f_m20 = 0, f_m02 = 0;
   u32 a_min = kFull, a_max = 0;
-#pragma unroll 1
-  for (u32 i0 = lane; i0 < n; i0 += 32 * kBatch) {
-    u32 k[kBatch], x[kBatch];
+  u32 k[kBatch], x[kBatch];
+  auto load_batch = [&](u32 i0, u32 (&kq)[kBatch], u32 (&xq)[kBatch]) {
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const u32 i = i0 + 32u * u;
-      k[u] = (i < n) ? (u32)offs[i] : 0xFFFFu;
+      kq[u] = (i < n) ? (u32)offs[i] : kNone;
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
-      x[u] = (k[u] != 0xFFFFu) ? (u32)__ldg(px + ((k[u] >> 6) * rs + (k[u] & 63u))) : 0u;
+      xq[u] = (kq[u] != kNone) ? (u32)__ldg(px + ((kq[u] >> 6) * rs + (kq[u] & 63u))) : 0u;
+    if (Z > 1) {
 #pragma unroll 1
-    for (int z = 1; z < Z; ++z) {
-      const PX* pz = px + (i64)z * z_stride;
+      for (int z = 1; z < Z; ++z) {
+        const PX* pz = px + (i64)z * z_stride;
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u)
-        if (k[u] != 0xFFFFu) {
-          const u32 y = (u32)__ldg(pz + ((k[u] >> 6) * rs + (k[u] & 63u)));
-          x[u] = (red == ABX_RED_MAX) ? max(x[u], y) : x[u] + y;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const bool ok = k[u] != 0xFFFFu;
-      const u32 v = x[u];
-      f_sum += v;
-      f_sq += (u64)v * (u64)v;
-      if (!kWide) f_wrap += (v * v) & kWrapMask;
-      a_min = min(a_min, ok ? v : kFull);
-      a_max = max(a_max, v);
-      if (want_moi) {
-        const u32 c = k[u] & 63u, r = (k[u] >> 6) & 63u;
-        const Acc xc = (Acc)v * c, xr = (Acc)v * r;
-        f_m10 += xc; f_m01 += xr;
-        f_m20 += (u64)xc * (u64)c; f_m02 += (u64)xr * (u64)r;
+        for (int u = 0; u < kBatch; ++u)
+          if (kq[u] != kNone) {
+            const u32 y = (u32)__ldg(pz + ((kq[u] >> 6) * rs + (kq[u] & 63u)));
+            xq[u] = (red == ABX_RED_MAX) ? max(xq[u], y) : xq[u] + y;
+          }
       }
-      if (!kWide && ok) vals[i0 + 32u * u] = (unsigned short)v;
     }
+  };
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) { k[u] = kNone; x[u] = 0; }
+  // iteration j loads batch j and accumulates batch j - 1 (one copy of each body in the code)
+#pragma unroll 1
+  for (int i0 = (int)lane - 32 * kBatch; i0 < (int)n; i0 += 32 * kBatch) {
+    u32 kn[kBatch], xn[kBatch];
+    load_batch((u32)(i0 + 32 * kBatch), kn, xn);  // indices >= n load nothing
+    if (i0 >= 0) {                                // warp-uniform
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const bool ok = k[u] != kNone;
+        const u32 v = x[u];
+        f_sum += v;
+        f_sq += (u64)v * (u64)v;
+        if (!kWide) f_wrap += (v * v) & kWrapMask;
+        a_min = min(a_min, ok ? v : kFull);
+        a_max = max(a_max, v);
+        if (want_moi) {
+          const u32 c = k[u] & 63u, r = (k[u] >> 6) & 63u;
+          const Acc xc = (Acc)v * c, xr = (Acc)v * r;
+          f_m10 += xc; f_m01 += xr;
+          f_m20 += (u64)xc * (u64)c; f_m02 += (u64)xr * (u64)r;
+        }
+        if (!kWide && ok) vals[(u32)i0 + 32u * u] = (unsigned short)v;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) { k[u] = kn[u]; x[u] = xn[u]; }
   }
   cs.sum = warp_sum64((u64)f_sum);
   cs.sumsq = warp_sum64(f_sq);
@@ -302,6 +318,12 @@ __device__ __noinline__ void moments_pass(u32 n, const unsigned short* __restric
   cs.vmax = __reduce_max_sync(kFull, a_max);
 }
 
+template <typename PX>
+__device__ __noinline__ void moments_wide(u32 n, const unsigned short* __restrict__ offs, const PX* __restrict__ px, u32 rs,
+                                          i64 z_stride, int Z, int red, bool want_moi, ChanStats& cs) {
+  moments_pass<PX, true>(n, offs, nullptr, px, rs, z_stride, Z, red, want_moi, cs);
+}
+
 // ------------------------------------------------------------------------------------------------
 // phase S: one (channel, reduction) request
 // ------------------------------------------------------------------------------------------------
@@ -314,7 +336,7 @@ __device__ __noinline__ void request_stats(u32 n, const unsigned short* __restri
   const bool wide = rq.reduction == ABX_RED_ADD && Z > 1;
   const u32 feats = rq.features;
   ChanStats cs;
-  if (wide) moments_pass<PX, true>(n, offs, vals, px, rs, z_stride, Z, rq.reduction, (feats & ABX_F_MOI) != 0, cs);
+  if (wide) moments_wide<PX>(n, offs, px, rs, z_stride, Z, rq.reduction, (feats & ABX_F_MOI) != 0, cs);
   else moments_pass<PX, false>(n, offs, vals, px, rs, z_stride, Z, rq.reduction, (feats & ABX_F_MOI) != 0, cs);
   cs.med_lo = cs.med_hi = 0;
   cs.top2p5_sum = cs.top5_sum = 0;
@@ -331,8 +353,20 @@ __device__ __noinline__ void request_stats(u32 n, const unsigned short* __restri
     __syncwarp();
     hist_zero(hist);
     __syncwarp();
+    if (!wide) {  // staged values, two per 32-bit shared-memory load
+      const u32* v32 = reinterpret_cast<const u32*>(vals);
+      const u32 pairs = n >> 1;
 #pragma unroll 4
-    for (u32 i = lane; i < n; i += 32) hist_add(hist, (value(i) - vmin) >> s0);
+      for (u32 w = lane; w < pairs; w += 32) {
+        const u32 xx = v32[w];
+        hist_add(hist, ((xx & 0xFFFFu) - vmin) >> s0);
+        hist_add(hist, ((xx >> 16) - vmin) >> s0);
+      }
+      if ((n & 1u) && lane == 0) hist_add(hist, ((u32)vals[n - 1] - vmin) >> s0);
+    } else {
+#pragma unroll 1
+      for (u32 i = lane; i < n; i += 32) hist_add(hist, (value(i) - vmin) >> s0);
+    }
     __syncwarp();
     const u32 k2p5 = (u32)ceil((double)n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
     const u32 k5 = min(n, 5u);

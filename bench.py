@@ -353,16 +353,18 @@ def ours(args):
     def e2e_step():
         return extract.extract_table(tree, masks_host, px_host, device=device, plan=plan)
 
-    for _ in range(2):
-        tab = e2e_step()
-    assert tab.values.shape == (n_objects, n_feat_cols)
     e2e_steps = max(3, min(args.steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        tab = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        for _ in range(2):
+            tab = e2e_step()
+        assert tab.values.shape == (n_objects, n_feat_cols)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            tab = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
 
     # ---- reduce over ranks: max time, sum of units ----
     t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=device)
@@ -441,6 +443,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fields", type=int, default=8, help="C2 fields per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

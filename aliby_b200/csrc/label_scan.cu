@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 128;  // 4 warps x 8 KB of staging = 32 KB static shared memory per CTA
 constexpr int kScanWarps = kScanThreads / 32;
 
 __global__ void init_records_kernel(abx_object_rec* recs, int n_objects, int n_planes, int H, int W, u32* err) {
@@ -69,18 +69,28 @@ __device__ __forceinline__ u32 bitpos_sum8(u32 m) {  // sum of the positions of 
 }
 
 // Column-strip walker.  A warp owns a band of kBandRows rows x 256 columns; lane l walks DOWN the
-// 8-pixel strip [c0, c0 + 8) with one 128-bit load per row (the 32 lanes of a row form one coalesced
-// 512-byte request), keeping the object it is inside of in registers: a row whose 8 labels all equal
-// the current label costs a handful of instructions, and an object is flushed to its global record
-// with one set of atomics per (strip, band) instead of one per row run.
+// 8-pixel strip [c0, c0 + 8): one 128-bit cp.async per row brings the strip into the lane's private
+// shared-memory slots (the 32 lanes of a row form one coalesced 512-byte request; kRowBatch rows per
+// group, two groups in flight), and the object the lane is inside of lives in registers: a row whose
+// 8 labels all equal the current label costs a handful of instructions, and an object is flushed to
+// its global record with one set of atomics per (strip, band) instead of one per row run.
 constexpr int kBandRows = 32;
-constexpr int kRowBatch = 8;  // rows whose loads are in flight together
+constexpr int kRowBatch = 8;  // rows per cp.async group
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kScanThreads)
 label_scan_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int W, i64 plane_stride, i64 row_stride,
                   const int32_t* __restrict__ plane_base, abx_object_rec* __restrict__ recs, int n_objects,
                   int vec_ok, u32* err) {
+  __shared__ uint4 stage_all[kScanWarps][2][kRowBatch][32];  // 8 KB per warp
   const u32 lane = lane_id();
+  uint4 (*stage)[kRowBatch][32] = stage_all[threadIdx.x >> 5];
   const i64 gwarp = (i64)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
   const i64 nwarps = (i64)gridDim.x * kScanWarps;
   const int col_groups = (W + 255) >> 8;
@@ -94,37 +104,44 @@ label_scan_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int 
     const int p = (int)(t / bands);
     const u32 c0 = (u32)cg * 256u + lane * 8u;
     if (c0 >= (u32)W) continue;
-    const bool full = vec_ok && c0 + 8u <= (u32)W;  // aligned 128-bit loads are legal for this strip
+    const bool full = vec_ok && c0 + 8u <= (u32)W;  // aligned 128-bit copies are legal for this strip
     const int r_begin = band * kBandRows, r_end = min(H, r_begin + kBandRows);
     const uint16_t* src = labels + (i64)p * plane_stride + c0;
     const int base = plane_base[p];
     const u32 n_labels = (u32)(plane_base[p + 1] - base);
 
-    Piece cur;
-    cur.label = 0; cur.n = 0; cur.sum_row = 0; cur.sum_col = 0; cur.rmin = 0; cur.rmax = 0; cur.cmask = 0;
-    for (int r0 = r_begin; r0 < r_end; r0 += kRowBatch) {
-      uint4 q[kRowBatch];
+    // rows [r0, r0 + kRowBatch) -> stage[buf]; the lane only ever reads back what it copied itself
+    auto issue = [&](int r0, int buf) {
 #pragma unroll
       for (int u = 0; u < kRowBatch; ++u) {
         const int r = r0 + u;
-        q[u] = make_uint4(0, 0, 0, 0);
-        if (r < r_end) {
-          const uint16_t* row = src + (i64)r * row_stride;
-          if (full) {
-            q[u] = __ldg(reinterpret_cast<const uint4*>(row));
-          } else {  // ragged right edge or unaligned rows: element loads, zero beyond the plane
-            u32 e[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = (c0 + j < (u32)W) ? (u32)__ldg(row + j) : 0u;
-            q[u] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-          }
+        if (r >= r_end) break;
+        const uint16_t* row = src + (i64)r * row_stride;
+        if (full) {
+          cp_async16(&stage[buf][u][lane], row);
+        } else {  // ragged right edge or unaligned rows: element loads, zero beyond the plane
+          uint16_t* dst = reinterpret_cast<uint16_t*>(&stage[buf][u][lane]);
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) dst[j] = (c0 + j < (u32)W) ? __ldg(row + j) : (uint16_t)0;
         }
       }
-#pragma unroll
-      for (int u = 0; u < kRowBatch; ++u) {
+      cp_async_commit();
+    };
+
+    Piece cur;
+    cur.label = 0; cur.n = 0; cur.sum_row = 0; cur.sum_col = 0; cur.rmin = 0; cur.rmax = 0; cur.cmask = 0;
+    issue(r_begin, 0);
+    int buf = 0;
+#pragma unroll 1
+    for (int r0 = r_begin; r0 < r_end; r0 += kRowBatch, buf ^= 1) {
+      if (r0 + kRowBatch < r_end) { issue(r0 + kRowBatch, buf ^ 1); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      const int rows = min(kRowBatch, r_end - r0);
+#pragma unroll 1
+      for (int u = 0; u < rows; ++u) {
         const u32 r = (u32)(r0 + u);
-        if ((int)r >= r_end) break;
-        const u32 w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        const uint4 q = stage[buf][u][lane];
+        const u32 w[4] = {q.x, q.y, q.z, q.w};
         const u32 pair = cur.label | (cur.label << 16);
         if (((w[0] ^ pair) | (w[1] ^ pair) | (w[2] ^ pair) | (w[3] ^ pair)) == 0u) {  // all 8 == current label
           if (cur.label) {
@@ -204,7 +221,7 @@ int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err,
   const i64 units = (i64)a->n_planes * ((a->H + kBandRows - 1) / kBandRows) * ((a->W + 255) / 256);
   if (units == 0) return abx_check_cuda(cudaGetLastError(), "init_records");
   i64 blocks = (units + kScanWarps - 1) / kScanWarps;
-  const i64 cap = 148 * 8;  // 8 CTAs of 8 warps per SM; more units than that are walked in a grid-stride loop
+  const i64 cap = 148 * 7;  // 7 CTAs of 4 warps per SM (shared memory); more units are walked in a grid-stride loop
   if (blocks > cap) blocks = cap;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(a->labels) & 15u) == 0) && (a->label_row_stride % 8 == 0) &&
                      (a->label_plane_stride % 8 == 0);

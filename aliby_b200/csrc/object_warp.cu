@@ -47,10 +47,14 @@ struct Obj {
   int h, w;
 };
 
+// Sum of a 64-bit quantity over the warp from three independent 32-bit REDUX reductions of its
+// 24/24/16-bit slices (each slice sum < 2^29): shorter and far less latency than five dependent
+// 64-bit shuffle steps.  Exact modulo 2^64 for any input.
 __device__ __forceinline__ u64 warp_sum64(u64 v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
+  const u32 a = __reduce_add_sync(kFull, (u32)v & 0xFFFFFFu);
+  const u32 b = __reduce_add_sync(kFull, (u32)(v >> 24) & 0xFFFFFFu);
+  const u32 c = __reduce_add_sync(kFull, (u32)(v >> 48));
+  return (u64)a + ((u64)b << 24) + ((u64)c << 48);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -305,9 +309,9 @@ __device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __rest
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) { k[u] = kn[u]; x[u] = xn[u]; }
   }
-  cs.sum = warp_sum64((u64)f_sum);
+  cs.sum = kWide ? warp_sum64((u64)f_sum) : (u64)__reduce_add_sync(kFull, (u32)f_sum);  // n * 65535 < 2^32
   cs.sumsq = warp_sum64(f_sq);
-  cs.wrapsq = kWide ? cs.sumsq : warp_sum64((u64)f_wrap);
+  cs.wrapsq = kWide ? cs.sumsq : (u64)__reduce_add_sync(kFull, (u32)f_wrap);
   if (want_moi) {
     cs.m10 = warp_sum64((u64)f_m10); cs.m01 = warp_sum64((u64)f_m01);
     cs.m20 = warp_sum64(f_m20); cs.m02 = warp_sum64(f_m02);
@@ -578,16 +582,36 @@ __device__ __noinline__ void shape_edt_warp(const Obj& o, const EdtSmem& s, u32 
   }
   __syncwarp();
   // ---- row distances of object pixels: nearest zero to the left / right (beyond the window = zero) ----
+  // Rows that are one run [a, b] (the common case) take their distances from the run ends; rowbase[]
+  // is reused for the per-row run descriptor a | b << 6 | single << 12.
+  for (u32 r = lane; r < (u32)h; r += 32) {
+    const u64 m = s.rowmask[r];
+    u32 info = 0;
+    if (m) {
+      const u32 a = (u32)__ffsll((long long)m) - 1u, b = 63u - (u32)__clzll((long long)m);
+      const u64 run = m >> a;
+      info = a | (b << 6) | (((run & (run + 1ull)) == 0ull) ? 0x1000u : 0u);
+    }
+    s.rowbase[r] = (unsigned short)info;
+  }
+  __syncwarp();
 #pragma unroll 2
   for (u32 i = lane; i < n; i += 32) {
     const u32 k = s.offs[i];
     const u32 r = k >> 6, c = k & 63u;
-    u64 z = ~s.rowmask[r];
-    if (w < 64) z |= (~0ull << w);
-    const u64 le = z & (~0ull >> (63 - c));  // zeros at columns <= c (never c itself)
-    const u32 dl = le ? (c - (63u - (u32)__clzll((long long)le))) : (c + 1u);
-    const u64 ge = z >> c;
-    const u32 dr = ge ? ((u32)__ffsll((long long)ge) - 1u) : (64u - c);
+    const u32 info = s.rowbase[r];
+    u32 dl, dr;
+    if (info & 0x1000u) {
+      dl = c - (info & 63u) + 1u;
+      dr = ((info >> 6) & 63u) - c + 1u;
+    } else {
+      u64 z = ~s.rowmask[r];
+      if (w < 64) z |= (~0ull << w);
+      const u64 le = z & (~0ull >> (63 - c));  // zeros at columns <= c (never c itself)
+      dl = le ? (c - (63u - (u32)__clzll((long long)le))) : (c + 1u);
+      const u64 ge = z >> c;
+      dr = ge ? ((u32)__ffsll((long long)ge) - 1u) : (64u - c);
+    }
     g[((r + 1u) << 6) | c] = (unsigned char)min(dl, dr);
   }
   __syncwarp();

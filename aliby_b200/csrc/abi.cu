@@ -127,13 +127,15 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   mark(0);
   if ((rc = launch_label_scan(args, ws.recs, ws.err, st))) return rc;
   mark(1);
-  if ((rc = launch_object_warp(args, ws, st))) return rc;   // objects with a window <= 64 x 64
+  if ((rc = launch_object_stats_warp(args, ws, st))) return rc;  // objects with a window <= 64 x 64
   mark(2);
+  if ((rc = launch_object_edt_warp(args, ws, st))) return rc;
+  mark(3);
   if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
   if ((rc = launch_shape_edt(args, ws, st))) return rc;
-  mark(3);
-  if ((rc = launch_finalize(args, ws, st))) return rc;
   mark(4);
+  if ((rc = launch_finalize(args, ws, st))) return rc;
+  mark(5);
   return ABX_OK;
 }
 

@@ -877,9 +877,7 @@ int launch_sqrt_table(double* tab, cudaStream_t st) {
   return abx_check_cuda(cudaGetLastError(), "sqrt_table");
 }
 
-int launch_object_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
-  const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
-  if (n_total == 0 || (a->n_requests == 0 && !a->need_edt)) return ABX_OK;
+static Common make_common(const abx_extract_args* a, const Workspace& ws, int n_total) {
   Common cm;
   cm.labels = static_cast<const uint16_t*>(a->labels);
   cm.lab_plane_stride = a->label_plane_stride;
@@ -890,27 +888,33 @@ int launch_object_warp(const abx_extract_args* a, const Workspace& ws, cudaStrea
   cm.n_objects = a->n_objects;
   cm.n_total = n_total;
   cm.recs = ws.recs;
-  int rc = ABX_OK;
-  if (a->n_requests > 0) {
-    cm.counters = ws.list_counts + 2;
-    if (a->pixel_dtype == ABX_U16) rc = launch_stats<uint16_t>(a, ws, cm, st);
-    else if (a->pixel_dtype == ABX_U8) rc = launch_stats<uint8_t>(a, ws, cm, st);
-    else rc = abx_set_error(ABX_ERR_UNSUPPORTED, "object_warp: pixel dtype %d has no kernel", a->pixel_dtype);
-    if (rc) return rc;
-  }
-  if (a->need_edt && a->n_objects > 0) {
-    constexpr size_t fixed = 512 + 128 + (kSide + 2) * kSide + 512;
-    constexpr size_t smem = (kEdtWarps - kLargeSlots) * (fixed + kCapSmall * 2) + kLargeSlots * (fixed + kCapLarge * 2);
-    static thread_local bool done[64] = {false};
-    rc = set_smem(object_edt_warp, smem, done);
-    if (rc) return rc;
-    if ((rc = launch_sqrt_table(ws.sqrt_tab, st))) return rc;
-    cm.counters = ws.list_counts + 4;
-    int grid = (a->n_objects + kEdtWarps - 1) / kEdtWarps;
-    if (grid > 148 * 2) grid = 148 * 2;
-    object_edt_warp<<<grid, kEdtWarps * 32, smem, st>>>(cm, (a->need_edt & 2) != 0, ws.sqrt_tab, ws.shape, ws.edt_list,
-                                                        ws.list_counts + 1);
-    rc = abx_check_cuda(cudaGetLastError(), "object_edt_warp");
-  }
-  return rc;
+  cm.counters = nullptr;
+  return cm;
+}
+
+int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+  const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
+  if (n_total == 0 || a->n_requests == 0) return ABX_OK;
+  Common cm = make_common(a, ws, n_total);
+  cm.counters = ws.list_counts + 2;
+  if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st);
+  if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st);
+  return abx_set_error(ABX_ERR_UNSUPPORTED, "object_stats_warp: pixel dtype %d has no kernel", a->pixel_dtype);
+}
+
+int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+  if (!a->need_edt || a->n_objects == 0) return ABX_OK;
+  constexpr size_t fixed = 512 + 128 + (kSide + 2) * kSide + 512;
+  constexpr size_t smem = (kEdtWarps - kLargeSlots) * (fixed + kCapSmall * 2) + kLargeSlots * (fixed + kCapLarge * 2);
+  static thread_local bool done[64] = {false};
+  int rc = set_smem(object_edt_warp, smem, done);
+  if (rc) return rc;
+  if ((rc = launch_sqrt_table(ws.sqrt_tab, st))) return rc;
+  Common cm = make_common(a, ws, a->n_objects);
+  cm.counters = ws.list_counts + 4;
+  int grid = (a->n_objects + kEdtWarps - 1) / kEdtWarps;
+  if (grid > 148 * 2) grid = 148 * 2;
+  object_edt_warp<<<grid, kEdtWarps * 32, smem, st>>>(cm, (a->need_edt & 2) != 0, ws.sqrt_tab, ws.shape, ws.edt_list,
+                                                      ws.list_counts + 1);
+  return abx_check_cuda(cudaGetLastError(), "object_edt_warp");
 }

@@ -265,8 +265,8 @@ def run_planes(
     a.request_feature_union = 0
     a.table = out.data_ptr()
     a.stream = torch.cuda.current_stream(device).cuda_stream
-    if stage_events is not None:  # 5 handles from abx_event_create (bench.py: live per-stage timing)
-        ev = (C.c_void_p * 5)(*stage_events)
+    if stage_events is not None:  # 6 handles from abx_event_create (bench.py: live per-stage timing)
+        ev = (C.c_void_p * 6)(*stage_events)
         a.stage_events = C.cast(ev, C.POINTER(C.c_void_p))
     need = C.c_size_t(0)
     nat.check(lib.abx_extract_workspace_bytes(C.byref(a), C.byref(need)), "abx_extract_workspace_bytes")

@@ -148,8 +148,8 @@ typedef struct abx_extract_args {
   void* workspace;
   size_t workspace_bytes;
   void* stream; /* cudaStream_t */
-  /* optional: 5 events made by abx_event_create, recorded on `stream` before the label scan and
-   * after the label scan / warp-per-object kernel / large-object kernels / finalisation */
+  /* optional: 6 events made by abx_event_create, recorded on `stream` before the label scan and after the
+   * label scan / object_stats_warp / object_edt_warp / large-object kernels / finalisation */
   void* const* stage_events;
 } abx_extract_args;
 

@@ -19,7 +19,7 @@ def run(tree, reps=5):
     evs = []
     for _ in range(reps):
         e = []
-        for _ in range(5):
+        for _ in range(6):
             h = C.c_void_p(); lib.abx_event_create(C.byref(h)); e.append(h)
         evs.append(e)
     for _ in range(3):
@@ -27,9 +27,9 @@ def run(tree, reps=5):
     for e in evs:
         engine.run_planes(plan, labd, np.arange(F, dtype=np.int32), nl, pxd, offs, H * W, H * W, W, 5, 1, stage_events=e)
     torch.cuda.synchronize()
-    ms = np.zeros(4)
+    ms = np.zeros(5)
     for e in evs:
-        for i in range(4):
+        for i in range(5):
             t = C.c_float(); lib.abx_event_elapsed_ms(e[i], e[i + 1], C.byref(t)); ms[i] += t.value
     return ms / reps
 
@@ -45,7 +45,7 @@ trees = {
     "full C2 tree": bench.c2_tree(),
     "1 channel all intensity": {0: {"max": bench.INTENSITY_FEATURES}},
 }
-print(f"{F} fields, {int(nl.sum())} objects; stage ms: scan | warp | large | finalize")
+print(f"{F} fields, {int(nl.sum())} objects; stage ms: scan | stats | edt | large | finalize")
 for name, tree in trees.items():
     ms = run(tree)
-    print(f"{name:32s} {ms[0]:7.3f} {ms[1]:7.3f} {ms[2]:7.3f} {ms[3]:7.3f}   total {ms.sum():7.3f}")
+    print(f"{name:32s} " + " ".join(f"{v:7.3f}" for v in ms) + f"   total {ms.sum():7.3f}")

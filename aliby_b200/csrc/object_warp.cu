@@ -40,12 +40,10 @@ constexpr int kStatsWarps = 9;   // 7 small + 2 large slots: 109 KB per CTA, 2 C
 constexpr int kEdtWarps = 10;    // 8 small + 2 large slots: 103 KB per CTA, 2 CTAs per SM
 constexpr u32 kFull = 0xFFFFFFFFu;
 
-struct Obj {
-  const uint16_t* lab;  // label window origin
-  i64 lab_rs;
-  u32 label, n;
-  int h, w;
-};
+// Every device function derives its shared-memory pointers from this array plus a byte offset, so that the
+// compiler keeps them in the shared address space (generic pointers passed through __noinline__ calls
+// compiled to LD.E/ST.E with 64-bit address arithmetic: 24 instructions per EDT step instead of 8).
+extern __shared__ __align__(16) unsigned char dyn[];
 
 // Sum of a 64-bit quantity over the warp from three independent 32-bit REDUX reductions of its
 // 24/24/16-bit slices (each slice sum < 2^29): shorter and far less latency than five dependent
@@ -76,28 +74,31 @@ struct Queue {
 
 // phase M: row bitmasks (optional), row bases (optional) and the compact offset list
 template <bool kMasks>
-__device__ __noinline__ void build_list(const Obj& o, unsigned short* __restrict__ offs, u64* __restrict__ rowmask,
-                                           unsigned short* __restrict__ rowbase) {
+__device__ __noinline__ void build_list(const uint16_t* __restrict__ lab, i64 lab_rs, u32 label, int h, int w, u32 offs_off,
+                                        u32 rowmask_off, u32 rowbase_off) {
+  unsigned short* offs = reinterpret_cast<unsigned short*>(dyn + offs_off);
+  u64* rowmask = reinterpret_cast<u64*>(dyn + rowmask_off);
+  unsigned short* rowbase = reinterpret_cast<unsigned short*>(dyn + rowbase_off);
   const u32 lane = lane_id();
   const u32 lt = (1u << lane) - 1u;
-  const bool two = o.w > 32;
+  const bool two = w > 32;
   u32 base = 0;
   constexpr int kRows = 8;  // label rows in flight per iteration (16 loads per lane)
 #pragma unroll 1
-  for (int r0 = 0; r0 < o.h; r0 += kRows) {
+  for (int r0 = 0; r0 < h; r0 += kRows) {
     u32 l0[kRows], l1[kRows];
 #pragma unroll
     for (int u = 0; u < kRows; ++u) {  // all loads of the row group first
-      const uint16_t* lrow = o.lab + (i64)(r0 + u) * o.lab_rs;
-      const bool in = r0 + u < o.h;
-      l0[u] = (in && lane < (u32)o.w) ? (u32)__ldg(lrow + lane) : kFull;
-      l1[u] = (in && two && lane + 32 < (u32)o.w) ? (u32)__ldg(lrow + lane + 32) : kFull;
+      const uint16_t* lrow = lab + (i64)(r0 + u) * lab_rs;
+      const bool in = r0 + u < h;
+      l0[u] = (in && lane < (u32)w) ? (u32)__ldg(lrow + lane) : kFull;
+      l1[u] = (in && two && lane + 32 < (u32)w) ? (u32)__ldg(lrow + lane + 32) : kFull;
     }
 #pragma unroll
     for (int u = 0; u < kRows; ++u) {
       const int r = r0 + u;
-      if (r >= o.h) break;
-      const bool hit0 = l0[u] == o.label, hit1 = l1[u] == o.label;
+      if (r >= h) break;
+      const bool hit0 = l0[u] == label, hit1 = l1[u] == label;
       const u32 b0 = __ballot_sync(kFull, hit0);
       const u32 b1 = __ballot_sync(kFull, hit1);
       if (kMasks && lane == 0) { rowmask[r] = (u64)b0 | ((u64)b1 << 32); rowbase[r] = (unsigned short)base; }
@@ -108,8 +109,8 @@ __device__ __noinline__ void build_list(const Obj& o, unsigned short* __restrict
     }
   }
   if (kMasks) {  // rows beyond the window read as empty
-    if (lane >= (u32)o.h) rowmask[lane] = 0;
-    if (lane + 32 >= (u32)o.h) rowmask[lane + 32] = 0;
+    if (lane >= (u32)h) rowmask[lane] = 0;
+    if (lane + 32 >= (u32)h) rowmask[lane + 32] = 0;
   }
   __syncwarp();
 }
@@ -257,8 +258,11 @@ __device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __rest
   Acc f_sum = 0, f_wrap = 0, f_m10 = 0, f_m01 = 0;
   u64 f_sq = 0, f_m20 = 0, f_m02 = 0;
   u32 a_min = kFull, a_max = 0;
-  u32 k[kBatch], x[kBatch];
-  auto load_batch = [&](u32 i0, u32 (&kq)[kBatch], u32 (&xq)[kBatch]) {
+  u32 x[kBatch];
+  // values of batch i0 (Z-reduced); the offsets are re-read from shared memory when the batch is consumed,
+  // so that only the values live across the pipeline stage
+  auto load_batch = [&](u32 i0, u32 (&xq)[kBatch]) {
+    u32 kq[kBatch];
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const u32 i = i0 + 32u * u;
@@ -281,33 +285,35 @@ __device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __rest
     }
   };
 #pragma unroll
-  for (int u = 0; u < kBatch; ++u) { k[u] = kNone; x[u] = 0; }
+  for (int u = 0; u < kBatch; ++u) x[u] = 0;
   // iteration j loads batch j and accumulates batch j - 1 (one copy of each body in the code)
 #pragma unroll 1
   for (int i0 = (int)lane - 32 * kBatch; i0 < (int)n; i0 += 32 * kBatch) {
-    u32 kn[kBatch], xn[kBatch];
-    load_batch((u32)(i0 + 32 * kBatch), kn, xn);  // indices >= n load nothing
-    if (i0 >= 0) {                                // warp-uniform
+    u32 xn[kBatch];
+    load_batch((u32)(i0 + 32 * kBatch), xn);  // indices >= n load nothing
+    if (i0 >= 0) {                            // warp-uniform
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const bool ok = k[u] != kNone;
-        const u32 v = x[u];
+        const u32 i = (u32)i0 + 32u * u;
+        const bool ok = i < n;
+        const u32 v = x[u];  // 0 when !ok
         f_sum += v;
         f_sq += (u64)v * (u64)v;
         if (!kWide) f_wrap += (v * v) & kWrapMask;
         a_min = min(a_min, ok ? v : kFull);
         a_max = max(a_max, v);
         if (want_moi) {
-          const u32 c = k[u] & 63u, r = (k[u] >> 6) & 63u;
+          const u32 k = ok ? (u32)offs[i] : 0u;
+          const u32 c = k & 63u, r = k >> 6;
           const Acc xc = (Acc)v * c, xr = (Acc)v * r;
           f_m10 += xc; f_m01 += xr;
           f_m20 += (u64)xc * (u64)c; f_m02 += (u64)xr * (u64)r;
         }
-        if (!kWide && ok) vals[(u32)i0 + 32u * u] = (unsigned short)v;
+        if (!kWide && ok) vals[i] = (unsigned short)v;
       }
     }
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) { k[u] = kn[u]; x[u] = xn[u]; }
+    for (int u = 0; u < kBatch; ++u) x[u] = xn[u];
   }
   cs.sum = kWide ? warp_sum64((u64)f_sum) : (u64)__reduce_add_sync(kFull, (u32)f_sum);  // n * 65535 < 2^32
   cs.sumsq = warp_sum64(f_sq);
@@ -323,30 +329,32 @@ __device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __rest
 }
 
 template <typename PX>
-__device__ __noinline__ void moments_wide(u32 n, const unsigned short* __restrict__ offs, const PX* __restrict__ px, u32 rs,
-                                          i64 z_stride, int Z, int red, bool want_moi, ChanStats& cs) {
-  moments_pass<PX, true>(n, offs, nullptr, px, rs, z_stride, Z, red, want_moi, cs);
+__device__ __noinline__ void moments_wide(u32 n, u32 slot_off, const PX* __restrict__ px, u32 rs, i64 z_stride, int Z, int red,
+                                          bool want_moi, ChanStats& cs) {
+  moments_pass<PX, true>(n, reinterpret_cast<const unsigned short*>(dyn + slot_off), nullptr, px, rs, z_stride, Z, red,
+                         want_moi, cs);
 }
 
 // ------------------------------------------------------------------------------------------------
 // phase S: one (channel, reduction) request
 // ------------------------------------------------------------------------------------------------
 template <typename PX>
-__device__ __noinline__ void request_stats(u32 n, const unsigned short* __restrict__ offs, unsigned short* __restrict__ vals,
-                                              u32* __restrict__ hist, u32* __restrict__ t, const PX* __restrict__ px,
-                                              u32 rs, i64 z_stride, int Z, const abx_request rq,
-                                              ChanStats* __restrict__ dst) {
+__device__ __noinline__ void request_stats(u32 n, u32 slot_off, u32 cap, const PX* __restrict__ px, u32 rs, i64 z_stride, int Z,
+                                           int reduction, u32 feats, ChanStats* __restrict__ dst) {
+  const unsigned short* offs = reinterpret_cast<const unsigned short*>(dyn + slot_off);
+  unsigned short* vals = reinterpret_cast<unsigned short*>(dyn + slot_off) + cap;
+  u32* hist = reinterpret_cast<u32*>(vals + cap);
+  u32* t = hist + kBins / 2;
   const u32 lane = lane_id();
-  const bool wide = rq.reduction == ABX_RED_ADD && Z > 1;
-  const u32 feats = rq.features;
+  const bool wide = reduction == ABX_RED_ADD && Z > 1;
   ChanStats cs;
-  if (wide) moments_wide<PX>(n, offs, px, rs, z_stride, Z, rq.reduction, (feats & ABX_F_MOI) != 0, cs);
-  else moments_pass<PX, false>(n, offs, vals, px, rs, z_stride, Z, rq.reduction, (feats & ABX_F_MOI) != 0, cs);
+  if (wide) moments_wide<PX>(n, slot_off, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0, cs);
+  else moments_pass<PX, false>(n, offs, vals, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0, cs);
   cs.med_lo = cs.med_hi = 0;
   cs.top2p5_sum = cs.top5_sum = 0;
 
   if (feats & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) {
-    ValueSource<PX> value{vals, offs, px, z_stride, rs, Z, rq.reduction, !wide};
+    ValueSource<PX> value{vals, offs, px, z_stride, rs, Z, reduction, !wide};
     const u32 vmin = cs.vmin;
     const unsigned short* h16 = reinterpret_cast<const unsigned short*>(hist);
     // ---- pass 2: range-adaptive histogram ----
@@ -479,18 +487,14 @@ __global__ void __launch_bounds__(kStatsWarps * 32, 2)
 object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __restrict__ tile_offset, i64 chan_stride,
                   i64 z_stride, i64 px_row_stride, int Z, const abx_request* __restrict__ requests, int n_requests,
                   ChanStats* __restrict__ chan, int* __restrict__ stats_list, u32* __restrict__ stats_count) {
-  extern __shared__ __align__(16) unsigned char dyn[];
   const u32 lane = lane_id();
   const int warp = threadIdx.x >> 5;
   constexpr int kSmall = kStatsWarps - kLargeSlots;
   constexpr u32 kSlotSmall = kCapSmall * 4 + kBins * 2 + 64, kSlotLarge = kCapLarge * 4 + kBins * 2 + 64;
   const bool large_slot = warp >= kSmall;
   const u32 cap = large_slot ? kCapLarge : kCapSmall;
-  unsigned char* slot = dyn + (large_slot ? kSmall * kSlotSmall + (warp - kSmall) * kSlotLarge : warp * kSlotSmall);
-  unsigned short* offs = reinterpret_cast<unsigned short*>(slot);
-  unsigned short* vals = offs + cap;
-  u32* hist = reinterpret_cast<u32*>(vals + cap);
-  u32* t = hist + kBins / 2;
+  // slot layout: offs u16[cap] | vals u16[cap] | hist u32[512] | t u32[16]
+  const u32 slot_off = large_slot ? kSmall * kSlotSmall + (warp - kSmall) * kSlotLarge : warp * kSlotSmall;
 
   Queue qu{cm.counters, cm.n_total, large_slot ? 1 : 0};
   int obj = qu.fetch();
@@ -521,19 +525,15 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
       if (lane == 0) stats_list[atomicAdd(stats_count, 1u)] = obj;
     } else if (fits && rec.n > lo && rec.n <= hi) {
       const int p = find_plane(cm.plane_base, cm.n_planes, obj);
-      Obj o;
-      o.label = (u32)(obj - cm.plane_base[p] + 1);
-      o.n = rec.n; o.h = h; o.w = w;
-      o.lab_rs = cm.lab_row_stride;
-      o.lab = cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin;
       __syncwarp();
-      build_list<false>(o, offs, nullptr, nullptr);
+      build_list<false>(cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin,
+                        cm.lab_row_stride, (u32)(obj - cm.plane_base[p] + 1), h, w, slot_off, 0, 0);
       const PX* px0 = pixels + tile_offset[cm.plane_tile[p]] + (i64)rec.rmin * px_row_stride + rec.cmin;
 #pragma unroll 1
       for (int q = 0; q < n_requests; ++q) {
         const abx_request rq = requests[q];
-        request_stats<PX>(rec.n, offs, vals, hist, t, px0 + (i64)rq.channel * chan_stride, (u32)px_row_stride, z_stride, Z,
-                          rq, chan + (i64)obj * n_requests + q);
+        request_stats<PX>(rec.n, slot_off, cap, px0 + (i64)rq.channel * chan_stride, (u32)px_row_stride, z_stride, Z,
+                          rq.reduction, rq.features, chan + (i64)obj * n_requests + q);
       }
     }
     obj = nxt;
@@ -562,17 +562,23 @@ __device__ __forceinline__ u32 nearest_bit_sq(u64 m, u32 c) {
 
 struct EdtSmem {
   u64* rowmask;             // [64] bit c of rowmask[r]: window pixel (r, c) belongs to the object
-  unsigned short* rowbase;  // [64] number of object pixels in rows < r
-  unsigned short* offs;     // [cap]
-  unsigned char* g;         // [66][64] row distances, one all-zero frame row above and below
   u64* topmask;             // [64] cone top
+  unsigned char* g;         // [66][64] row distances, one all-zero frame row above and below
+  unsigned short* rowbase;  // [64] number of object pixels in rows < r; later the per-row run descriptor
+  unsigned short* offs;     // [cap]
 };
+// slot layout of the EDT kernel (byte offsets from the slot start)
+constexpr u32 kEdtTopOff = 512, kEdtGOff = 1024, kEdtRowbaseOff = 1024 + (kSide + 2) * kSide, kEdtOffsOff = kEdtRowbaseOff + 128;
 
-__device__ __noinline__ void shape_edt_warp(const Obj& o, const EdtSmem& s, u32 rmin, u32 cmin, bool want_conical,
-                                               const double* __restrict__ sqrt_tab, ShapeStats* __restrict__ dst) {
+__device__ __noinline__ void shape_edt_warp(u32 n, int h, int w, u32 slot_off, u32 rmin, u32 cmin, bool want_conical,
+                                            const double* __restrict__ sqrt_tab, ShapeStats* __restrict__ dst) {
+  EdtSmem s;
+  s.rowmask = reinterpret_cast<u64*>(dyn + slot_off);
+  s.topmask = reinterpret_cast<u64*>(dyn + slot_off + kEdtTopOff);
+  s.g = dyn + slot_off + kEdtGOff;
+  s.rowbase = reinterpret_cast<unsigned short*>(dyn + slot_off + kEdtRowbaseOff);
+  s.offs = reinterpret_cast<unsigned short*>(dyn + slot_off + kEdtOffsOff);
   const u32 lane = lane_id();
-  const int h = o.h, w = o.w;
-  const u32 n = o.n;
   unsigned char* g = s.g;
   // zero g (non-object pixels and the frame rows have row distance 0) and the cone-top mask
   {
@@ -636,12 +642,13 @@ __device__ __noinline__ void shape_edt_warp(const Obj& o, const EdtSmem& s, u32 
       }
       u32 d64 = 64, dd = 1, step = 3;  // d * 64, d * d, 2 d + 1
       while ((dd < best[0]) | (dd < best[1]) | (dd < best[2]) | (dd < best[3])) {
+        // branch-free: a finished pixel re-reads its own cell (candidate g0^2 + dd >= best, a no-op)
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (dd < best[u]) {
-            const u32 m2 = min((u32)g[kk[u] - d64], (u32)g[kk[u] + d64]);
-            best[u] = min(best[u], m2 * m2 + dd);
-          }
+        for (int u = 0; u < 4; ++u) {
+          const u32 off = (dd < best[u]) ? d64 : 0u;
+          const u32 m2 = min((u32)g[kk[u] - off], (u32)g[kk[u] + off]);
+          best[u] = min(best[u], m2 * m2 + dd);
+        }
         dd += step; step += 2; d64 += 64;
       }
 #pragma unroll
@@ -778,20 +785,13 @@ __device__ __noinline__ void shape_edt_warp(const Obj& o, const EdtSmem& s, u32 
 __global__ void __launch_bounds__(kEdtWarps * 32, 2)
 object_edt_warp(const Common cm, int want_conical, const double* __restrict__ sqrt_tab, ShapeStats* __restrict__ shape,
                 int* __restrict__ edt_list, u32* __restrict__ edt_count) {
-  extern __shared__ __align__(16) unsigned char dyn[];
   const u32 lane = lane_id();
   const int warp = threadIdx.x >> 5;
   constexpr int kSmall = kEdtWarps - kLargeSlots;
-  constexpr u32 kFixed = 512 + 128 + (kSide + 2) * kSide + 512;  // rowmask, rowbase, g, topmask
+  constexpr u32 kFixed = 512 + 128 + (kSide + 2) * kSide + 512;  // rowmask, topmask, g, rowbase
   constexpr u32 kSlotSmall = kFixed + kCapSmall * 2, kSlotLarge = kFixed + kCapLarge * 2;
   const bool large_slot = warp >= kSmall;
-  unsigned char* slot = dyn + (large_slot ? kSmall * kSlotSmall + (warp - kSmall) * kSlotLarge : warp * kSlotSmall);
-  EdtSmem s;
-  s.rowmask = reinterpret_cast<u64*>(slot);
-  s.topmask = reinterpret_cast<u64*>(slot + 512);
-  s.g = slot + 1024;
-  s.rowbase = reinterpret_cast<unsigned short*>(slot + 1024 + (kSide + 2) * kSide);
-  s.offs = s.rowbase + 64;
+  const u32 slot_off = large_slot ? kSmall * kSlotSmall + (warp - kSmall) * kSlotLarge : warp * kSlotSmall;
 
   Queue qu{cm.counters, cm.n_objects, large_slot ? 1 : 0};
   int obj = qu.fetch();
@@ -815,14 +815,11 @@ object_edt_warp(const Common cm, int want_conical, const double* __restrict__ sq
       if (lane == 0) edt_list[atomicAdd(edt_count, 1u)] = obj;
     } else if (fits && rec.n > lo && rec.n <= hi) {
       const int p = find_plane(cm.plane_base, cm.n_planes, obj);
-      Obj o;
-      o.label = (u32)(obj - cm.plane_base[p] + 1);
-      o.n = rec.n; o.h = h; o.w = w;
-      o.lab_rs = cm.lab_row_stride;
-      o.lab = cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin;
       __syncwarp();
-      build_list<true>(o, s.offs, s.rowmask, s.rowbase);
-      shape_edt_warp(o, s, rec.rmin, rec.cmin, want_conical != 0, sqrt_tab, shape + obj);
+      build_list<true>(cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin,
+                       cm.lab_row_stride, (u32)(obj - cm.plane_base[p] + 1), h, w, slot_off + kEdtOffsOff, slot_off,
+                       slot_off + kEdtRowbaseOff);
+      shape_edt_warp(rec.n, h, w, slot_off, rec.rmin, rec.cmin, want_conical != 0, sqrt_tab, shape + obj);
     }
     obj = nxt;
     nxt = obj < cm.n_objects ? qu.fetch() : cm.n_objects;

@@ -156,11 +156,28 @@ def _host_u16(plane) -> "np.ndarray":
     return np.ascontiguousarray(plane)
 
 
+def _contiguous_run(planes):
+    """One (k, Y, X) view over `planes` when they sit back to back in memory (slices of one array), else None."""
+    if len(planes) < 2:
+        return None
+    first = planes[0]
+    step = first.nbytes
+    addr0 = first.__array_interface__["data"][0]
+    for j, pl in enumerate(planes):
+        if pl.shape != first.shape or not pl.flags.c_contiguous or pl.__array_interface__["data"][0] != addr0 + j * step:
+            return None
+    # the planes themselves keep the memory alive while the view is in use
+    return np.lib.stride_tricks.as_strided(first, shape=(len(planes), *first.shape), strides=(step, *first.strides))
+
+
 def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
-    """Host arrays in, host table out, with the uploads of later tiles overlapping the kernels of
-    earlier ones: all H2D copies are queued on a copy stream (asynchronous when the arrays are
-    pinned), each chunk of tiles is extracted as soon as its copy has landed, and its table goes
-    back with an asynchronous D2H copy.  Returns ``(values (n, dense columns), n_labels per kept tile)``."""
+    """Host arrays in, host table out, with the uploads overlapping the kernels.
+
+    Copy stream: all label planes first (1/6 of the bytes), then the pixels in chunks of tiles (asynchronous
+    when the arrays are pinned).  Compute stream: the per-plane label maxima as soon as the labels have landed
+    (their D2H is the only host synchronisation before the end: the row count sizes the table), then one
+    ``abx_extract`` per chunk as its pixels land, all writing into one device table that goes back with a
+    single D2H copy.  Returns ``(values (n, dense columns), n_labels per kept tile)``."""
     import torch
 
     T, C_, Z_, Y, X = pixels.shape
@@ -172,10 +189,17 @@ def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
     cps.wait_stream(cur)  # buffers handed out by the caching allocator may still be in use on `cur`
     staged = []
     with torch.cuda.stream(cps):
+        lab = torch.empty((len(keep), Y, X), dtype=torch.uint16, device=device)
+        planes = [_host_u16(masks[t]) for t in keep]
+        run = _contiguous_run(planes)
+        if run is not None:  # the planes are slices of one array: one copy instead of one per plane
+            lab.copy_(torch.from_numpy(run), non_blocking=True)
+        else:
+            for j, plane in enumerate(planes):
+                lab[j].copy_(torch.from_numpy(plane), non_blocking=True)
+        ev_lab = torch.cuda.Event()
+        ev_lab.record(cps)
         for tiles in chunks:
-            lab = torch.empty((len(tiles), Y, X), dtype=torch.uint16, device=device)
-            for j, t in enumerate(tiles):
-                lab[j].copy_(torch.from_numpy(_host_u16(masks[t])), non_blocking=True)
             if plan.requests:
                 consecutive = tiles == list(range(tiles[0], tiles[0] + len(tiles)))
                 src = pixels[tiles[0] : tiles[0] + len(tiles)] if consecutive else pixels[tiles]
@@ -185,30 +209,32 @@ def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
                 px = torch.empty(0, dtype=torch.uint16, device=device)
             ev = torch.cuda.Event()
             ev.record(cps)
-            staged.append((tiles, lab, px, ev))
-    outs, n_all = [], []
-    for tiles, lab, px, ev in staged:
+            staged.append((tiles, px, ev))
+    cur.wait_event(ev_lab)
+    nmax_host = torch.empty(len(keep), dtype=torch.int32, pin_memory=True)
+    nmax_host.copy_(_label_max(lab, device), non_blocking=True)
+    done = torch.cuda.Event()
+    done.record(cur)
+    done.synchronize()  # the row count has to reach the host; the pixel uploads keep running meanwhile
+    n_labels = nmax_host.numpy().astype(np.int64)
+    rows = np.concatenate([[0], np.cumsum(n_labels)])
+    table = torch.empty((int(rows[-1]), plan.n_columns), dtype=torch.float64, device=device)
+    p0 = 0
+    for tiles, px, ev in staged:
         cur.wait_event(ev)
-        nmax_host = torch.empty(len(tiles), dtype=torch.int32, pin_memory=True)
-        nmax_host.copy_(_label_max(lab, device), non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(cur)
-        done.synchronize()  # the row count has to reach the host; later uploads keep running meanwhile
-        n_labels = nmax_host.numpy().astype(np.int64)
-        n_all.append(n_labels)
+        p1 = p0 + len(tiles)
         offs = np.arange(len(tiles), dtype=np.int64) * (C_ * Z_ * Y * X)
-        table = engine.run_planes(plan, lab, np.arange(len(tiles), dtype=np.int32), n_labels, px, offs,
-                                  Z_ * Y * X, Y * X, X, C_, Z_)
-        host = torch.empty(table.shape, dtype=torch.float64, pin_memory=True)
-        host.copy_(table, non_blocking=True)
-        outs.append((host, table))
+        engine.run_planes(plan, lab[p0:p1], np.arange(len(tiles), dtype=np.int32), n_labels[p0:p1], px, offs,
+                          Z_ * Y * X, Y * X, X, C_, Z_, out=table[int(rows[p0]) : int(rows[p1])])
+        p0 = p1
+    host = torch.empty(table.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(table, non_blocking=True)
     cur.synchronize()
-    values = np.concatenate([h.numpy() for h, _ in outs]) if outs else np.zeros((0, plan.n_columns))
-    return values, np.concatenate(n_all) if n_all else np.zeros(0, np.int64)
+    return host.numpy(), n_labels
 
 
 def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | None = None,
-                  chunk_bytes: int = 48 << 20) -> ExtractionTable:
+                  chunk_bytes: int = 160 << 20) -> ExtractionTable:
     """Fast public entry point: tree + host (or device) arrays in, dense per-object table out.
 
     Does what ``process_tree_masks`` + ``extract_tree`` + the pivot of ``format_extraction`` do
@@ -259,7 +285,11 @@ def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | No
         [np.repeat(np.asarray(keep, dtype=np.int64), n_labels), np.concatenate([np.arange(1, k + 1) for k in n_labels])],
         axis=1,
     ) if n_labels.sum() else np.zeros((0, 2), np.int64)
-    return ExtractionTable(objects, names, values[:, cols] if len(cols) else values[:, :0])
+    if not len(cols):
+        values = values[:, :0]
+    elif not np.array_equal(cols, np.arange(values.shape[1])):  # duplicate instructions share a dense column
+        values = values[:, cols]
+    return ExtractionTable(objects, names, values)
 
 
 def _results_from_dense(plan, dense, row_of_item, inst_of_item):

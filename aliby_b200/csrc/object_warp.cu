@@ -646,7 +646,9 @@ __device__ __noinline__ void shape_edt_warp(u32 n, int h, int w, u32 slot_off, u
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const u32 off = (dd < best[u]) ? d64 : 0u;
-          const u32 m2 = min((u32)g[kk[u] - off], (u32)g[kk[u] + off]);
+          const u32 ga = g[kk[u] - off], gb = g[kk[u] + off];
+          u32 m2;  // plain 32-bit min: the compiler otherwise packs the two bytes into a 16x2 min + unpack
+          asm("min.u32 %0, %1, %2;" : "=r"(m2) : "r"(ga), "r"(gb));
           best[u] = min(best[u], m2 * m2 + dd);
         }
         dd += step; step += 2; d64 += 64;

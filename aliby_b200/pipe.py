@@ -97,3 +97,40 @@ def get_profiles_from_state(state: dict, pipeline: dict):
         for table in wide[1:]:
             profiles = profiles.join(table, keys=[f"metadata_{k}" for k in ("tp", "tile", "object", "label")])
     return profiles
+
+
+def profiles_from_tables(tables, object_name: str, prefix: str = "extract"):
+    """Profile table of one extract step straight from dense per-time-point results.
+
+    ``tables[tp]`` is an :class:`aliby_b200.extract.ExtractionTable` (or ``None`` for a time point without
+    objects).  Produces what :func:`get_profiles_from_state` builds for a step named ``{prefix}_{object_name}``
+    (pipe_core.py:482-497): ``metadata_tile, metadata_label, <sorted features>, metadata_object, metadata_tp``
+    (uint16), rows concatenated over time points — without the per-item Python lists."""
+    import pyarrow as pa
+
+    parts = []
+    for tp, tab in enumerate(tables):
+        if tab is None or not len(tab.objects):
+            continue
+        t = tab.to_arrow()
+        t = t.rename_columns([{"tile": "metadata_tile", "label": "metadata_label"}.get(c, c) for c in t.column_names])
+        t = t.append_column("metadata_object", pa.array([object_name] * len(t), pa.string()))
+        t = t.append_column("metadata_tp", pa.array(np.full(len(t), tp, dtype=np.uint16), pa.uint16()))
+        parts.append(t)
+    if not parts:
+        return pa.Table.from_pylist([], schema=pa.schema([
+            pa.field("metadata_tile", pa.int64()), pa.field("metadata_label", pa.int64()),
+            pa.field("metadata_object", pa.string()), pa.field("metadata_tp", pa.int64())]))
+    return pa.concat_tables(parts)
+
+
+def write_profiles(profiles, output_path, pipeline_name: str):
+    """``<output_path>/profiles/<pipeline_name>.parquet`` with zstd compression (pipe_core.py:403,411-413)."""
+    from pathlib import Path
+
+    import pyarrow.parquet as pq
+
+    path = Path(output_path) / "profiles" / f"{pipeline_name}.parquet"
+    path.parent.mkdir(parents=True, exist_ok=True)
+    pq.write_table(profiles, path, compression="zstd")
+    return path

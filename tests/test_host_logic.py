@@ -191,3 +191,34 @@ def test_sharded_extraction_two_ranks_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD_OK 5" in outs[0]
+
+
+def test_profiles_from_dense_tables_match_item_path(tmp_path):
+    """Dense tables -> profile parquet == the reference-shaped path (format_extraction + get_profiles_from_state)."""
+    import pyarrow.parquet as pq
+
+    from aliby_b200 import pipe
+    from aliby_b200.extract import ExtractionTable
+
+    rng = np.random.default_rng(5)
+    insts = [("None", "None", "area"), (1, "max", "median"), (0, "max", "mean")]
+    names = ["/".join(str(x) for x in i) + f"/{i[-1]}" for i in insts]
+    state = {"data": {"extract_nuclei": []}}
+    tables = []
+    for tp in range(3):
+        objs = np.array([(t, l) for t in range(2) for l in range(1, 3 + tp)], dtype=np.int64)
+        vals = rng.normal(size=(len(objs), len(insts)))
+        vals[0, 1] = np.nan  # absent label -> NaN row cell
+        tables.append(ExtractionTable(objs, names, vals))
+        items = tuple(((int(t), int(l)), i) for (t, l) in objs for i in insts)
+        state["data"]["extract_nuclei"].append((items, vals.reshape(-1).tolist()))
+    want = pipe.get_profiles_from_state(state, {"steps": {"extract_nuclei": {}}})
+    got = pipe.profiles_from_tables(tables, "nuclei")
+    assert got.column_names == want.column_names and got.schema.field("metadata_tp").type == "uint16"
+    for c in want.column_names:
+        a, b = got.column(c).to_pylist(), want.column(c).to_pylist()
+        assert all((x == y) or (x != x and y != y) for x, y in zip(a, b, strict=True)), c
+    path = pipe.write_profiles(got, tmp_path, "pos001")
+    back = pq.read_table(path)
+    assert back.num_rows == got.num_rows and back.column_names == got.column_names
+    assert pq.ParquetFile(path).metadata.row_group(0).column(0).compression == "ZSTD"

@@ -18,7 +18,7 @@ __device__ __forceinline__ double u128_to_double(unsigned __int128 v) {
   return (double)(u64)(v >> 64) * 18446744073709551616.0 + (double)(u64)v;
 }
 
-__device__ double moment_of_inertia(const ChanStats& c) {
+__device__ __forceinline__ double moment_of_inertia(const ChanStats& c) {
   // cell.py:232-265 with coordinates relative to the bbox origin (central moments are
   // translation invariant): mu20 = m20 - m10^2 / m00, eta = mu / m00^2
   if (c.sum == 0) return nan("");
@@ -48,7 +48,7 @@ __global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const C
     double minor = 0, major = 0;
     if (cd.metric == ABX_M_ECCENTRICITY || cd.metric == ABX_M_VOLUME || cd.metric == ABX_M_MINOR_AXIS ||
         cd.metric == ABX_M_MAJOR_AXIS) {
-      const ShapeStats s = shape[obj];
+      const ShapeStats& s = shape[obj];
       minor = rint(sqrt((double)s.max_nn2));                       // np.round: half to even
       major = rint(sqrt((double)s.max_dn2) + s.sum_top / 2.0);
     }
@@ -74,13 +74,13 @@ __global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const C
   } else if (cd.metric == ABX_M_IMBACKGROUND || cd.metric == ABX_M_BACKGROUND_MAX5) {
     const int p = find_plane(plane_base, n_planes, obj);
     const u32 nb = recs[n_objects + p].n;
-    const ChanStats c = chan[(i64)(n_objects + p) * n_requests + cd.request];
+    const ChanStats& c = chan[(i64)(n_objects + p) * n_requests + cd.request];  // only the fields used are loaded
     if (nb) {
       if (cd.metric == ABX_M_IMBACKGROUND) v = ((double)c.med_lo + (double)c.med_hi) / 2.0;
       else v = (double)c.top5_sum / (double)(nb < 5u ? nb : 5u);  // np.mean(np.sort(bg)[-5:])
     }
   } else {
-    const ChanStats c = chan[(i64)obj * n_requests + cd.request];
+    const ChanStats& c = chan[(i64)obj * n_requests + cd.request];  // only the fields used are loaded
     const bool add = requests[cd.request].reduction == ABX_RED_ADD;
     switch (cd.metric) {
       case ABX_M_MEAN: v = r.n ? (double)c.sum / n : kNaN; break;

@@ -54,14 +54,17 @@ __device__ __forceinline__ void emit_piece(abx_object_rec* __restrict__ recs, in
 // bit j of the result <-> halfword j of (w0..w3) equals `label`
 __device__ __forceinline__ u32 eq_mask8(const u32 (&w)[4], u32 label) {
   const u32 pair = label | (label << 16);
-  u32 m = 0;
+  // carry-free "halfword != 0" test: bit 15 / 31 of nz is set iff the low / high halfword of x is non-zero
+  u32 nz[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const u32 x = w[j] ^ pair;
-    m |= ((x & 0xFFFFu) == 0u ? 1u : 0u) << (2 * j);
-    m |= ((x >> 16) == 0u ? 2u : 0u) << (2 * j);
+    nz[j] = (((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) & 0x80008000u;
   }
-  return m;
+  // gather the eight flag bits: low halfwords -> even positions, high halfwords -> odd positions
+  const u32 a = (nz[0] >> 15) | (nz[1] >> 13) | (nz[2] >> 11) | (nz[3] >> 9);  // bits {0,16},{2,18},{4,20},{6,22}
+  const u32 ne = (a & 0x55u) | ((a >> 15) & 0xAAu);
+  return ne ^ 0xFFu;
 }
 
 __device__ __forceinline__ u32 bitpos_sum8(u32 m) {  // sum of the positions of the set bits of an 8-bit mask

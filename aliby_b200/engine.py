@@ -194,6 +194,34 @@ def _workspace(device, nbytes: int):
     return buf
 
 
+_meta_cache: dict = {}
+
+
+def _device_meta(device, plane_tile: np.ndarray, plane_base: np.ndarray, tile_offset: np.ndarray):
+    """tile_offset (i64) | plane_tile (i32) | plane_base (i32) as ONE device buffer, uploaded with one
+    asynchronous copy from pinned staging and cached by content: a pipeline calls the extract step with the
+    same tile table at every time point (and the bench with identical arguments at every step), so the usual
+    call uploads nothing and the host never blocks."""
+    import torch
+
+    blob = tile_offset.tobytes() + plane_tile.tobytes() + plane_base.tobytes()
+    key = (str(device), blob)
+    hit = _meta_cache.get(key)
+    if hit is not None:
+        torch.cuda.current_stream(device).wait_event(hit._abx_ready)  # no-op on the uploading stream
+        return hit
+    if len(_meta_cache) >= 64:
+        _meta_cache.pop(next(iter(_meta_cache)))
+    host = torch.frombuffer(bytearray(blob), dtype=torch.uint8).pin_memory()
+    dev = torch.empty(len(blob), dtype=torch.uint8, device=device)
+    dev.copy_(host, non_blocking=True)
+    _meta_cache[key] = dev
+    dev._abx_host = host  # keep the pinned staging alive until the copy has certainly run
+    dev._abx_ready = torch.cuda.Event()
+    dev._abx_ready.record(torch.cuda.current_stream(device))
+    return dev
+
+
 def pixel_dtype_enum(torch_dtype) -> int:
     name = str(torch_dtype).replace("torch.", "")
     if name not in _DTYPES:
@@ -238,8 +266,7 @@ def run_planes(
         raise IndexError(f"index {plan.max_channel} is out of bounds for axis 1 with size {n_channels}")
     base = np.zeros(P + 1, dtype=np.int32)
     np.cumsum(n_labels, out=base[1:])
-    meta = torch.from_numpy(np.concatenate([np.asarray(plane_tile, dtype=np.int32), base])).to(device)
-    offs = torch.from_numpy(np.ascontiguousarray(tile_offset, dtype=np.int64)).to(device)
+    meta = _device_meta(device, np.asarray(plane_tile, dtype=np.int32), base, np.ascontiguousarray(tile_offset, dtype=np.int64))
     req_t, col_t = plan.device_arrays(device)
 
     a = nat.ExtractArgs()
@@ -247,15 +274,16 @@ def run_planes(
     a.label_dtype = nat.U16
     a.n_planes, a.H, a.W = P, H, W
     a.label_plane_stride, a.label_row_stride = labels.stride(0), labels.stride(1)
-    a.plane_tile = meta.data_ptr()
-    a.plane_base = meta.data_ptr() + 4 * P
+    n_tiles = len(tile_offset)
+    a.tile_offset = meta.data_ptr()  # int64 [n_tiles] first (8-byte aligned), then the two int32 arrays
+    a.plane_tile = meta.data_ptr() + 8 * n_tiles
+    a.plane_base = meta.data_ptr() + 8 * n_tiles + 4 * P
     a.n_objects = n_objects
     a.with_background = int(plan.with_background)
     a.pixels = pixels.data_ptr() if plan.requests else None
     a.pixel_dtype = pixel_dtype_enum(pixels.dtype) if plan.requests else nat.U16
-    a.n_tiles = len(tile_offset)
+    a.n_tiles = n_tiles
     a.C, a.Z = max(1, n_channels), max(1, n_z)
-    a.tile_offset = offs.data_ptr()
     a.chan_stride, a.z_stride, a.row_stride = int(chan_stride), int(z_stride), int(row_stride)
     a.requests = req_t.data_ptr()
     a.n_requests = len(plan.requests)
@@ -275,5 +303,5 @@ def run_planes(
     a.workspace_bytes = ws.numel()
     with torch.cuda.device(device):
         nat.check(lib.abx_extract(C.byref(a)), "abx_extract")
-    # meta/offs must outlive the launch: the caching allocator only reuses them stream-ordered
+    # meta must outlive the launch: it is kept alive by the per-device cache
     return out

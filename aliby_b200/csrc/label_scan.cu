@@ -9,6 +9,10 @@
 // (strip, band, object).  The first version (one warp per 256-pixel row chunk, one set of atomics
 // per row run) executed 2.35 warp instructions per pixel and ran at 0.6 TB/s
 // (profiles/r01e_summary.md).
+#include <cstring>
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace {
@@ -87,18 +91,53 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA (cp.async.bulk.tensor) plumbing: one elected lane brings a [kRowBatch rows x 256 columns] box of the
+// label plane into the warp's staging buffer and the 32 lanes wait on the buffer's mbarrier.  Boxes that stick out
+// of the plane are zero-filled by the hardware (label 0 = background), so ragged edges need no special case.
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  u32 done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_box(u32 dst, const CUtensorMap* tmap, int x, int y, int z, u32 bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+template <bool kTma>
 __global__ void __launch_bounds__(kScanThreads)
-label_scan_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int W, i64 plane_stride, i64 row_stride,
-                  const int32_t* __restrict__ plane_base, abx_object_rec* __restrict__ recs, int n_objects,
-                  int vec_ok, u32* err) {
-  __shared__ uint4 stage_all[kScanWarps][2][kRowBatch][32];  // 8 KB per warp
+label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __restrict__ labels, int n_planes, int H, int W,
+                  i64 plane_stride, i64 row_stride, const int32_t* __restrict__ plane_base,
+                  abx_object_rec* __restrict__ recs, int n_objects, int vec_ok, u32* err) {
+  __shared__ __align__(128) uint4 stage_all[kScanWarps][2][kRowBatch][32];  // 8 KB per warp
+  __shared__ __align__(8) u64 bars[kScanWarps][2];
   const u32 lane = lane_id();
-  uint4 (*stage)[kRowBatch][32] = stage_all[threadIdx.x >> 5];
-  const i64 gwarp = (i64)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  uint4 (*stage)[kRowBatch][32] = stage_all[warp];
+  const i64 gwarp = (i64)blockIdx.x * kScanWarps + warp;
   const i64 nwarps = (i64)gridDim.x * kScanWarps;
   const int col_groups = (W + 255) >> 8;
   const int bands = (H + kBandRows - 1) / kBandRows;
   const i64 total = (i64)n_planes * bands * col_groups;
+  u32 parity0 = 0, parity1 = 0;  // phase of the two mbarriers (warp-uniform)
+  if (kTma) {
+    if (lane == 0) {
+      mbar_init(smem_u32(&bars[warp][0]), 1);
+      mbar_init(smem_u32(&bars[warp][1]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
 
   for (i64 unit = gwarp; unit < total; unit += nwarps) {
     const int cg = (int)(unit % col_groups);
@@ -106,15 +145,24 @@ label_scan_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int 
     const int band = (int)(t % bands);
     const int p = (int)(t / bands);
     const u32 c0 = (u32)cg * 256u + lane * 8u;
-    if (c0 >= (u32)W) continue;
+    if (!kTma && c0 >= (u32)W) continue;  // (TMA: the whole warp stays converged; such lanes read zeros)
     const bool full = vec_ok && c0 + 8u <= (u32)W;  // aligned 128-bit copies are legal for this strip
     const int r_begin = band * kBandRows, r_end = min(H, r_begin + kBandRows);
     const uint16_t* src = labels + (i64)p * plane_stride + c0;
     const int base = plane_base[p];
     const u32 n_labels = (u32)(plane_base[p + 1] - base);
 
-    // rows [r0, r0 + kRowBatch) -> stage[buf]; the lane only ever reads back what it copied itself
+    // rows [r0, r0 + kRowBatch) -> stage[buf]
     auto issue = [&](int r0, int buf) {
+      if constexpr (kTma) {
+        __syncwarp();  // every lane has finished reading the buffer that is overwritten
+        if (lane == 0) {
+          const u32 bar = smem_u32(&bars[warp][buf]);
+          mbar_expect_tx(bar, kRowBatch * 512u);
+          tma_load_box(smem_u32(&stage[buf][0][0]), &tmap, cg * 256, r0, p, bar);
+        }
+      } else {
+      // fallback (unaligned strides, planes smaller than a box): the lane copies what it will read back itself
 #pragma unroll
       for (int u = 0; u < kRowBatch; ++u) {
         const int r = r0 + u;
@@ -129,6 +177,17 @@ label_scan_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int 
         }
       }
       cp_async_commit();
+      }
+    };
+    auto wait_for = [&](int buf, bool more_in_flight) {
+      if (kTma) {
+        if (buf == 0) { mbar_wait(smem_u32(&bars[warp][0]), parity0); parity0 ^= 1u; }
+        else { mbar_wait(smem_u32(&bars[warp][1]), parity1); parity1 ^= 1u; }
+      } else if (more_in_flight) {
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
     };
 
     Piece cur;
@@ -137,8 +196,9 @@ label_scan_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int 
     int buf = 0;
 #pragma unroll 1
     for (int r0 = r_begin; r0 < r_end; r0 += kRowBatch, buf ^= 1) {
-      if (r0 + kRowBatch < r_end) { issue(r0 + kRowBatch, buf ^ 1); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
+      const bool more = r0 + kRowBatch < r_end;
+      if (more) issue(r0 + kRowBatch, buf ^ 1);
+      wait_for(buf, more);
       const int rows = min(kRowBatch, r_end - r0);
 #pragma unroll 1
       for (int u = 0; u < rows; ++u) {
@@ -218,6 +278,34 @@ __global__ void label_max_kernel(const uint16_t* __restrict__ labels, int n_plan
 
 }  // namespace
 
+// The tensor map of the label planes (u16, dims W x H x P, box 256 x kRowBatch x 1), or false when the layout
+// does not qualify for TMA (unaligned base / strides, planes smaller than one box) or the driver lacks the encoder.
+static bool make_label_tensor_map(const abx_extract_args* a, CUtensorMap* tm) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return false;
+  const i64 plane_stride = a->n_planes > 1 ? a->label_plane_stride : (i64)a->H * a->label_row_stride;
+  if ((reinterpret_cast<uintptr_t>(a->labels) & 15u) || a->label_row_stride % 8 || plane_stride % 8 || a->W < 256 ||
+      a->H < kRowBatch || a->label_row_stride < a->W || plane_stride < (i64)a->H * a->label_row_stride)
+    return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->n_planes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)a->label_row_stride * 2u, (cuuint64_t)plane_stride * 2u};
+  const cuuint32_t box[3] = {256u, (cuuint32_t)kRowBatch, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(a->labels), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, cudaStream_t st) {
   const int n_rec = a->n_objects + a->n_planes;
   init_records_kernel<<<(n_rec + 255) / 256, 256, 0, st>>>(recs, a->n_objects, a->n_planes, a->H, a->W, err);
@@ -228,9 +316,16 @@ int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err,
   if (blocks > cap) blocks = cap;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(a->labels) & 15u) == 0) && (a->label_row_stride % 8 == 0) &&
                      (a->label_plane_stride % 8 == 0);
-  label_scan_kernel<<<(int)blocks, kScanThreads, 0, st>>>(
-      static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,
-      a->plane_base, recs, a->n_objects, vec_ok, err);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (make_label_tensor_map(a, &tm))
+    label_scan_kernel<true><<<(int)blocks, kScanThreads, 0, st>>>(
+        tm, static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,
+        a->plane_base, recs, a->n_objects, vec_ok, err);
+  else
+    label_scan_kernel<false><<<(int)blocks, kScanThreads, 0, st>>>(
+        tm, static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,
+        a->plane_base, recs, a->n_objects, vec_ok, err);
   if (a->with_background)
     background_count_kernel<<<a->n_planes, 256, 0, st>>>(recs, a->plane_base, a->n_objects, a->H, a->W);
   return abx_check_cuda(cudaGetLastError(), "label_scan");

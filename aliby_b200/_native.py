@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libaliby_b200.so")
 
 # enums of include/aliby_b200.h
-U8, U16, U32, F32 = 0, 1, 2, 3
-RED_MAX, RED_ADD = 0, 1
+U8, U16, U32, F32, F64 = 0, 1, 2, 3, 4
+RED_MAX, RED_ADD, RED_DIV = 0, 1, 2
 
 METRIC = {
     "area": 0,
@@ -48,6 +48,7 @@ EDT_METRICS = {4, 5, 6, 7, 8}
 CONICAL_METRIC = 6
 
 F_MEDIAN, F_TOP2P5, F_TOP5, F_WRAPSQ, F_MOI = 1, 2, 4, 8, 16
+F_HAS_DIV = 0x40000000
 
 EXPORTS = (
     "abx_version",

@@ -34,8 +34,9 @@ int abx_validate(const abx_extract_args* a) {
   if (a->n_planes > 0 && (a->H <= 0 || a->W <= 0 || a->H > 32767 || a->W > 32767))
     return abx_set_error(ABX_ERR_INVALID, "plane size %d x %d outside [1, 32767]", a->H, a->W);
   if (a->n_requests > 0) {
-    if (a->pixel_dtype != ABX_U8 && a->pixel_dtype != ABX_U16)
-      return abx_set_error(ABX_ERR_UNSUPPORTED, "pixel dtype %d has no kernel (uint8/uint16); there is no CPU fallback",
+    if (a->pixel_dtype != ABX_U8 && a->pixel_dtype != ABX_U16 && a->pixel_dtype != ABX_F32 && a->pixel_dtype != ABX_F64)
+      return abx_set_error(ABX_ERR_UNSUPPORTED,
+                           "pixel dtype %d has no kernel (uint8/uint16/float32/float64); there is no CPU fallback",
                            a->pixel_dtype);
     if (a->Z < 1 || a->C < 1) return abx_set_error(ABX_ERR_INVALID, "C and Z must be >= 1");
     if (a->row_stride < 1 || a->row_stride >= (1LL << 25))
@@ -132,6 +133,7 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   if ((rc = launch_object_edt_warp(args, ws, st))) return rc;
   mark(3);
   if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
+  if ((rc = launch_object_float(args, ws, st))) return rc;  // floating-point requests (float pixels, `div`)
   if ((rc = launch_shape_edt(args, ws, st))) return rc;
   mark(4);
   if ((rc = launch_finalize(args, ws, st))) return rc;
@@ -200,6 +202,10 @@ extern "C" int abx_crop_tiles(const void* frame, int32_t dtype, int32_t C, int32
     crop_tiles_kernel<float><<<(unsigned)lines, threads, 0, st>>>(static_cast<const float*>(frame), C, Z, chan_stride,
                                                                   z_stride, row_stride, tile_origin, n_tiles, h, w,
                                                                   static_cast<float*>(out));
+  else if (dtype == ABX_F64)
+    crop_tiles_kernel<double><<<(unsigned)lines, threads, 0, st>>>(static_cast<const double*>(frame), C, Z, chan_stride,
+                                                                   z_stride, row_stride, tile_origin, n_tiles, h, w,
+                                                                   static_cast<double*>(out));
   else
     return abx_set_error(ABX_ERR_UNSUPPORTED, "abx_crop_tiles: dtype %d has no kernel", dtype);
   return abx_check_cuda(cudaGetLastError(), "crop_tiles");

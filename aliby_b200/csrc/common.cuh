@@ -23,6 +23,23 @@ struct ChanStats {
   u32 med_lo, med_hi;  // the two middle order statistics (equal for odd n)
 };
 
+// The same 96-byte slot for a request whose values are floating point (float pixels or the `div` reducer).
+struct FloatStats {
+  double sum, sumsq;      // sum x, sum x^2
+  double css;             // sum (x - mean)^2  (two-pass, like np.std)
+  double moi;             // moment_of_inertia, final value (cell.py:232-265)
+  double top2p5_sum, top5_sum;
+  double med_lo, med_hi;  // the two middle order statistics
+  double vmin, vmax;
+  u32 has_nan;            // any NaN among the object's values: every statistic is NaN, like NumPy
+  u32 pad_;
+};
+static_assert(sizeof(FloatStats) <= sizeof(ChanStats), "FloatStats must fit the ChanStats slot");
+
+__host__ __device__ __forceinline__ bool request_is_float(int pixel_dtype, int reduction) {
+  return pixel_dtype == ABX_F32 || pixel_dtype == ABX_F64 || reduction == ABX_RED_DIV;
+}
+
 // Raw per-object output of the three chained EDTs (cell.py:207-229).
 struct ShapeStats {
   double sum_nn;   // sum of sqrt(nn^2) over the object   (conical_volume / 4)
@@ -55,6 +72,7 @@ int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cud
 int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_object_float(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int abx_sqrt_table_entries();
 

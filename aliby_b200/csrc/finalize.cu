@@ -30,11 +30,41 @@ __device__ __forceinline__ double moment_of_inertia(const ChanStats& c) {
   return u128_to_double(n20) / d3 + u128_to_double(n02) / d3;
 }
 
+// intensity metric of a floating-point request (object_float.cu), NumPy float semantics
+__device__ double float_metric(const FloatStats& f, int metric, u32 n_px, int pixel_dtype) {
+  const double kNaN = nan("");
+  if (n_px == 0)  // absent label: np.sum of an empty selection is 0.0, every other statistic is NaN
+    return (metric == ABX_M_TOTAL || metric == ABX_M_TOTAL_SQUARED) ? 0.0 : kNaN;
+  if (f.has_nan) return kNaN;  // a NaN poisons every statistic
+  const double n = (double)n_px;
+  // np.median averages the two middle values in the array's own dtype: float32 pixels round in float32
+  const double med = pixel_dtype == ABX_F32 ? (double)(((float)f.med_lo + (float)f.med_hi) / 2.0f)
+                                            : (f.med_lo + f.med_hi) / 2.0;
+  switch (metric) {
+    case ABX_M_MEAN: return f.sum / n;
+    case ABX_M_TOTAL: return f.sum;
+    case ABX_M_TOTAL_SQUARED: return f.sumsq;
+    case ABX_M_STD: return sqrt(f.css / n);
+    case ABX_M_MEDIAN:
+    case ABX_M_IMBACKGROUND: return med;
+    case ABX_M_MAX2P5PC: return f.top2p5_sum / (double)(u32)ceil(n * 0.025);
+    case ABX_M_MAX5PX_MEDIAN: {
+      if (n_px <= 5u) return kNaN;
+      return med == 0.0 ? kNaN : (f.top5_sum / 5.0) / med;
+    }
+    case ABX_M_BACKGROUND_MAX5: return f.top5_sum / (double)(n_px < 5u ? n_px : 5u);
+    case ABX_M_MOMENT_OF_INERTIA: return f.moi;
+    case ABX_M_MAX: return f.vmax;
+    case ABX_M_MIN: return f.vmin;
+    default: return kNaN;  // ratio
+  }
+}
+
 __global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __restrict__ chan,
                                 const ShapeStats* __restrict__ shape, const int32_t* __restrict__ plane_base,
                                 int n_planes, int n_objects, const abx_request* __restrict__ requests,
                                 int n_requests, const abx_column* __restrict__ columns, int n_columns,
-                                double* __restrict__ table) {
+                                int pixel_dtype, double* __restrict__ table) {
   const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (i64)n_objects * n_columns) return;
   const int obj = (int)(idx / n_columns);
@@ -71,6 +101,11 @@ __global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const C
       case ABX_M_BBOX_CMAX: v = r.n ? (double)r.cmax : kNaN; break;
       default: break;
     }
+  } else if (request_is_float(pixel_dtype, requests[cd.request].reduction)) {
+    const bool bg = cd.metric == ABX_M_IMBACKGROUND || cd.metric == ABX_M_BACKGROUND_MAX5;
+    const int row = bg ? n_objects + find_plane(plane_base, n_planes, obj) : obj;
+    v = float_metric(*reinterpret_cast<const FloatStats*>(&chan[(i64)row * n_requests + cd.request]), cd.metric,
+                     recs[row].n, pixel_dtype);
   } else if (cd.metric == ABX_M_IMBACKGROUND || cd.metric == ABX_M_BACKGROUND_MAX5) {
     const int p = find_plane(plane_base, n_planes, obj);
     const u32 nb = recs[n_objects + p].n;
@@ -120,6 +155,6 @@ int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t
   const i64 blocks = (cells + threads - 1) / threads;
   finalize_kernel<<<(unsigned)blocks, threads, 0, st>>>(ws.recs, ws.chan, ws.shape, a->plane_base, a->n_planes,
                                                        a->n_objects, a->requests, a->n_requests, a->columns,
-                                                       a->n_columns, a->table);
+                                                       a->n_columns, a->pixel_dtype, a->table);
   return abx_check_cuda(cudaGetLastError(), "finalize");
 }

@@ -172,6 +172,7 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
 
     for (int q = 0; q < n_requests; ++q) {
       const abx_request rq = requests[q];
+      if (rq.reduction == ABX_RED_DIV) continue;  // floating-point request: object_float.cu (block-uniform)
       const u32 feats = is_bg ? rq.bg_features : rq.features;
       ChanStats* dst = out + (i64)obj * n_requests + q;
       if (n == 0 || (is_bg && feats == 0)) {  // block-uniform
@@ -353,7 +354,7 @@ int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStre
       a->n_requests, ws.recs, ws.chan, ws.stats_list, ws.list_counts)
   if (a->pixel_dtype == ABX_U16) ABX_LAUNCH_OS(uint16_t);
   else if (a->pixel_dtype == ABX_U8) ABX_LAUNCH_OS(uint8_t);
-  else return abx_set_error(ABX_ERR_UNSUPPORTED, "object_stats: pixel dtype %d has no kernel", a->pixel_dtype);
+  else return ABX_OK;  // float pixels: every request belongs to object_float.cu
 #undef ABX_LAUNCH_OS
   return abx_check_cuda(cudaGetLastError(), "object_stats");
 }

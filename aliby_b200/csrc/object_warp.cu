@@ -532,6 +532,7 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
 #pragma unroll 1
       for (int q = 0; q < n_requests; ++q) {
         const abx_request rq = requests[q];
+        if (rq.reduction == ABX_RED_DIV) continue;  // floating-point request: object_float.cu
         request_stats<PX>(rec.n, slot_off, cap, px0 + (i64)rq.channel * chan_stride, (u32)px_row_stride, z_stride, Z,
                           rq.reduction, rq.features, chan + (i64)obj * n_requests + q);
       }
@@ -898,7 +899,7 @@ int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cud
   cm.counters = ws.list_counts + 2;
   if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st);
   if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st);
-  return abx_set_error(ABX_ERR_UNSUPPORTED, "object_stats_warp: pixel dtype %d has no kernel", a->pixel_dtype);
+  return ABX_OK;  // float pixels: every request belongs to object_float.cu
 }
 
 int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {

@@ -131,7 +131,7 @@ def compile_instructions(instructions: list) -> Plan:
         key = (int(ch), red)
         if key not in req_index:
             req_index[key] = len(plan.requests)
-            plan.requests.append([int(ch), nat.RED_MAX if red == "max" else nat.RED_ADD, 0, 0])
+            plan.requests.append([int(ch), {"max": nat.RED_MAX, "add": nat.RED_ADD, "div": nat.RED_DIV}[red], 0, 0])
         return req_index[key]
 
     def column(req, metric_name):
@@ -155,10 +155,6 @@ def compile_instructions(instructions: list) -> Plan:
             if has_pixels:
                 if REDUCERS[red] != "ufunc":
                     raise Exception(f"{REDUCERS[red]} is an invalid reducer.")  # distributors.py:24
-                if red == "div":
-                    raise NotImplementedError(
-                        "Z reduction 'div' (np.divide.reduce) has no CUDA kernel in aliby_b200 and there is no CPU fallback"
-                    )
             if metric in SHAPE_METRICS:
                 cols = tuple(column(-1, m) for m in SHAPE_METRICS[metric])
             else:
@@ -179,7 +175,8 @@ def compile_instructions(instructions: list) -> Plan:
     return plan
 
 
-_DTYPES = {"uint8": nat.U8, "uint16": nat.U16}
+_DTYPES = {"uint8": nat.U8, "uint16": nat.U16, "float32": nat.F32, "float64": nat.F64}
+PIXEL_DTYPES = tuple(_DTYPES)  # numpy / torch dtype names with a kernel
 _workspaces: dict = {}
 
 
@@ -226,7 +223,7 @@ def pixel_dtype_enum(torch_dtype) -> int:
     name = str(torch_dtype).replace("torch.", "")
     if name not in _DTYPES:
         raise NotImplementedError(
-            f"pixel dtype {name} has no CUDA kernel in aliby_b200 (uint8/uint16 only) and there is no CPU fallback"
+            f"pixel dtype {name} has no CUDA kernel in aliby_b200 (uint8/uint16/float32/float64) and there is no CPU fallback"
         )
     return _DTYPES[name]
 
@@ -290,7 +287,7 @@ def run_planes(
     a.columns = col_t.data_ptr()
     a.n_columns = n_cols
     a.need_edt = int(plan.need_edt)
-    a.request_feature_union = 0
+    a.request_feature_union = nat.F_HAS_DIV if any(r[1] == nat.RED_DIV for r in plan.requests) else 0
     a.table = out.data_ptr()
     a.stream = torch.cuda.current_stream(device).cuda_stream
     if stage_events is not None:  # 6 handles from abx_event_create (bench.py: live per-stage timing)

@@ -79,10 +79,10 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
     else:
         if isinstance(pixels, np.ndarray):
             if plan.requests:
-                if pixels.dtype not in (np.uint8, np.uint16):
+                if str(pixels.dtype) not in engine.PIXEL_DTYPES:
                     raise NotImplementedError(
-                        f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200 (uint8/uint16 only) "
-                        "and there is no CPU fallback"
+                        f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200 "
+                        "(uint8/uint16/float32/float64) and there is no CPU fallback"
                     )
                 px_dev = torch.from_numpy(np.ascontiguousarray(pixels)).to(device, non_blocking=True)
             else:
@@ -259,9 +259,9 @@ def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | No
         return ExtractionTable(np.zeros((0, 2), np.int64), names, np.zeros((0, len(names))))
     host_inputs = isinstance(pixels, np.ndarray) and not isinstance(masks[keep[0]], torch.Tensor)
     if host_inputs:
-        if plan.requests and pixels.dtype not in (np.uint8, np.uint16):
+        if plan.requests and str(pixels.dtype) not in engine.PIXEL_DTYPES:
             raise NotImplementedError(
-                f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200 (uint8/uint16 only) and there is no CPU fallback"
+                f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200 (uint8/uint16/float32/float64) and there is no CPU fallback"
             )
         values, n_labels = _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes)
     else:

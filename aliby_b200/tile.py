@@ -72,7 +72,7 @@ class TileView:
                 device = torch.device("cuda", torch.cuda.current_device())
             f = self.frame
             if isinstance(f, np.ndarray):
-                if f.dtype not in (np.uint8, np.uint16):
+                if str(f.dtype) not in ("uint8", "uint16", "float32", "float64"):
                     raise NotImplementedError(f"pixel dtype {f.dtype} has no CUDA kernel in aliby_b200")
                 f = torch.from_numpy(np.ascontiguousarray(f))
             self._dev = f.to(device, non_blocking=True).contiguous()
@@ -96,7 +96,7 @@ class TileView:
         if len(self.origins) == 0:
             return out
         org = torch.from_numpy(self.origins.astype(np.int32)).to(f.device)
-        dt = {torch.uint8: nat.U8, torch.uint16: nat.U16, torch.float32: nat.F32}[f.dtype]
+        dt = {torch.uint8: nat.U8, torch.uint16: nat.U16, torch.float32: nat.F32, torch.float64: nat.F64}[f.dtype]
         with torch.cuda.device(f.device):
             nat.check(
                 nat.lib().abx_crop_tiles(

@@ -13,6 +13,8 @@
  *                      total_squared, median, max2p5pc, max5px_median, std, moment_of_inertia),
  *                      src/extraction/core/functions/trap.py:6-43 (background = label 0),
  *                      src/aliby/tile/tiler.py:309-366 (tile crop, fused through tile offsets)
+ *                      Requests whose values are floating point (float32/float64 pixels, e.g. CropTiler's
+ *                      standard_scale tiler.py:95-102, or the `div` reducer) take a generic fp64 kernel.
  *   abx_shape_edt      src/extraction/core/functions/cell.py:30-40,160-229 (eccentricity,
  *                      volume, conical_volume, min_maj_approximation: three chained EDTs)
  *   abx_finalize       the scalar arithmetic of the functions above + the dense
@@ -49,10 +51,11 @@ typedef enum abx_status {
   ABX_ERR_WORKSPACE = -4  /* workspace too small */
 } abx_status;
 
-typedef enum abx_dtype { ABX_U8 = 0, ABX_U16 = 1, ABX_U32 = 2, ABX_F32 = 3 } abx_dtype;
+typedef enum abx_dtype { ABX_U8 = 0, ABX_U16 = 1, ABX_U32 = 2, ABX_F32 = 3, ABX_F64 = 4 } abx_dtype;
 
-/* Z reductions of REDUCTION_FUNS (loaders.py:110-127) that are legal ufuncs. */
-typedef enum abx_reduction { ABX_RED_MAX = 0, ABX_RED_ADD = 1 } abx_reduction;
+/* Z reductions of REDUCTION_FUNS (loaders.py:110-127) that are legal ufuncs.  DIV is np.divide.reduce: a
+ * left fold of true divisions whose result is float64 whatever the pixel dtype (distributors.py:19-21). */
+typedef enum abx_reduction { ABX_RED_MAX = 0, ABX_RED_ADD = 1, ABX_RED_DIV = 2 } abx_reduction;
 
 /* Dense-table column kinds. 0-15 need only the label plane, 16+ a pixel request. */
 typedef enum abx_metric {
@@ -90,6 +93,9 @@ typedef enum abx_metric {
 #define ABX_F_TOP5 4u
 #define ABX_F_WRAPSQ 8u   /* total_squared with the square wrapped in the pixel dtype */
 #define ABX_F_MOI 16u
+/* abx_extract_args.request_feature_union only: some request uses ABX_RED_DIV (the float kernel must run
+ * even though the pixels are integers) */
+#define ABX_F_HAS_DIV 0x40000000u
 
 /* One (channel, Z-reduction) pair of the extraction tree. */
 typedef struct abx_request {
@@ -130,7 +136,7 @@ typedef struct abx_extract_args {
    * which covers a dense (tiles,C,Z,h,w) array and a tile crop fused straight out of
    * full frames (tile_offset = frame base + row0*row_stride + col0). */
   const void* pixels;
-  int32_t pixel_dtype; /* ABX_U8 | ABX_U16 */
+  int32_t pixel_dtype; /* ABX_U8 | ABX_U16 (integer kernels) | ABX_F32 | ABX_F64 (float kernel: CropTiler / NaN tiles) */
   int32_t n_tiles;
   int32_t C, Z;
   const int64_t* tile_offset; /* [n_tiles] */
@@ -141,7 +147,7 @@ typedef struct abx_extract_args {
   const abx_column* columns;   /* device, [n_columns] */
   int32_t n_columns;
   int32_t need_edt;            /* bit 0: ECCENTRICITY/VOLUME/MINOR/MAJOR requested, bit 1: CONICAL_VOLUME */
-  int32_t request_feature_union; /* OR of features|bg_features over requests (host copy) */
+  int32_t request_feature_union; /* OR of features|bg_features over requests (host copy), | ABX_F_HAS_DIV */
   /* output: [n_objects][n_columns] float64, row-major */
   double* table;
   /* scratch */

@@ -243,7 +243,7 @@ def test_error_behaviour(ab):
     with pytest.raises(Exception, match="invalid reducer"):
         ab.process_tree_masks({0: {"None": ["mean"]}}, lab, px, ab.extract_tree)
     with pytest.raises(NotImplementedError):
-        ab.process_tree_masks({0: {"max": ["mean"]}}, lab, px.astype(np.float32), ab.extract_tree)
+        ab.process_tree_masks({0: {"max": ["mean"]}}, lab, px.astype(np.int32), ab.extract_tree)
     # no objects -> the reference never reaches the lookups, neither do we
     items, got = ab.process_tree_masks({0: {"max": ["not_a_metric"]}}, np.zeros_like(lab), px, ab.extract_tree)
     assert items == ()
@@ -322,3 +322,70 @@ def test_extract_table_pipelined_matches_item_api(ab):
         assert_same(tab.values, want, 0.0, f"chunk_bytes={chunk}")
         assert [tuple(o) for o in tab.objects.tolist()] == [it[0] for it in items[::10]]
     assert tab.to_arrow().num_rows == want.shape[0]
+
+
+def _float_case(ab, pixels, labels, tree, rtol, atol=1e-12):
+    from oracle import fast
+
+    items, got = ab.process_tree_masks(tree, labels, pixels, ab.extract_tree)
+    o_items, want = fast.run_tree(tree, labels, pixels)
+    assert [tuple(i[1]) for i in items] == [tuple(i[1]) for i in o_items]
+    ga, _ = as_float_pairs(got)
+    wa, _ = as_float_pairs(want)
+    metrics = np.array([it[1][2] for it in items])
+    exact = np.isin(metrics, ["median", "max", "min", "imBackground"])  # order statistics: bit-exact
+    assert_same(ga[exact], wa[exact], 0.0, "float order statistics")
+    # fp64 sums: relative tolerance, plus an absolute floor for quantities that are rounding noise in NumPy
+    # itself (the std of a constant object is ~1e-17 instead of 0)
+    g, w_ = ga[~exact], wa[~exact]
+    noise = np.abs(w_) < atol
+    assert_same(np.where(noise, 0.0, g), np.where(noise, 0.0, w_), rtol, "float sums")
+    assert (np.abs(g[noise & ~np.isnan(w_)]) < atol).all()
+    return items, ga
+
+
+FLOAT_METRICS = ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median", "moment_of_inertia",
+                 "max", "min"]
+
+
+def test_float64_pixels_cropTiler_standard_scale(ab):
+    """C1 variant with float64 pixels: what CropTiler's standard_scale hands to extraction (tiler.py:95-102)."""
+    from aliby_b200 import synth
+
+    px16, labels = synth.make_field(1011, (540, 600), 2, 90, n_z=2)
+    pix = px16.astype(np.float64)
+    mean = pix.mean(axis=(-3, -2, -1))
+    std = pix.std(axis=(-3, -2, -1))
+    pixels = ((pix.T - mean.T) / std.T).T  # per (tile, channel) standardisation, negative and positive values
+    tree = {"None": {"None": ["area", "centroid_x", "eccentricity"]},
+            0: {"max": FLOAT_METRICS + ["imBackground", "background_max5"]}, 1: {"add": FLOAT_METRICS}}
+    _float_case(ab, pixels, labels, tree, 1e-9)
+
+
+def test_float32_pixels_and_nan_tile(ab):
+    """float32 pixels (NumPy computes in float32: agreement within 1e-5) and a NaN-poisoned object
+    (NaN tiles of tiler.py:644-646): every statistic of an object that holds a NaN is NaN."""
+    from aliby_b200 import synth
+
+    px16, labels = synth.make_field(1012, (200, 260), 1, 25, semi_axes=(4, 12))
+    pixels = (px16.astype(np.float32) / np.float32(7.0))
+    tree = {0: {"max": ["mean", "median", "max", "min", "total", "std", "max2p5pc"]}}
+    # float32 arithmetic inside NumPy: 1e-7 relative noise on values of ~1e4 (std of a constant object ~1e-3)
+    _float_case(ab, pixels, labels, tree, 2e-5, atol=5e-3)
+    poisoned = pixels.astype(np.float64)
+    rr, cc = np.nonzero(labels == 3)
+    poisoned[0, 0, 0, rr[0], cc[0]] = np.nan
+    items, ga = _float_case(ab, poisoned, labels, tree, 1e-9)
+    rows = np.array([it[0][1] == 3 for it in items])
+    assert np.isnan(ga[rows]).all() and not np.isnan(ga[~rows]).any()
+
+
+def test_div_reducer_on_integer_pixels(ab):
+    """`div` = np.divide.reduce over Z: float64 values out of uint16 pixels, next to integer requests of the same tree."""
+    from aliby_b200 import synth
+
+    pixels, labels = synth.make_field(1013, (180, 240), 2, 20, n_z=3, semi_axes=(4, 12))
+    pixels = np.maximum(pixels, 1)  # no division by zero
+    tree = {0: {"div": ["mean", "median", "std", "total", "max2p5pc", "max"], "max": ["mean", "median", "total"]},
+            1: {"add": ["median", "total"], "div": ["median"]}}
+    _float_case(ab, pixels, labels, tree, 1e-9)

@@ -40,7 +40,7 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     assert b"label dtype" in lib.abx_last_error()
     a.label_dtype = nat.U16
     a.n_planes, a.H, a.W, a.n_objects = 4, 2160, 2160, 8000
-    a.n_requests, a.pixel_dtype, a.C, a.Z, a.row_stride = 5, nat.F32, 5, 1, 2160
+    a.n_requests, a.pixel_dtype, a.C, a.Z, a.row_stride = 5, nat.U32, 5, 1, 2160
     assert lib.abx_extract_workspace_bytes(ctypes.byref(a), ctypes.byref(need)) == -2
     a.pixel_dtype = nat.U16
     assert lib.abx_extract_workspace_bytes(ctypes.byref(a), ctypes.byref(need)) == 0
@@ -65,8 +65,10 @@ def test_plan_compiler_matches_reference_flattening():
     assert plan.requests[2][2] == nat.F_TOP5 | nat.F_MEDIAN and plan.requests[2][3] == nat.F_MEDIAN
     for bad, exc in [({0: {"max": ["nope"]}}, KeyError), ({0: {"nope": ["mean"]}}, KeyError),
                      ({0: {"median": ["mean"]}}, Exception), ({"None": {"None": ["mean"]}}, TypeError),
-                     ({0: {"div": ["mean"]}}, NotImplementedError)]:
+                     ]:
         assert isinstance(engine.compile_tree(bad).error, exc), bad
+    div = engine.compile_tree({0: {"div": ["mean"]}})  # np.divide.reduce: served by the float kernel
+    assert div.error is None and div.requests[0][1] == nat.RED_DIV
 
 
 def test_registry_names_match_reference():

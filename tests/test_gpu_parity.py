@@ -389,3 +389,48 @@ def test_div_reducer_on_integer_pixels(ab):
     tree = {0: {"div": ["mean", "median", "std", "total", "max2p5pc", "max"], "max": ["mean", "median", "total"]},
             1: {"add": ["median", "total"], "div": ["median"]}}
     _float_case(ab, pixels, labels, tree, 1e-9)
+
+
+def test_config_c4_zstack_full_size(ab):
+    """BASELINE.json configs[3]: 5 channels x 16 z x 2048^2, Z reduced inside the gather ('max' and one 'add' channel)."""
+    from aliby_b200 import synth
+
+    rng = np.random.default_rng(synth.CONFIG_SEEDS["C4"])
+    labels = synth.ellipse_labels(rng, (2048, 2048), 1500)
+    # cheap synthetic stack (the Poisson generator of synth needs minutes at this size)
+    base = rng.integers(100, 4000, size=(5, 1, 2048, 2048), dtype=np.uint16)
+    zmod = rng.integers(0, 3000, size=(5, 16, 1, 1), dtype=np.uint16)
+    noise = rng.integers(0, 64, size=(5, 16, 2048, 2048), dtype=np.uint16)
+    pixels = (base + zmod + noise)[None]
+    tree = {"None": {"None": ["area", "centroid_x", "centroid_y"]}}
+    for ch in range(4):
+        tree[ch] = {"max": ["mean", "median", "max2p5pc", "std", "max"]}
+    tree[4] = {"add": ["mean", "median", "total", "max5px_median"]}
+    items, got = against_oracle(ab, tree, labels, pixels)
+    a, _ = as_float_pairs(got)
+    metrics = np.array([it[1][2] for it in items])
+    chans = np.array([str(it[1][0]) for it in items])
+    tot = a[(metrics == "total") & (chans == "4")].sum()
+    assert tot == pixels[0, 4].astype(np.uint64).sum(axis=0)[labels > 0].sum()
+
+
+def test_config_c3_trap_position_real_geometry(ab):
+    """BASELINE.json configs[2]: 1200^2 frames, 40 tiles of 96^2, 5 channels; extraction fused with the tile crop,
+    time point by time point, with per-tile background metrics (global_settings.py:37-53 feature set)."""
+    from aliby_b200.tile import FusedTiler
+    from aliby_b200 import synth
+    from oracle import fast, port
+
+    frames, centres, labels = synth.make_trap_position(synth.CONFIG_SEEDS["C3"], n_tp=3)
+    tiler = FusedTiler(frames, centres, 96)
+    tree = {"None": {"None": ["area", "volume", "eccentricity", "centroid_x", "centroid_y"]}}
+    for ch in range(5):
+        tree[ch] = {"max": ["mean", "median", "std", "imBackground", "max5px_median"]}
+    for tp in range(3):
+        view = tiler.run_tp(tp)["pixels"]
+        masks = [m for m in labels[tp]]
+        items, got = ab.process_tree_masks(tree, masks, view, ab.extract_tree)
+        crop = port.crop_tiles(frames[tp], centres, (96, 96), (), tp)
+        o_items, want = fast.run_tree(tree, masks, crop)
+        assert [tuple(i[0]) for i in o_items] == [i[0] for i in items]
+        check_items(items, got, as_float_pairs(want)[0])

@@ -224,3 +224,24 @@ def test_profiles_from_dense_tables_match_item_path(tmp_path):
     back = pq.read_table(path)
     assert back.num_rows == got.num_rows and back.column_names == got.column_names
     assert pq.ParquetFile(path).metadata.row_group(0).column(0).compression == "ZSTD"
+
+
+def test_init_step_seam_matches_reference_partial_shape():
+    """init_step_fn seam (pipe.py:47-72, pipe_core.py:68-81): extract_* -> partial(process, measure_fn, tree, **kwargs)."""
+    from functools import partial
+
+    from aliby_b200 import extract, pipe
+
+    tree = {"None": {"None": ["area"]}, 0: {"max": ["mean"]}}
+    step = pipe.init_step("extract_nuclei", {"tree": tree, "kwargs": {"ncores": None}})
+    assert isinstance(step, partial) and step.func is extract.process_tree_masks
+    assert step.keywords["measure_fn"] is extract.extract_tree and step.keywords["tree"] is tree
+    assert step.keywords["ncores"] is None
+    baby = pipe.init_step("extract_cells", {"tree": tree}, overlap=True)
+    assert baby.func is extract.process_tree_masks_overlap and baby.keywords["measure_fn"].keywords == {"overlap": True}
+    with pytest.raises(ValueError, match="missing required 'tree'"):
+        pipe.init_step("extract_nuclei", {})
+    with pytest.raises(NotImplementedError):
+        pipe.init_step("extractmulti_nuclei", {"tree": tree})
+    with pytest.raises(ImportError):  # the reference is not installed next to us in this container
+        pipe.init_step("segment_nuclei", {})

@@ -434,3 +434,36 @@ def test_config_c3_trap_position_real_geometry(ab):
         o_items, want = fast.run_tree(tree, masks, crop)
         assert [tuple(i[0]) for i in o_items] == [i[0] for i in items]
         check_items(items, got, as_float_pairs(want)[0])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_label_planes(ab, seed):
+    """Randomised planes that stress the scan and the window classes: salt-and-pepper labels (several ids inside
+    one 8-pixel strip), touching blocks, rings with holes, objects wider than 64 px, id gaps, several tiles with
+    different label counts, odd plane sizes, uint8/uint16, Z in {1, 2, 3}, max/add."""
+    rng = np.random.default_rng(1000 + seed)
+    H, W = int(rng.integers(17, 150)), int(rng.integers(17, 300))
+    n_tiles = int(rng.integers(1, 4))
+    Z = int(rng.integers(1, 4))
+    dtype = np.uint8 if seed % 3 == 0 else np.uint16
+    masks = []
+    for _ in range(n_tiles):
+        lab = np.zeros((H, W), np.uint16)
+        next_id = 1
+        for _ in range(int(rng.integers(0, 12))):  # blocks, some overlapping (later ones overwrite), some with holes
+            h, w = int(rng.integers(1, min(H, 90))), int(rng.integers(1, min(W, 120)))
+            r, c = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+            lab[r : r + h, c : c + w] = next_id
+            if h > 6 and w > 6 and rng.random() < 0.5:
+                lab[r + 2 : r + h - 2, c + 2 : c + w - 2] = 0 if rng.random() < 0.5 else next_id + 1
+                next_id += 1
+            next_id += int(rng.integers(1, 3))  # id gaps
+        speck = rng.random((H, W)) < 0.03  # salt and pepper: many ids per strip, 1-pixel objects
+        lab[speck] = rng.integers(1, max(2, next_id + 3), size=int(speck.sum()))
+        masks.append(lab)
+    pixels = rng.integers(0, np.iinfo(dtype).max + 1, size=(n_tiles, 2, Z, H, W)).astype(dtype)
+    tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume",
+                              "min_maj_approximation"]},
+            0: {"max": INTENSITY + ["max", "min", "imBackground", "background_max5"]},
+            1: {"add": ["mean", "median", "total", "total_squared", "max2p5pc", "max5px_median", "std"]}}
+    against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)

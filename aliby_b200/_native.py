@@ -58,6 +58,7 @@ EXPORTS = (
     "abx_label_scan",
     "abx_label_max",
     "abx_crop_tiles",
+    "abx_crop_tiles_padded",
     "abx_event_create",
     "abx_event_destroy",
     "abx_event_elapsed_ms",
@@ -149,6 +150,10 @@ def lib() -> C.CDLL:
     ]
     handle.abx_crop_tiles.argtypes = [
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+    ]
+    handle.abx_crop_tiles_padded.argtypes = [
+        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
     ]
     handle.abx_event_create.argtypes = [C.POINTER(C.c_void_p)]

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -209,4 +210,112 @@ extern "C" int abx_crop_tiles(const void* frame, int32_t dtype, int32_t C, int32
   else
     return abx_set_error(ABX_ERR_UNSUPPORTED, "abx_crop_tiles: dtype %d has no kernel", dtype);
   return abx_check_cuda(cudaGetLastError(), "crop_tiles");
+}
+
+// ---- tile crop with the reference's out-of-frame rules (tiler.py:601-650) -----------------------------------
+// np.pad(tile, [[0, 0], [top, bottom], [left, right]], "median") pads axis by axis: first the missing ROWS of
+// every column get that column's median over the rows that exist, then the missing COLUMNS of every row (the new
+// rows included) get that row's median over the columns that exist; integer medians are rounded half to even
+// (numpy/lib/arraypad.py: _get_stats + _round_if_needed).  Tiles with more than 25 % padding become NaN tiles in
+// the reference: that decision (and the float64 promotion it implies) is the caller's, see aliby_b200/tile.py.
+namespace {
+template <typename T>
+__global__ void crop_clip_kernel(const T* __restrict__ frame, int C, int Z, i64 chan_stride, i64 z_stride, i64 row_stride,
+                                 int H, int W, const int32_t* __restrict__ origin, int h, int w, T* __restrict__ out) {
+  const i64 line = blockIdx.x;  // (tile, c, z, row)
+  const int r = (int)(line % h);
+  i64 t = line / h;
+  const int z = (int)(t % Z); t /= Z;
+  const int c = (int)(t % C); t /= C;
+  const int tile = (int)t;
+  const int fr = origin[2 * tile] + r, fc0 = origin[2 * tile + 1];
+  T* dst = out + line * w;
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {
+    const int fc = fc0 + x;
+    dst[x] = (fr >= 0 && fr < H && fc >= 0 && fc < W)
+                 ? frame[(i64)c * chan_stride + (i64)z * z_stride + (i64)fr * row_stride + fc] : T(0);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T median_of_line(const T* __restrict__ base, i64 stride, int n) {
+  // n <= a tile side: rank every element by counting (ties broken by position), pick the middle one(s)
+  const int k_lo = (n - 1) / 2, k_hi = n / 2;
+  double lo = 0, hi = 0;
+  for (int i = 0; i < n; ++i) {
+    const T xi = base[(i64)i * stride];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const T xj = base[(i64)j * stride];
+      rank += (xj < xi) || (xj == xi && j < i);
+    }
+    if (rank == k_lo) lo = (double)xi;
+    if (rank == k_hi) hi = (double)xi;
+  }
+  if (std::is_integral<T>::value) return (T)rint((lo + hi) / 2.0);  // np.round: half to even
+  if (sizeof(T) == 4) return (T)(((float)lo + (float)hi) / 2.0f);    // float32 mean of the two middle values
+  return (T)((lo + hi) / 2.0);
+}
+
+// axis 0: one thread per (plane, existing column): fill the missing rows with the column median
+// axis 1: one thread per (plane, row): fill the missing columns with the row median over the existing columns
+template <typename T>
+__global__ void pad_median_kernel(T* __restrict__ out, const int32_t* __restrict__ origin, int n_tiles, int CZ, int H, int W,
+                                  int h, int w, int axis) {
+  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_plane = axis == 0 ? w : h;
+  if (idx >= (i64)n_tiles * CZ * per_plane) return;
+  const int k = (int)(idx % per_plane);
+  const i64 plane = idx / per_plane;
+  const int tile = (int)(plane / CZ);
+  const int r0 = origin[2 * tile], c0 = origin[2 * tile + 1];
+  const int rv0 = max(0, -r0), rv1 = min(h, H - r0);  // rows of the tile that exist in the frame
+  const int cv0 = max(0, -c0), cv1 = min(w, W - c0);
+  if (rv1 <= rv0 || cv1 <= cv0) return;  // entirely outside: a NaN tile for the caller
+  T* p = out + plane * (i64)h * w;
+  if (axis == 0) {
+    if ((rv0 == 0 && rv1 == h) || k < cv0 || k >= cv1) return;
+    const T m = median_of_line(p + (i64)rv0 * w + k, (i64)w, rv1 - rv0);
+    for (int r = 0; r < rv0; ++r) p[(i64)r * w + k] = m;
+    for (int r = rv1; r < h; ++r) p[(i64)r * w + k] = m;
+  } else {
+    if (cv0 == 0 && cv1 == w) return;
+    const T m = median_of_line(p + (i64)k * w + cv0, (i64)1, cv1 - cv0);
+    for (int c = 0; c < cv0; ++c) p[(i64)k * w + c] = m;
+    for (int c = cv1; c < w; ++c) p[(i64)k * w + c] = m;
+  }
+}
+
+template <typename T>
+int crop_padded(const void* frame, int C, int Z, i64 chan_stride, i64 z_stride, i64 row_stride, int H, int W,
+                const int32_t* origin, int n_tiles, int h, int w, void* out, cudaStream_t st) {
+  const i64 lines = (i64)n_tiles * C * Z * h;
+  if (lines > 2147483647LL) return abx_set_error(ABX_ERR_INVALID, "abx_crop_tiles_padded: too many rows");
+  const int threads = w >= 128 ? 128 : (w >= 64 ? 64 : 32);
+  crop_clip_kernel<T><<<(unsigned)lines, threads, 0, st>>>(static_cast<const T*>(frame), C, Z, chan_stride, z_stride,
+                                                          row_stride, H, W, origin, h, w, static_cast<T*>(out));
+  for (int axis = 0; axis < 2; ++axis) {
+    const i64 n = (i64)n_tiles * C * Z * (axis == 0 ? w : h);
+    pad_median_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(static_cast<T*>(out), origin, n_tiles, C * Z, H, W, h,
+                                                                       w, axis);
+  }
+  return abx_check_cuda(cudaGetLastError(), "crop_tiles_padded");
+}
+}  // namespace
+
+extern "C" int abx_crop_tiles_padded(const void* frame, int32_t dtype, int32_t C, int32_t Z, int64_t chan_stride,
+                                     int64_t z_stride, int64_t row_stride, int32_t H, int32_t W,
+                                     const int32_t* tile_origin, int32_t n_tiles, int32_t h, int32_t w, void* out,
+                                     void* stream) {
+  if (!frame || !tile_origin || !out || C < 1 || Z < 1 || n_tiles < 0 || h < 1 || w < 1 || H < 1 || W < 1)
+    return abx_set_error(ABX_ERR_INVALID, "abx_crop_tiles_padded: bad arguments");
+  if (n_tiles == 0) return ABX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case ABX_U8: return crop_padded<uint8_t>(frame, C, Z, chan_stride, z_stride, row_stride, H, W, tile_origin, n_tiles, h, w, out, st);
+    case ABX_U16: return crop_padded<uint16_t>(frame, C, Z, chan_stride, z_stride, row_stride, H, W, tile_origin, n_tiles, h, w, out, st);
+    case ABX_F32: return crop_padded<float>(frame, C, Z, chan_stride, z_stride, row_stride, H, W, tile_origin, n_tiles, h, w, out, st);
+    case ABX_F64: return crop_padded<double>(frame, C, Z, chan_stride, z_stride, row_stride, H, W, tile_origin, n_tiles, h, w, out, st);
+    default: return abx_set_error(ABX_ERR_UNSUPPORTED, "abx_crop_tiles_padded: dtype %d has no kernel", dtype);
+  }
 }

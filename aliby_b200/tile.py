@@ -8,10 +8,13 @@ records only the per-tile origins; the extraction kernels read the windows in pl
 pixel leaves HBM once), and :meth:`TileView.materialize` produces the reference's dense
 array on the device for consumers that want it (a segmenter).
 
-Out-of-bounds windows (median padding / NaN tiles of ``tiler.py:601-650``) have no CUDA
-kernel: the reference filters edge tiles at time point 0 (``tiler.py:685-690``) and its
-drift is pinned to zero in this fork, so they do not occur on the pipeline
-path; asking for one raises ``NotImplementedError`` (there is no CPU fallback).
+Windows that leave the frame follow ``if_out_of_bounds_pad`` (``tiler.py:601-650``): the tiles
+are then materialised on the device by ``abx_crop_tiles_padded`` (per-line median padding,
+integers rounded half to even), and a tile with more than 25 % padding becomes a NaN tile, which
+— exactly like ``np.stack`` of a float64 NaN tile with uint16 tiles in the reference — promotes
+the whole ``pixels`` array to float64 (served by the float kernel).  This is the cold path: the
+reference filters edge tiles at time point 0 (``tiler.py:685-690``) and its drift is pinned to
+zero in this fork.
 """
 
 from __future__ import annotations
@@ -42,14 +45,13 @@ class TileView:
         self.size = (size, size) if isinstance(size, int) else tuple(size)
         C_, Z_, H, W = frame.shape
         h, w = self.size
-        bad = (
-            (self.origins[:, 0] < 0) | (self.origins[:, 1] < 0) | (self.origins[:, 0] + h > H) | (self.origins[:, 1] + w > W)
-        )
-        if bad.any():
-            raise NotImplementedError(
-                f"tile windows {np.flatnonzero(bad).tolist()} leave the {H}x{W} frame: the median/NaN padding of "
-                "tiler.py:601-650 has no CUDA kernel and there is no CPU fallback"
-            )
+        r0, c0 = self.origins[:, 0], self.origins[:, 1]
+        # padding before / after on both axes (tiler.py:634-639)
+        pad = np.stack([np.maximum(0, -r0), np.maximum(0, r0 + h - H), np.maximum(0, -c0), np.maximum(0, c0 + w - W)], axis=1)
+        self.out_of_frame = pad.any(axis=1)
+        # tiler.py:644: ``(padding / 0.25 > tile_shape).any()`` broadcasts the (2, 2) padding against [h, w]
+        # column-wise: the "before" pads are compared with h, the "after" pads with w (reproduced as written)
+        self.nan_tiles = ((pad[:, [0, 2]] / 0.25 > h) | (pad[:, [1, 3]] / 0.25 > w)).any(axis=1)
         self._dev = None
 
     @property
@@ -59,7 +61,7 @@ class TileView:
 
     @property
     def dtype(self):
-        return self.frame.dtype
+        return np.dtype(np.float64) if self.nan_tiles.any() else self.frame.dtype
 
     def __len__(self):
         return len(self.origins)
@@ -79,14 +81,19 @@ class TileView:
         return self._dev
 
     def addressing(self, device=None):
-        """(device frame, tile element offsets, chan/z/row strides, C, Z) for the kernels."""
+        """(device pixels, tile element offsets, chan/z/row strides, C, Z) for the kernels."""
+        if self.out_of_frame.any():  # cold path: materialised tiles with the reference's padding rules
+            t = self.materialize(device)
+            n, C_, Z_, h, w = t.shape
+            return t, np.arange(n, dtype=np.int64) * (C_ * Z_ * h * w), Z_ * h * w, h * w, w, C_, Z_
         f = self.device_frame(device)
         C_, Z_, H, W = f.shape
         offs = self.origins[:, 0] * W + self.origins[:, 1]
         return f, offs.astype(np.int64), Z_ * H * W, H * W, W, C_, Z_
 
     def materialize(self, device=None):
-        """Dense ``(tiles, C, Z, h, w)`` device tensor (what ``Tiler.get_fczyx`` returns)."""
+        """Dense ``(tiles, C, Z, h, w)`` device tensor (what ``Tiler.get_fczyx`` returns, tiler.py:309-366),
+        including the median padding / NaN tiles of windows that leave the frame (tiler.py:601-650)."""
         import torch
 
         f = self.device_frame(device)
@@ -97,14 +104,27 @@ class TileView:
             return out
         org = torch.from_numpy(self.origins.astype(np.int32)).to(f.device)
         dt = {torch.uint8: nat.U8, torch.uint16: nat.U16, torch.float32: nat.F32, torch.float64: nat.F64}[f.dtype]
+        stream = C.c_void_p(torch.cuda.current_stream(f.device).cuda_stream)
         with torch.cuda.device(f.device):
-            nat.check(
-                nat.lib().abx_crop_tiles(
-                    f.data_ptr(), dt, C_, Z_, Z_ * H * W, H * W, W, org.data_ptr(), len(self.origins), h, w,
-                    out.data_ptr(), C.c_void_p(torch.cuda.current_stream(f.device).cuda_stream),
-                ),
-                "abx_crop_tiles",
-            )
+            if self.out_of_frame.any():
+                nat.check(
+                    nat.lib().abx_crop_tiles_padded(
+                        f.data_ptr(), dt, C_, Z_, Z_ * H * W, H * W, W, H, W, org.data_ptr(), len(self.origins), h, w,
+                        out.data_ptr(), stream,
+                    ),
+                    "abx_crop_tiles_padded",
+                )
+            else:
+                nat.check(
+                    nat.lib().abx_crop_tiles(
+                        f.data_ptr(), dt, C_, Z_, Z_ * H * W, H * W, W, org.data_ptr(), len(self.origins), h, w,
+                        out.data_ptr(), stream,
+                    ),
+                    "abx_crop_tiles",
+                )
+        if self.nan_tiles.any():  # np.stack of a float64 NaN tile with the others promotes everything to float64
+            out = out.to(torch.float64)
+            out[torch.from_numpy(np.flatnonzero(self.nan_tiles)).to(f.device)] = float("nan")
         return out
 
     def __array__(self, dtype=None, copy=None):

@@ -23,6 +23,7 @@
  *   abx_extract        all four, stream-ordered (one call per extract step and timepoint,
  *                      i.e. what src/aliby/pipe_core.py:217 invokes)
  *   abx_crop_tiles     src/aliby/tile/tiler.py:309-366 materialised (tiles, C, Z, h, w)
+ *   abx_crop_tiles_padded  the same with if_out_of_bounds_pad (tiler.py:601-650) for windows leaving the frame
  *
  * Conventions: plain C, no exceptions; every call returns 0 on success or a negative
  * abx_status, with a thread-local message behind abx_last_error().  The caller owns
@@ -180,6 +181,15 @@ int abx_label_max(const void* labels, int32_t label_dtype, int32_t n_planes, int
 int abx_crop_tiles(const void* frame, int32_t dtype, int32_t C, int32_t Z, int64_t chan_stride,
                    int64_t z_stride, int64_t row_stride, const int32_t* tile_origin /* [n_tiles][2] */,
                    int32_t n_tiles, int32_t h, int32_t w, void* out, void* stream);
+
+/* Tile crop with the reference's out-of-frame rule for windows that leave the H x W frame (tiler.py:601-650):
+ * the part inside the frame is copied, missing rows then missing columns are filled with np.pad's per-line
+ * "median" (integers rounded half to even).  Origins may be negative or beyond the frame.  Whether a tile has
+ * too much padding (> 25 %: a NaN tile in the reference) is the caller's decision. */
+int abx_crop_tiles_padded(const void* frame, int32_t dtype, int32_t C, int32_t Z, int64_t chan_stride,
+                          int64_t z_stride, int64_t row_stride, int32_t H, int32_t W,
+                          const int32_t* tile_origin /* [n_tiles][2] */, int32_t n_tiles, int32_t h, int32_t w,
+                          void* out, void* stream);
 
 /* Timing events for abx_extract_args.stage_events (thin wrappers over cudaEvent_t). */
 int abx_event_create(void** event);

@@ -467,3 +467,47 @@ def test_fuzz_random_label_planes(ab, seed):
             0: {"max": INTENSITY + ["max", "min", "imBackground", "background_max5"]},
             1: {"add": ["mean", "median", "total", "total_squared", "max2p5pc", "max5px_median", "std"]}}
     against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)
+
+
+def test_out_of_frame_tiles_golden_and_extraction(ab):
+    """if_out_of_bounds_pad (tiler.py:601-650): median-padded and NaN tiles, against the golden crops written by the
+    real reference, then extraction through padded / NaN tiles against the oracle on the reference-shaped crop."""
+    import torch
+
+    from aliby_b200.tile import TileView, tile_origins
+    from oracle import fast, port
+
+    g = load_golden("tile_crop.npz")
+    frame, centres, drifts = g["frame"], g["centres"], g["drifts"]  # frame: (Z, Y, X) of one channel
+    for tp in (0, 1):
+        view = TileView(frame[None], tile_origins(centres, 16, drifts, tp), 16)
+        tiles = view.materialize().cpu().numpy()  # (tiles, 1, Z, 16, 16)
+        for i in range(len(centres)):
+            want = g[f"tp{tp}_tile{i}"]
+            assert_same(tiles[i, 0], want, 0.0, f"tp{tp} tile{i}")
+        assert (tiles.dtype == np.float64) == any(g[f"tp{tp}_tile{i}"].dtype == np.float64 for i in range(len(centres)))
+
+    # extraction: uint16 frame, tiles hanging over every edge (<= 25 % -> median pad), then one NaN tile too
+    rng = np.random.default_rng(21)
+    fr = rng.integers(100, 4000, size=(2, 2, 90, 110)).astype(np.uint16)  # (C, Z, H, W)
+    size = 32
+    lab = np.zeros((size, size), np.uint16)
+    lab[3:14, 2:12] = 1
+    lab[18:30, 15:31] = 2
+    lab[0:6, 24:32] = 3
+    tree = {"None": {"None": ["area", "centroid_x"]}, 0: {"max": ["mean", "median", "std", "max2p5pc", "imBackground"]},
+            1: {"add": ["total", "median"]}}
+    for centres2 in ([(12, 12), (80, 100), (45, 10), (20, 104)], [(12, 12), (80, 100), (2, 50)]):
+        centres2 = np.asarray(centres2)
+        view = TileView(fr, tile_origins(centres2, size), size)
+        crop = port.crop_tiles(fr, centres2, (size, size), (), 0)  # the reference's own (tiles, C, Z, h, w)
+        assert view.out_of_frame.any() and (view.nan_tiles.any() == (crop.dtype == np.float64))
+        masks = [lab.copy() for _ in centres2]
+        items, got = ab.process_tree_masks(tree, masks, view, ab.extract_tree)
+        o_items, want = fast.run_tree(tree, masks, crop)
+        ga, _ = as_float_pairs(got)
+        wa, _ = as_float_pairs(want)
+        metrics = np.array([it[1][2] for it in items])
+        loose = np.isin(metrics, ["std", "mean", "total", "max2p5pc"]) if crop.dtype == np.float64 else (metrics == "std")
+        assert_same(ga[~loose], wa[~loose], 0.0, "padded tiles: exact metrics")
+        assert_same(ga[loose], wa[loose], RTOL_LOOSE, "padded tiles: fp64 sums")

@@ -342,26 +342,39 @@ def process_tree_masks_overlap(
     progress_bar: bool = False,
     overlap: bool = True,
     cp_measure_kwargs=None,
+    original_ids: bool = False,
 ):
     """BABY-style ``(tile, stack, label)`` enumeration (extract.py:456-517).
 
-    Like the live reference path, the ids enumerated for a stack are ``1..k`` with ``k`` the
-    number of distinct non-zero labels in that stack (``relabel_sequential`` ids), while the
-    measurement reads the plane of the *original* id; for
-    sequential labels — the supported case — both coincide."""
+    Default (``original_ids=False``) = the live reference path: the ids enumerated for a stack are ``1..k``
+    with ``k`` the number of distinct non-zero labels in that stack (``relabel_sequential`` ids), while the
+    measurement reads the plane of the id itself in the ORIGINAL labelling; for
+    sequential labels — the supported case of the reference — both coincide.
+
+    ``original_ids=True`` = what the reference's (uncalled) ``format_extraction_overlap`` was written for
+    (extract.py:602-682): sequential id ``j`` measures the object whose original id is the ``j``-th smallest
+    of its stack, and a third element ``inverse_mappings[(tile, stack)][j] -> original id`` is returned for
+    :func:`format_extraction_overlap`."""
     masks = _as_mask_list(masks)
     instructions = kv(flatten(tree))
     tile_stack_mask = []
+    inverse_mappings = {}
     for tile_i, masks_in_tile in enumerate(masks):
         for stack_i, stack_pixels in enumerate(masks_in_tile):
-            k = int(np.count_nonzero(np.unique(stack_pixels)))
-            tile_stack_mask.extend((tile_i, stack_i, mask_i) for mask_i in range(1, k + 1))
+            ids = np.unique(stack_pixels)
+            ids = ids[ids > 0]
+            inverse_mappings[(tile_i, stack_i)] = np.concatenate([[0], ids]).astype(np.int64)
+            tile_stack_mask.extend((tile_i, stack_i, mask_i) for mask_i in range(1, len(ids) + 1))
     tileid_instructions = tuple(product(tile_stack_mask, instructions))
     _last_items.update(items=tileid_instructions, objects=tile_stack_mask, plan=engine.compile_instructions(instructions))
     extra = {}
     if cp_measure_kwargs is not None:
         extra["cp_measure_kwargs"] = cp_measure_kwargs
+    if original_ids:
+        extra["inverse_mappings"] = inverse_mappings
     result = measure_fn(tileid_instructions, masks, pixels, ncores=ncores, progress_bar=progress_bar, **extra)
+    if original_ids:
+        return tileid_instructions, result, inverse_mappings
     return tileid_instructions, result
 
 
@@ -373,6 +386,7 @@ def extract_tree(
     progress_bar: bool = False,
     overlap: bool = False,
     cp_measure_kwargs=None,
+    inverse_mappings=None,
 ):
     """All measurements of ``tileid_instructions`` in one pass on the GPU (extract.py:304-375).
 
@@ -409,7 +423,7 @@ def extract_tree(
             plane_of[(tile_i, stack_i) if overlap else (tile_i,)] = len(planes)
             planes.append(plane)
             plane_tile.append(tile_i)
-            if overlap:  # ids 1..k, k = number of distinct labels of the stack (see docstring above)
+            if overlap and inverse_mappings is None:  # ids 1..k, k = number of distinct labels of the stack
                 n_labels.append(int(np.count_nonzero(np.unique(plane))))
             else:
                 n_labels.append(int(plane.max()) if plane.size else 0)
@@ -420,9 +434,12 @@ def extract_tree(
     obj_rows = np.empty(len(objects), dtype=np.int64)
     for k, obj in enumerate(objects):
         p = plane_of[tuple(obj[:-1])]
-        if not (1 <= obj[-1] <= n_labels[p]):
-            raise IndexError(f"index {obj[-1] - 1} is out of bounds for axis 0 with size {n_labels[p]}")
-        obj_rows[k] = base[p] + obj[-1] - 1
+        label = obj[-1]
+        if inverse_mappings is not None:  # sequential id -> original id of its (tile, stack)
+            label = int(inverse_mappings[tuple(obj[:-1])][label])
+        if not (1 <= label <= n_labels[p]):
+            raise IndexError(f"index {label - 1} is out of bounds for axis 0 with size {n_labels[p]}")
+        obj_rows[k] = base[p] + label - 1
     if row_of_item is None:
         row_of_item = np.repeat(obj_rows, n_inst)
         inst_of_item = np.tile(np.arange(n_inst), len(objects))
@@ -487,6 +504,47 @@ def format_extraction(instructions_result):
         for m in metrics_list:
             wide[m].append(row.get(m, None))
     return pa.Table.from_pydict(wide)
+
+
+def format_extraction_overlap(instructions_result):
+    """``(instructions, results, inverse_mappings)`` -> wide table keyed by the ORIGINAL label ids
+    (extract.py:602-682): like :func:`format_extraction`, with ``label = inverse_mappings[(tile, stack)][label]``
+    and the columns already renamed to ``metadata_tile`` / ``metadata_label``."""
+    import pyarrow as pa
+
+    instructions, results, inverse_mappings = instructions_result
+    names = ("tile", "label", "metric", "value")
+    formatted = {k: [] for k in names}
+    for inst, metrics in zip(instructions, results, strict=True):
+        tileid, stack_id, label = inst[0]
+        branch = "/".join(str(x) for x in inst[1])
+        original = int(inverse_mappings[tileid, stack_id][label])
+        if isinstance(metrics, (int, float)):
+            rows = [(f"{branch}/{inst[1][-1]}", metrics)]
+        elif isinstance(metrics, dict):
+            rows = [(f"{branch}/{k}", value) for k, values in metrics.items() for value in values]
+        elif isinstance(metrics, list):
+            rows = [(f"{branch}/{inst[1][-1]}", value) for value in metrics]
+        else:
+            rows = []
+        for name, value in rows:
+            formatted["tile"].append(tileid)
+            formatted["label"].append(original)
+            formatted["metric"].append(name)
+            formatted["value"].append(value)
+    pivoted: dict = {}
+    for t, lbl, m, v in zip(formatted["tile"], formatted["label"], formatted["metric"], formatted["value"], strict=True):
+        pivoted.setdefault((t, lbl), {"tile": t, "label": lbl})[m] = v
+    metrics_list = sorted(set(formatted["metric"]))
+    wide = {"tile": [], "label": []}
+    wide.update({m: [] for m in metrics_list})
+    for row in pivoted.values():
+        wide["tile"].append(row["tile"])
+        wide["label"].append(row["label"])
+        for m in metrics_list:
+            wide[m].append(row.get(m, None))
+    table = pa.Table.from_pydict(wide)
+    return table.rename_columns([{"tile": "metadata_tile", "label": "metadata_label"}.get(c, c) for c in table.column_names])
 
 
 def _format_dense(results: ExtractionResults, pa):

@@ -511,3 +511,36 @@ def test_out_of_frame_tiles_golden_and_extraction(ab):
         loose = np.isin(metrics, ["std", "mean", "total", "max2p5pc"]) if crop.dtype == np.float64 else (metrics == "std")
         assert_same(ga[~loose], wa[~loose], 0.0, "padded tiles: exact metrics")
         assert_same(ga[loose], wa[loose], RTOL_LOOSE, "padded tiles: fp64 sums")
+
+
+def test_overlap_original_ids_and_format(ab):
+    """(tile, stack, label) extraction keyed by the ORIGINAL, non-sequential ids — what the reference's
+    format_extraction_overlap (extract.py:602-682) was written for — against the oracle on each stack plane."""
+    from functools import partial
+
+    from oracle import fast
+
+    rng = np.random.default_rng(8)
+    H, W = 48, 64
+    pixels = rng.integers(50, 3000, size=(2, 2, 2, H, W)).astype(np.uint16)
+    masks = []
+    for t in range(2):
+        stacks = np.zeros((2, H, W), np.uint16)
+        stacks[0, 4:20, 5:25] = 7
+        stacks[0, 25:40, 30:60] = 3
+        stacks[1, 10:30, 15:40] = 12 if t == 0 else 5  # overlaps stack 0, non-sequential ids
+        masks.append(stacks)
+    tree = {"None": {"None": ["area", "centroid_x"]}, 0: {"max": ["mean", "median"]}, 1: {"add": ["total"]}}
+    items, got, inv = ab.process_tree_masks_overlap(tree, masks, pixels, partial(ab.extract_tree, overlap=True),
+                                                    original_ids=True)
+    assert [it[0] for it in items[::5]] == [(0, 0, 1), (0, 0, 2), (0, 1, 1), (1, 0, 1), (1, 0, 2), (1, 1, 1)]
+    assert inv[(0, 0)].tolist() == [0, 3, 7] and inv[(0, 1)].tolist() == [0, 12] and inv[(1, 1)].tolist() == [0, 5]
+    want = []
+    for (t, s, j), inst in items:
+        o_items, o_res = fast.run_tree({inst[0]: {inst[1]: [inst[2]]}}, masks[t][s], pixels[t : t + 1])
+        want.append(float(o_res[int(inv[(t, s)][j]) - 1]))
+    assert_same(np.asarray(got, dtype=float), np.asarray(want), 0.0, "overlap, original ids")
+    table = ab.format_extraction_overlap((items, got, inv))
+    assert table.column_names[:2] == ["metadata_tile", "metadata_label"]
+    keys = sorted(zip(table.column("metadata_tile").to_pylist(), table.column("metadata_label").to_pylist()))
+    assert keys == [(0, 3), (0, 7), (0, 12), (1, 3), (1, 5), (1, 7)]

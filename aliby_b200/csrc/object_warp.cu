@@ -262,7 +262,31 @@ __device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __rest
   // values of batch i0 (Z-reduced); the offsets are re-read from shared memory when the batch is consumed,
   // so that only the values live across the pipeline stage
   auto load_batch = [&](u32 i0, u32 (&xq)[kBatch]) {
-    u32 kq[kBatch];
+    if (i0 - lane + 32u * kBatch <= n) {
+      // whole batch inside the list (warp-uniform test): no predicates, so the compiler keeps the memory
+      // descriptor and the row stride in uniform registers instead of rebuilding them for every pixel
+      u32 go[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const u32 kq = offs[i0 + 32u * u];
+        go[u] = (kq >> 6) * rs + (kq & 63u);
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) xq[u] = (u32)__ldg(px + go[u]);
+      if (Z > 1) {
+#pragma unroll 1
+        for (int z = 1; z < Z; ++z) {
+          const PX* pz = px + (i64)z * z_stride;
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const u32 y = (u32)__ldg(pz + go[u]);
+            xq[u] = (red == ABX_RED_MAX) ? max(xq[u], y) : xq[u] + y;
+          }
+        }
+      }
+      return;
+    }
+    u32 kq[kBatch];  // ragged last batch (and the empty one past the end)
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const u32 i = i0 + 32u * u;

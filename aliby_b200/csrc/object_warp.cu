@@ -363,7 +363,7 @@ __device__ __noinline__ void moments_wide(u32 n, u32 slot_off, const PX* __restr
 // phase S: one (channel, reduction) request
 // ------------------------------------------------------------------------------------------------
 template <typename PX>
-__device__ __noinline__ void request_stats(u32 n, u32 slot_off, u32 cap, const PX* __restrict__ px, u32 rs, i64 z_stride, int Z,
+__device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, const PX* __restrict__ px, u32 rs, i64 z_stride, int Z,
                                            int reduction, u32 feats, ChanStats* __restrict__ dst) {
   const unsigned short* offs = reinterpret_cast<const unsigned short*>(dyn + slot_off);
   unsigned short* vals = reinterpret_cast<unsigned short*>(dyn + slot_off) + cap;

@@ -595,7 +595,7 @@ struct EdtSmem {
 // slot layout of the EDT kernel (byte offsets from the slot start)
 constexpr u32 kEdtTopOff = 512, kEdtGOff = 1024, kEdtRowbaseOff = 1024 + (kSide + 2) * kSide, kEdtOffsOff = kEdtRowbaseOff + 128;
 
-__device__ __noinline__ void shape_edt_warp(u32 n, int h, int w, u32 slot_off, u32 rmin, u32 cmin, bool want_conical,
+__device__ __forceinline__ void shape_edt_warp(u32 n, int h, int w, u32 slot_off, u32 rmin, u32 cmin, bool want_conical,
                                             const double* __restrict__ sqrt_tab, ShapeStats* __restrict__ dst) {
   EdtSmem s;
   s.rowmask = reinterpret_cast<u64*>(dyn + slot_off);

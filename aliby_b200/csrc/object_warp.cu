@@ -74,7 +74,7 @@ struct Queue {
 
 // phase M: row bitmasks (optional), row bases (optional) and the compact offset list
 template <bool kMasks>
-__device__ __noinline__ void build_list(const uint16_t* __restrict__ lab, i64 lab_rs, u32 label, int h, int w, u32 offs_off,
+__device__ __forceinline__ void build_list(const uint16_t* __restrict__ lab, i64 lab_rs, u32 label, int h, int w, u32 offs_off,
                                         u32 rowmask_off, u32 rowbase_off) {
   unsigned short* offs = reinterpret_cast<unsigned short*>(dyn + offs_off);
   u64* rowmask = reinterpret_cast<u64*>(dyn + rowmask_off);
@@ -352,11 +352,21 @@ __device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __rest
   cs.vmax = __reduce_max_sync(kFull, a_max);
 }
 
+// The wide variant out of line.  Its results travel through the (still unused) histogram area of the slot, so that
+// the caller's ChanStats never has to live in local memory for the sake of a by-reference argument.
 template <typename PX>
-__device__ __noinline__ void moments_wide(u32 n, u32 slot_off, const PX* __restrict__ px, u32 rs, i64 z_stride, int Z, int red,
-                                          bool want_moi, ChanStats& cs) {
+__device__ __noinline__ void moments_wide(u32 n, u32 slot_off, u32 hist_off, const PX* __restrict__ px, u32 rs, i64 z_stride,
+                                          int Z, int red, bool want_moi) {
+  ChanStats cs;
   moments_pass<PX, true>(n, reinterpret_cast<const unsigned short*>(dyn + slot_off), nullptr, px, rs, z_stride, Z, red,
                          want_moi, cs);
+  __syncwarp();
+  if (lane_id() == 0) {
+    u64* o = reinterpret_cast<u64*>(dyn + hist_off);
+    o[0] = cs.sum; o[1] = cs.sumsq; o[2] = cs.wrapsq; o[3] = cs.m10; o[4] = cs.m01; o[5] = cs.m20; o[6] = cs.m02;
+    o[7] = (u64)cs.vmin | ((u64)cs.vmax << 32);
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -372,7 +382,13 @@ __device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, cons
   const u32 lane = lane_id();
   const bool wide = reduction == ABX_RED_ADD && Z > 1;
   ChanStats cs;
-  if (wide) moments_wide<PX>(n, slot_off, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0, cs);
+  if (wide) {
+    moments_wide<PX>(n, slot_off, slot_off + 4u * cap, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0);
+    const u64* o = reinterpret_cast<const u64*>(hist);
+    cs.sum = o[0]; cs.sumsq = o[1]; cs.wrapsq = o[2]; cs.m10 = o[3]; cs.m01 = o[4]; cs.m20 = o[5]; cs.m02 = o[6];
+    cs.vmin = (u32)o[7]; cs.vmax = (u32)(o[7] >> 32);
+    __syncwarp();
+  }
   else moments_pass<PX, false>(n, offs, vals, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0, cs);
   cs.med_lo = cs.med_hi = 0;
   cs.top2p5_sum = cs.top5_sum = 0;
@@ -471,12 +487,11 @@ __device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, cons
 
 // L2 prefetch of the next object's windows: label rows, and one line pair per pixel row / request / z
 template <typename PX>
-__device__ __noinline__ void prefetch_object(const abx_object_rec& nr, u32 lo, u32 hi, const uint16_t* __restrict__ lab,
+__device__ __noinline__ void prefetch_object(u32 n_px, int nh, int nw, u32 lo, u32 hi, const uint16_t* __restrict__ lab,
                                                 i64 lab_rs, const PX* __restrict__ px, i64 px_rs, i64 chan_stride,
                                                 i64 z_stride, int Z, const abx_request* __restrict__ requests,
                                                 int n_requests) {
-  const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
-  if (nr.n <= lo || nr.n > hi || nh > kSide || nw > kSide) return;
+  if (n_px <= lo || n_px > hi || nh > kSide || nw > kSide) return;
   const u32 lane = lane_id();
   const i64 tail = (i64)nw - 1;
   for (int r = lane; r < nh; r += 32) {
@@ -529,7 +544,8 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
     if (nxt < cm.n_total && nxt < cm.n_objects) {
       const abx_object_rec nr = cm.recs[nxt];
       const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
-      prefetch_object<PX>(nr, lo, hi, cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
+      prefetch_object<PX>(nr.n, (int)(nr.rmax - nr.rmin) + 1, (int)(nr.cmax - nr.cmin) + 1, lo, hi,
+                          cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
                           cm.lab_row_stride,
                           pixels + tile_offset[cm.plane_tile[np]] + (i64)nr.rmin * px_row_stride + nr.cmin, px_row_stride,
                           chan_stride, z_stride, Z, requests, n_requests);
@@ -829,7 +845,7 @@ object_edt_warp(const Common cm, int want_conical, const double* __restrict__ sq
     if (nxt < cm.n_objects) {
       const abx_object_rec nr = cm.recs[nxt];
       const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
-      prefetch_object<uint16_t>(nr, lo, hi,
+      prefetch_object<uint16_t>(nr.n, (int)(nr.rmax - nr.rmin) + 1, (int)(nr.cmax - nr.cmin) + 1, lo, hi,
                                 cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
                                 cm.lab_row_stride, nullptr, 0, 0, 0, 0, nullptr, 0);
     }

@@ -155,27 +155,44 @@ __device__ __forceinline__ void find_ranks16(const unsigned short* h16, u32 nb, 
     if (lane >= (u32)o) { icnt += c; icb += q; }
   }
   const u32 ecnt = icnt - cnt, ecb = icb - cb;
-#pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
-    const u32 tr = ranks[j];
-    const u32 owner = (u32)__ffs(__ballot_sync(kFull, tr >= ecnt && tr < ecnt + cnt)) - 1u;
-    const u32 ob = owner * per;
-    const u32 e = __shfl_sync(kFull, ecnt, owner), eb = __shfl_sync(kFull, ecb, owner);
-    const u32 c = (lane < per) ? (u32)h16[ob + lane] : 0u;
-    u32 ic = c, iq = c * (ob + lane);
-    const u32 q0 = iq;
+  // level B, the four ranks at once: eight lanes per rank walk the (<= 32) bins of the rank's owner lane
+  const u32 grp = lane >> 3, sub = lane & 7u;
+  u32 own = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 a = __shfl_up_sync(kFull, ic, o);
-      const u32 b = __shfl_up_sync(kFull, iq, o);
-      if (lane >= (u32)o) { ic += a; iq += b; }
-    }
-    const u32 hit = (u32)__ffs(__ballot_sync(kFull, tr < e + ic)) - 1u;
-    if (lane == hit) {
-      t[j] = ob + lane;                 // key
-      t[4 + j] = tr - (e + ic - c);     // rank inside the bin
-      t[8 + j] = e + ic - c;            // count below
-      t[12 + j] = eb + iq - q0;         // sum(count * bin) below
+  for (int j = 0; j < 4; ++j) {
+    const u32 o = (u32)__ffs(__ballot_sync(kFull, ranks[j] >= ecnt && ranks[j] < ecnt + cnt)) - 1u;
+    if (grp == (u32)j) own = o;
+  }
+  const u32 tr = grp == 0 ? ranks[0] : (grp == 1 ? ranks[1] : (grp == 2 ? ranks[2] : ranks[3]));
+  const u32 e = __shfl_sync(kFull, ecnt, own), eb = __shfl_sync(kFull, ecb, own);
+  const u32 nper = per >> 3;              // bins per lane of the group: 1..4
+  const u32 lb = own * per + sub * nper;  // first bin of this lane
+  u32 c4[4], lc = 0, lq = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    c4[k] = ((u32)k < nper) ? (u32)h16[lb + k] : 0u;
+    lc += c4[k];
+    lq += c4[k] * (lb + k);
+  }
+  u32 ic = lc, iq = lq;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const u32 a = __shfl_up_sync(kFull, ic, o, 8);
+    const u32 b = __shfl_up_sync(kFull, iq, o, 8);
+    if (sub >= (u32)o) { ic += a; iq += b; }
+  }
+  u32 acc = e + ic - lc, accq = eb + iq - lq;  // counts / weighted counts below this lane's first bin
+  if (tr >= acc && tr < acc + lc) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (tr >= acc && tr < acc + c4[k]) {
+        t[grp] = lb + k;          // key
+        t[4 + grp] = tr - acc;    // rank inside the bin
+        t[8 + grp] = acc;         // count below
+        t[12 + grp] = accq;       // sum(count * bin) below
+      }
+      acc += c4[k];
+      accq += c4[k] * (lb + k);
     }
   }
   __syncwarp();

@@ -504,7 +504,7 @@ __device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, cons
 
 // L2 prefetch of the next object's windows: label rows, and one line pair per pixel row / request / z
 template <typename PX>
-__device__ __noinline__ void prefetch_object(u32 n_px, int nh, int nw, u32 lo, u32 hi, const uint16_t* __restrict__ lab,
+__device__ __forceinline__ void prefetch_object(u32 n_px, int nh, int nw, u32 lo, u32 hi, const uint16_t* __restrict__ lab,
                                                 i64 lab_rs, const PX* __restrict__ px, i64 px_rs, i64 chan_stride,
                                                 i64 z_stride, int Z, const abx_request* __restrict__ requests,
                                                 int n_requests) {

@@ -18,9 +18,11 @@
 //            pixels per lane in flight), cone top as a second bitmask, plateau distances
 //
 // Both kernels are written for a SMALL CODE FOOTPRINT (one path per phase, loops not unrolled
-// beyond what memory-level parallelism needs): the first version of this file compiled to 165 KB
-// of SASS per kernel and stalled on instruction fetch (ncu: stall_no_instruction 4 of 11 cycles per
-// issue, profiles/r01e_summary.md).  A CTA mixes two slot sizes — most warps own a slot for
+// beyond what memory-level parallelism needs, only the cold variants — wide sums, re-gather —
+// out of line): the first version of this file compiled to 165 KB of SASS per kernel and stalled on
+// instruction fetch (ncu: stall_no_instruction 4 of 11 cycles per issue, profiles/r01e_summary.md);
+// hot phases are inlined at their single call site, because a __noinline__ call cost a frame in
+// local memory (profiles/r01zz_summary.md).  A CTA mixes two slot sizes — most warps own a slot for
 // objects of <= 2048 pixels, two own a slot for <= 4096 — so that one launch serves every object
 // of the window class without a tail.  No __syncthreads: the warps of a CTA are independent.
 // Larger windows and the per-plane background go to work lists that the CTA-per-object kernels

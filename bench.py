@@ -174,6 +174,18 @@ def cpu_port_sample(n_objects_sample=6, seed=4242):
     return len(items) / dt, len(items), dt, int(lab.max())
 
 
+def cpu_fast_sample(seed=4242):
+    """oracle.fast — the O(YX log) sort-by-label CPU implementation of the same numbers (the "fair CPU" of
+    SURVEY.md 8d) — on one whole C2 field, 1 core."""
+    from oracle import fast
+
+    px, lab = _make(seed)
+    t0 = time.perf_counter()
+    items, _ = fast.run_tree(c2_tree(), lab, px[None])
+    dt = time.perf_counter() - t0
+    return len(items) / dt, len(items), dt
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def _ref_job(args):
     from oracle import port
@@ -433,6 +445,12 @@ def ours(args):
                 "value": v, "unit": "object-features/s", "cores": 1, "kind": "port",
                 "sample": f"{n_items} (object, instruction) items = 6 random objects x {n_feat_cols} instructions of one "
                           f"C2 field in {dt:.1f} s; oracle.port, the faithful restatement of the reference loop",
+            }
+            v, n_items, dt = cpu_fast_sample()
+            line["cpu_fast"] = {
+                "value": v, "unit": "object-features/s", "cores": 1, "kind": "port-fast",
+                "sample": f"{n_items} items = every object x {n_feat_cols} instructions of one whole C2 field "
+                          f"in {dt:.1f} s; oracle.fast (sort-by-label NumPy/SciPy, same numbers as the reference algorithm)",
             }
         print(json.dumps(line))
     if dist is not None:

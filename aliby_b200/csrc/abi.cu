@@ -62,6 +62,8 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   off = align_up(off + 8 * sizeof(u32));
   ws->sqrt_tab = reinterpret_cast<double*>(b + off);
   off = align_up(off + (a->need_edt ? (size_t)abx_sqrt_table_entries() * sizeof(double) : 0));
+  ws->bg_hist = reinterpret_cast<u32*>(b + off);
+  off = align_up(off + abx_big_background_bytes(a));
   ws->stats_list = reinterpret_cast<int*>(b + off);
   off = align_up(off + n_rec * sizeof(int));
   ws->edt_list = reinterpret_cast<int*>(b + off);
@@ -134,6 +136,7 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   if ((rc = launch_object_edt_warp(args, ws, st))) return rc;
   mark(3);
   if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
+  if ((rc = launch_big_background(args, ws, st))) return rc;  // backgrounds of large planes: streaming histogram
   if ((rc = launch_object_float(args, ws, st))) return rc;  // floating-point requests (float pixels, `div`)
   if ((rc = launch_shape_edt(args, ws, st))) return rc;
   mark(4);

@@ -59,6 +59,7 @@ struct Workspace {
   int* edt_list;     // objects the warp kernel handed to the CTA EDT kernel
   u32* list_counts;  // = err + 1: [0] stats_list length, [1] edt_list length, [2..3] / [4..5] work counters
   double* sqrt_tab;  // sqrt(d2) of every squared distance the warp EDT can produce
+  u32* bg_hist;      // [n_planes][n_requests][65536] value histograms of large-plane backgrounds (background.cu)
   size_t total;
 };
 
@@ -73,12 +74,16 @@ int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaS
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_float(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_big_background(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+bool abx_big_background(const abx_extract_args* a);
+size_t abx_big_background_bytes(const abx_extract_args* a);
 int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int abx_sqrt_table_entries();
 
 constexpr int kEdtLargeCtas = 8;           // CTAs that own a whole-plane EDT scratch slot
 constexpr int kEdtSmemWindow = 96 * 96;    // padded window (pixels) that is handled in shared memory
 constexpr int kEdtBytesPerPixel = 8;       // mask(1) + flags(1) + g(2) + d2(4)
+constexpr long long kBigBackground = 128 * 128;  // planes above this many pixels take the streaming background path
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
 

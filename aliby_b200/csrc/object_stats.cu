@@ -148,7 +148,7 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
                     const i64* __restrict__ tile_offset, i64 chan_stride, i64 z_stride, i64 px_row_stride, int Z,
                     const abx_request* __restrict__ requests, int n_requests,
                     const abx_object_rec* __restrict__ recs, ChanStats* __restrict__ out,
-                    const int* __restrict__ work_list, const u32* __restrict__ work_count) {
+                    const int* __restrict__ work_list, const u32* __restrict__ work_count, int big_background) {
   __shared__ Smem s;
   const u32 lane = lane_id(), warp = threadIdx.x >> 5;
   constexpr u32 kWrapMask = (sizeof(PX) == 1) ? 0xFFu : 0xFFFFu;
@@ -173,6 +173,7 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
     for (int q = 0; q < n_requests; ++q) {
       const abx_request rq = requests[q];
       if (rq.reduction == ABX_RED_DIV) continue;  // floating-point request: object_float.cu (block-uniform)
+      if (is_bg && big_background && !(rq.reduction == ABX_RED_ADD && Z > 1)) continue;  // background.cu
       const u32 feats = is_bg ? rq.bg_features : rq.features;
       ChanStats* dst = out + (i64)obj * n_requests + q;
       if (n == 0 || (is_bg && feats == 0)) {  // block-uniform
@@ -351,7 +352,7 @@ int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStre
       static_cast<const uint16_t*>(a->labels), a->label_plane_stride, a->label_row_stride, a->plane_tile,         \
       a->plane_base, a->n_planes, a->n_objects, n_total, static_cast<const PX*>(a->pixels),                       \
       reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride, a->row_stride, a->Z, a->requests, \
-      a->n_requests, ws.recs, ws.chan, ws.stats_list, ws.list_counts)
+      a->n_requests, ws.recs, ws.chan, ws.stats_list, ws.list_counts, (int)abx_big_background(a))
   if (a->pixel_dtype == ABX_U16) ABX_LAUNCH_OS(uint16_t);
   else if (a->pixel_dtype == ABX_U8) ABX_LAUNCH_OS(uint8_t);
   else return ABX_OK;  // float pixels: every request belongs to object_float.cu

@@ -544,3 +544,26 @@ def test_overlap_original_ids_and_format(ab):
     assert table.column_names[:2] == ["metadata_tile", "metadata_label"]
     keys = sorted(zip(table.column("metadata_tile").to_pylist(), table.column("metadata_label").to_pylist()))
     assert keys == [(0, 3), (0, 7), (0, 12), (1, 3), (1, 5), (1, 7)]
+
+
+def test_background_of_a_whole_field_streaming_path(ab):
+    """imBackground / background_max5 (trap.py:6-43) on a whole 2160^2 field: the streaming 65 536-bin path."""
+    import time
+
+    from aliby_b200 import synth
+
+    pixels, labels = synth.make_field(1020, (2160, 2160), 3, 400, n_z=2)
+    tree = {0: {"max": ["imBackground", "background_max5", "median"]}, 2: {"max": ["background_max5"]},
+            1: {"add": ["imBackground"]}}  # the Z-add request stays on the per-object path (wide values)
+    t0 = time.perf_counter()
+    tab = ab.extract_table(tree, [labels], pixels)
+    dt = time.perf_counter() - t0
+    bg = labels == 0
+    for name, ch, red, fn in [("0/max/imBackground/imBackground", 0, np.maximum, np.median),
+                              ("0/max/background_max5/background_max5", 0, np.maximum, lambda v: np.mean(np.sort(v)[-5:])),
+                              ("2/max/background_max5/background_max5", 2, np.maximum, lambda v: np.mean(np.sort(v)[-5:])),
+                              ("1/add/imBackground/imBackground", 1, np.add, np.median)]:
+        want = float(fn(red.reduce(pixels[0, ch], axis=0)[bg]))
+        col = tab.values[:, tab.names.index(name)]
+        assert (col == want).all(), (name, col[:3], want)
+    assert dt < 5.0

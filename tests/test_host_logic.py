@@ -245,3 +245,35 @@ def test_init_step_seam_matches_reference_partial_shape():
         pipe.init_step("extractmulti_nuclei", {"tree": tree})
     with pytest.raises(ImportError):  # the reference is not installed next to us in this container
         pipe.init_step("segment_nuclei", {})
+
+
+def test_ctypes_mirrors_match_the_c_header(tmp_path):
+    """Field offsets / sizes of the ctypes mirrors == what a C compiler lays out for include/aliby_b200.h."""
+    import shutil
+
+    from aliby_b200 import _native as nat
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    fields = [f[0] for f in nat.ExtractArgs._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "aliby_b200.h"', "int main(void) {"]
+    prog += [f'  printf("{f} %zu\\n", offsetof(abx_extract_args, {f}));' for f in fields]
+    prog += ['  printf("sizeof_args %zu\\n", sizeof(abx_extract_args));',
+             '  printf("sizeof_request %zu\\n", sizeof(abx_request));',
+             '  printf("sizeof_column %zu\\n", sizeof(abx_column));',
+             '  printf("sizeof_rec %zu\\n", sizeof(abx_object_rec));',
+             '  printf("enums %d %d %d %d %d %d\\n", ABX_F64, ABX_RED_DIV, ABX_M_BACKGROUND_MAX5, ABX_M_MEAN, ABX_F_MOI, ABX_ERR_UNSUPPORTED);',
+             "  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split(" ", 1) for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for f in fields:
+        assert int(out[f]) == getattr(nat.ExtractArgs, f).offset, f
+    assert int(out["sizeof_args"]) == ctypes.sizeof(nat.ExtractArgs)
+    assert int(out["sizeof_request"]) == ctypes.sizeof(nat.Request) and int(out["sizeof_column"]) == ctypes.sizeof(nat.Column)
+    assert int(out["sizeof_rec"]) == ctypes.sizeof(nat.ObjectRec)
+    assert out["enums"].split() == [str(v) for v in (nat.F64, nat.RED_DIV, nat.METRIC["background_max5"], nat.METRIC["mean"],
+                                                     nat.F_MOI, -2)]

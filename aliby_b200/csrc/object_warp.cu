@@ -22,7 +22,7 @@
 // out of line): the first version of this file compiled to 165 KB of SASS per kernel and stalled on
 // instruction fetch (ncu: stall_no_instruction 4 of 11 cycles per issue, profiles/r01e_summary.md);
 // hot phases are inlined at their single call site, because a __noinline__ call cost a frame in
-// local memory (profiles/r01zz_summary.md).  A CTA mixes two slot sizes — most warps own a slot for
+// local memory (profiles/r01_final_summary.md).  A CTA mixes two slot sizes — most warps own a slot for
 // objects of <= 2048 pixels, two own a slot for <= 4096 — so that one launch serves every object
 // of the window class without a tail.  No __syncthreads: the warps of a CTA are independent.
 // Larger windows and the per-plane background go to work lists that the CTA-per-object kernels

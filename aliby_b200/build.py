@@ -53,8 +53,9 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = find_nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
-    if os.environ.get("ABX_PHASE_TIMING"):
-        extra.append("-DABX_PHASE_TIMING")
+    for flag in ("ABX_NO_PREFETCH",):  # experiment switches: ABX_NO_PREFETCH=1 python -m aliby_b200.build --force
+        if os.environ.get(flag):
+            extra.append(f"-D{flag}")
     objs = []
     jobs = []
     for src in SOURCES:

@@ -511,6 +511,9 @@ __device__ __forceinline__ void prefetch_object(u32 n_px, int nh, int nw, u32 lo
                                                 i64 z_stride, int Z, const abx_request* __restrict__ requests,
                                                 int n_requests) {
   if (n_px <= lo || n_px > hi || nh > kSide || nw > kSide) return;
+#ifdef ABX_NO_PREFETCH
+  return;
+#endif
   const u32 lane = lane_id();
   const i64 tail = (i64)nw - 1;
   for (int r = lane; r < nh; r += 32) {

@@ -23,11 +23,12 @@ __device__ __forceinline__ double moment_of_inertia(const ChanStats& c) {
   // translation invariant): mu20 = m20 - m10^2 / m00, eta = mu / m00^2
   if (c.sum == 0) return nan("");
   const unsigned __int128 m00 = c.sum;
-  const unsigned __int128 n20 = m00 * c.m20 - (unsigned __int128)c.m10 * c.m10;
-  const unsigned __int128 n02 = m00 * c.m02 - (unsigned __int128)c.m01 * c.m01;
+  // eta20 + eta02 from one exact integer numerator: m00 * (m20 + m02) - m10^2 - m01^2 (each central moment is
+  // non-negative, so the total is; producers may store the two second moments separately or as one sum in m20)
+  const unsigned __int128 num = m00 * ((unsigned __int128)c.m20 + c.m02) - (unsigned __int128)c.m10 * c.m10 -
+                                (unsigned __int128)c.m01 * c.m01;
   const double d = (double)c.sum;
-  const double d3 = d * d * d;
-  return u128_to_double(n20) / d3 + u128_to_double(n02) / d3;
+  return u128_to_double(num) / (d * d * d);
 }
 
 // intensity metric of a floating-point request (object_float.cu), NumPy float semantics

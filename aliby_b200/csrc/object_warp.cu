@@ -33,46 +33,7 @@
 
 namespace {
 
-constexpr int kSide = 64;        // maximum window side
-constexpr int kCapSmall = 2048;  // pixels per object, small slot
-constexpr int kCapLarge = 4096;  // pixels per object, large slot (= kSide * kSide)
-constexpr int kBins = 1024;      // level-0 histogram bins, 16-bit counters packed in pairs
-constexpr int kLargeSlots = 2;   // warps per CTA that own a large slot (the last ones)
-constexpr int kStatsWarps = 9;   // 7 small + 2 large slots: 109 KB per CTA, 2 CTAs per SM
-constexpr int kEdtWarps = 10;    // 8 small + 2 large slots: 103 KB per CTA, 2 CTAs per SM
-constexpr u32 kFull = 0xFFFFFFFFu;
-
-// Every device function derives its shared-memory pointers from this array plus a byte offset, so that the
-// compiler keeps them in the shared address space (generic pointers passed through __noinline__ calls
-// compiled to LD.E/ST.E with 64-bit address arithmetic: 24 instructions per EDT step instead of 8).
-extern __shared__ __align__(16) unsigned char dyn[];
-
-// Sum of a 64-bit quantity over the warp from three independent 32-bit REDUX reductions of its
-// 24/24/16-bit slices (each slice sum < 2^29): shorter and far less latency than five dependent
-// 64-bit shuffle steps.  Exact modulo 2^64 for any input.
-__device__ __forceinline__ u64 warp_sum64(u64 v) {
-  const u32 a = __reduce_add_sync(kFull, (u32)v & 0xFFFFFFu);
-  const u32 b = __reduce_add_sync(kFull, (u32)(v >> 24) & 0xFFFFFFu);
-  const u32 c = __reduce_add_sync(kFull, (u32)(v >> 48));
-  return (u64)a + ((u64)b << 24) + ((u64)c << 48);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Work distribution: one atomic per object; a warp always holds the NEXT object too and prefetches
-// its windows into L2 while it works.  Small-slot warps walk counter 0 and take the objects of
-// <= kCapSmall pixels (plus the bookkeeping: empty objects, hand-over lists); large-slot warps walk
-// counter 1 for the bigger ones first and then help with counter 0.
-// ------------------------------------------------------------------------------------------------
-struct Queue {
-  u32* counters;  // [2]
-  int n_total;
-  int phase;      // 1: large objects (counter 1), 0: small objects (counter 0)
-  __device__ __forceinline__ int fetch() {
-    int v = 0;
-    if (lane_id() == 0) v = (int)atomicAdd(&counters[phase], 1u);
-    return __shfl_sync(kFull, v, 0);
-  }
-};
+#include "warp_common.cuh"
 
 // phase M: row bitmasks (optional), row bases (optional) and the compact offset list
 template <bool kMasks>
@@ -117,123 +78,6 @@ __device__ __forceinline__ void build_list(const uint16_t* __restrict__ lab, i64
   __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------------
-// phase S helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hist_zero(u32* hist) {  // 1024 bins = 128 x uint4
-  uint4* h4 = reinterpret_cast<uint4*>(hist);
-#pragma unroll
-  for (int k = 0; k < kBins / 8 / 32; ++k) h4[lane_id() + 32 * k] = make_uint4(0, 0, 0, 0);
-}
-__device__ __forceinline__ void hist_add(u32* hist, u32 bin) {
-  atomicAdd(&hist[bin >> 1], 1u << ((bin & 1u) << 4));
-}
-
-// Locate four ranks in the 16-bit histogram h16[0, nb).  Level A: each lane sums `per` consecutive
-// bins (a multiple of 8, read as uint4) and a warp scan finds the owning lane; level B: the 32
-// lanes scan the owner's bins.  For rank t: key = its bin, rank = t - (count below the bin),
-// cnt = count below the bin, cb = sum over the bins below of count * bin index.  out: t[0..16).
-__device__ __forceinline__ void find_ranks16(const unsigned short* h16, u32 nb, const u32 (&ranks)[4], u32* t) {
-  const u32 lane = lane_id();
-  const u32 per = (((nb + 31u) >> 5) + 7u) & ~7u;  // 8, 16, 24 or 32
-  const u32 b0 = lane * per;
-  u32 cnt = 0, cb = 0;
-#pragma unroll 1
-  for (u32 k = 0; k < per; k += 8) {
-    const uint4 v = *reinterpret_cast<const uint4*>(h16 + b0 + k);
-    const u32 w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const u32 hi = w[j] >> 16, pair = (w[j] & 0xFFFFu) + hi;
-      cnt += pair;
-      cb += pair * (b0 + k + 2 * j) + hi;
-    }
-  }
-  u32 icnt = cnt, icb = cb;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const u32 c = __shfl_up_sync(kFull, icnt, o);
-    const u32 q = __shfl_up_sync(kFull, icb, o);
-    if (lane >= (u32)o) { icnt += c; icb += q; }
-  }
-  const u32 ecnt = icnt - cnt, ecb = icb - cb;
-  // level B, the four ranks at once: eight lanes per rank walk the (<= 32) bins of the rank's owner lane
-  const u32 grp = lane >> 3, sub = lane & 7u;
-  u32 own = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const u32 o = (u32)__ffs(__ballot_sync(kFull, ranks[j] >= ecnt && ranks[j] < ecnt + cnt)) - 1u;
-    if (grp == (u32)j) own = o;
-  }
-  const u32 tr = grp == 0 ? ranks[0] : (grp == 1 ? ranks[1] : (grp == 2 ? ranks[2] : ranks[3]));
-  const u32 e = __shfl_sync(kFull, ecnt, own), eb = __shfl_sync(kFull, ecb, own);
-  const u32 nper = per >> 3;              // bins per lane of the group: 1..4
-  const u32 lb = own * per + sub * nper;  // first bin of this lane
-  u32 c4[4], lc = 0, lq = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    c4[k] = ((u32)k < nper) ? (u32)h16[lb + k] : 0u;
-    lc += c4[k];
-    lq += c4[k] * (lb + k);
-  }
-  u32 ic = lc, iq = lq;
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    const u32 a = __shfl_up_sync(kFull, ic, o, 8);
-    const u32 b = __shfl_up_sync(kFull, iq, o, 8);
-    if (sub >= (u32)o) { ic += a; iq += b; }
-  }
-  u32 acc = e + ic - lc, accq = eb + iq - lq;  // counts / weighted counts below this lane's first bin
-  if (tr >= acc && tr < acc + lc) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (tr >= acc && tr < acc + c4[k]) {
-        t[grp] = lb + k;          // key
-        t[4 + grp] = tr - acc;    // rank inside the bin
-        t[8 + grp] = acc;         // count below
-        t[12 + grp] = accq;       // sum(count * bin) below
-      }
-      acc += c4[k];
-      accq += c4[k] * (lb + k);
-    }
-  }
-  __syncwarp();
-}
-
-// Four independent rank searches at once: eight lanes per 128-bin sub-histogram (refinement).
-// in: t[4 + g] = rank inside group g; out: t[g] = sub-bin, t[4 + g] = rank inside the sub-bin.
-__device__ __forceinline__ void find_ranks16_x4(const unsigned short* h16, u32* t) {
-  const u32 lane = lane_id();
-  const u32 grp = lane >> 3, sub = lane & 7u;
-  const u32 b0 = grp * 128u + sub * 16u;
-  u32 cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 16; k += 8) {
-    const uint4 v = *reinterpret_cast<const uint4*>(h16 + b0 + k);
-    cnt += (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) +
-           (v.w & 0xFFFFu) + (v.w >> 16);
-  }
-  u32 icnt = cnt;
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    const u32 c = __shfl_up_sync(kFull, icnt, o, 8);
-    if (sub >= (u32)o) icnt += c;
-  }
-  const u32 ecnt = icnt - cnt;
-  const u32 tr = t[4 + grp];
-  __syncwarp();
-  if (tr >= ecnt && tr < ecnt + cnt) {
-    u32 acc = ecnt;
-#pragma unroll 1
-    for (u32 bq = b0; bq < b0 + 16u; ++bq) {
-      const u32 c = h16[bq];
-      if (tr < acc + c) { t[grp] = bq - grp * 128u; t[4 + grp] = tr - acc; break; }
-      acc += c;
-    }
-  }
-  __syncwarp();
-}
-
 // One pixel of a request, Z-reduced (slow path: values that were not staged).
 template <typename PX>
 __device__ __noinline__ u32 gather_reduced(const PX* __restrict__ p, int Z, i64 z_stride, int red) {
@@ -262,128 +106,141 @@ struct ValueSource {  // value i of the current request
   }
 };
 
-// pass 1: moments and extrema of one request; values staged when they fit 16 bits (kWide = false).
-// kWide (Z reduction "add"): 64-bit accumulators, nothing staged.  The gather is software-pipelined:
-// the loads of batch b + 1 are in flight while batch b is accumulated.
-template <typename PX, bool kWide>
-__device__ __forceinline__ void moments_pass(u32 n, const unsigned short* __restrict__ offs, unsigned short* __restrict__ vals,
-                                             const PX* __restrict__ px, u32 rs, i64 z_stride, int Z, int red,
-                                             bool want_moi, ChanStats& cs) {
-  using Acc = typename std::conditional<kWide, u64, u32>::type;
-  constexpr u32 kWrapMask = (sizeof(PX) == 1) ? 0xFFu : 0xFFFFu;
-  constexpr int kBatch = 8;
-  constexpr u32 kNone = 0xFFFFu;
+// Four pixels per lane of the padded list, Z-reduced with max (the only narrow reduction): values of
+// list entries i0 + 32 u.  No predicates anywhere: the list is padded with copies of its first entry.
+template <typename PX>
+__device__ __forceinline__ void gather4(u32 i0, const unsigned short* __restrict__ offs, const PX* __restrict__ px, u32 rs,
+                                        i64 z_stride, int Z, u32 (&xq)[4]) {
+  u32 go[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const u32 kq = offs[i0 + 32u * u];
+    go[u] = (kq >> 6) * rs + (kq & 63u);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) xq[u] = (u32)__ldg(px + go[u]);
+  if (Z > 1) {
+#pragma unroll 1
+    for (int z = 1; z < Z; ++z) {
+      const PX* pz = px + (i64)z * z_stride;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xq[u] = max(xq[u], (u32)__ldg(pz + go[u]));
+    }
+  }
+}
+
+// pass 1 (narrow values: one plane, or the Z maximum): moments and extrema of one request over the PADDED
+// list (n_pad entries, a multiple of 128; entries >= n repeat entry 0, whose contribution is taken out of
+// the sums afterwards and which cannot move the extrema).  kDepth gathers of four pixels per lane rotate
+// through registers, so that eight loads are in flight while four values are accumulated.  Per value:
+// sum, sum of squares (64-bit mad), sum of (x^2 >> bits) by a high multiply — NumPy's wrapped v**2 is
+// sum(x^2) - 2^bits * that — min, max; for moment_of_inertia x*c, x*r and x*(c^2 + r^2).  Values are staged
+// in shared memory for pass 2 when `stage`.
+template <typename PX>
+__device__ __forceinline__ void moments_pass(u32 n, u32 n_pad, const unsigned short* __restrict__ offs,
+                                             unsigned short* __restrict__ vals, bool stage, const PX* __restrict__ px, u32 rs,
+                                             i64 z_stride, int Z, bool want_moi, ChanStats& cs, u32& v0_out) {
+  constexpr int kShift = (sizeof(PX) == 1) ? 12 : 8;  // (x << kShift)^2 >> 32 == x^2 >> bits(PX)
   const u32 lane = lane_id();
-  Acc f_sum = 0, f_wrap = 0, f_m10 = 0, f_m01 = 0;
-  u64 f_sq = 0, f_m20 = 0, f_m02 = 0;
+  u32 f_sum = 0, f_wh = 0, f_m10 = 0, f_m01 = 0;
+  u64 f_sq = 0, f_q = 0;
   u32 a_min = kFull, a_max = 0;
-  u32 x[kBatch];
-  // values of batch i0 (Z-reduced); the offsets are re-read from shared memory when the batch is consumed,
-  // so that only the values live across the pipeline stage
-  auto load_batch = [&](u32 i0, u32 (&xq)[kBatch]) {
-    if (i0 - lane + 32u * kBatch <= n) {
-      // whole batch inside the list (warp-uniform test): no predicates, so the compiler keeps the memory
-      // descriptor and the row stride in uniform registers instead of rebuilding them for every pixel
-      u32 go[kBatch];
+  auto accumulate = [&](u32 i0, const u32 (&xq)[4]) {
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const u32 kq = offs[i0 + 32u * u];
-        go[u] = (kq >> 6) * rs + (kq & 63u);
-      }
-#pragma unroll
-      for (int u = 0; u < kBatch; ++u) xq[u] = (u32)__ldg(px + go[u]);
-      if (Z > 1) {
-#pragma unroll 1
-        for (int z = 1; z < Z; ++z) {
-          const PX* pz = px + (i64)z * z_stride;
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            const u32 y = (u32)__ldg(pz + go[u]);
-            xq[u] = (red == ABX_RED_MAX) ? max(xq[u], y) : xq[u] + y;
-          }
-        }
-      }
-      return;
-    }
-    u32 kq[kBatch];  // ragged last batch (and the empty one past the end)
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
+    for (int u = 0; u < 4; ++u) {
+      const u32 v = xq[u];
       const u32 i = i0 + 32u * u;
-      kq[u] = (i < n) ? (u32)offs[i] : kNone;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      xq[u] = (kq[u] != kNone) ? (u32)__ldg(px + ((kq[u] >> 6) * rs + (kq[u] & 63u))) : 0u;
-    if (Z > 1) {
-#pragma unroll 1
-      for (int z = 1; z < Z; ++z) {
-        const PX* pz = px + (i64)z * z_stride;
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          if (kq[u] != kNone) {
-            const u32 y = (u32)__ldg(pz + ((kq[u] >> 6) * rs + (kq[u] & 63u)));
-            xq[u] = (red == ABX_RED_MAX) ? max(xq[u], y) : xq[u] + y;
-          }
+      f_sum += v;
+      f_sq += (u64)v * (u64)v;
+      const u32 a = v << kShift;
+      f_wh += __umulhi(a, a);
+      a_min = min(a_min, v);
+      a_max = max(a_max, v);
+      if (want_moi) {
+        const u32 k = offs[i];
+        const u32 c = k & 63u, r = k >> 6;
+        f_m10 += v * c;
+        f_m01 += v * r;
+        f_q += (u64)v * (u64)(c * c + r * r);
       }
+      if (stage) vals[i] = (unsigned short)v;
     }
   };
+  // kDepth quads rotate through registers: while one is accumulated, kDepth - 1 gathers (four loads each) are in
+  // flight — the loads hit L2 (prefetched one request ahead) and L2 latency is what a warp has to cover
+  const u32 nq = n_pad >> 7;  // quads of the list (>= 1)
+  u32 x[kDepth][4];
 #pragma unroll
-  for (int u = 0; u < kBatch; ++u) x[u] = 0;
-  // iteration j loads batch j and accumulates batch j - 1 (one copy of each body in the code)
+  for (int d = 0; d < kDepth; ++d)
+    if ((u32)d < nq) gather4<PX>(lane + 128u * d, offs, px, rs, z_stride, Z, x[d]);
+  const u32 first = x[0][0];
 #pragma unroll 1
-  for (int i0 = (int)lane - 32 * kBatch; i0 < (int)n; i0 += 32 * kBatch) {
-    u32 xn[kBatch];
-    load_batch((u32)(i0 + 32 * kBatch), xn);  // indices >= n load nothing
-    if (i0 >= 0) {                            // warp-uniform
+  for (u32 q = 0; q < nq; q += kDepth) {
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const u32 i = (u32)i0 + 32u * u;
-        const bool ok = i < n;
-        const u32 v = x[u];  // 0 when !ok
-        f_sum += v;
-        f_sq += (u64)v * (u64)v;
-        if (!kWide) f_wrap += (v * v) & kWrapMask;
-        a_min = min(a_min, ok ? v : kFull);
-        a_max = max(a_max, v);
-        if (want_moi) {
-          const u32 k = ok ? (u32)offs[i] : 0u;
-          const u32 c = k & 63u, r = k >> 6;
-          const Acc xc = (Acc)v * c, xr = (Acc)v * r;
-          f_m10 += xc; f_m01 += xr;
-          f_m20 += (u64)xc * (u64)c; f_m02 += (u64)xr * (u64)r;
-        }
-        if (!kWide && ok) vals[i] = (unsigned short)v;
+    for (int d = 0; d < kDepth; ++d) {
+      if (q + d < nq) {  // warp-uniform
+        const u32 i0 = lane + ((q + d) << 7);
+        accumulate(i0, x[d]);
+        if (q + d + kDepth < nq) gather4<PX>(i0 + 128u * kDepth, offs, px, rs, z_stride, Z, x[d]);
       }
     }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) x[u] = xn[u];
   }
-  cs.sum = kWide ? warp_sum64((u64)f_sum) : (u64)__reduce_add_sync(kFull, (u32)f_sum);  // n * 65535 < 2^32
-  cs.sumsq = warp_sum64(f_sq);
-  cs.wrapsq = kWide ? cs.sumsq : (u64)__reduce_add_sync(kFull, (u32)f_wrap);
+  // take the padding (n_pad - n copies of entry 0) out of the sums
+  const u32 v0 = __shfl_sync(kFull, first, 0);
+  const u64 p = (u64)(n_pad - n);
+  const u32 k0 = offs[0];
+  const u32 c0 = k0 & 63u, r0 = k0 >> 6;
+  const u32 a0 = v0 << kShift;
+  cs.sum = (u64)__reduce_add_sync(kFull, f_sum) - p * v0;  // n * 65535 < 2^32
+  cs.sumsq = warp_sum64(f_sq) - p * ((u64)v0 * v0);
+  const u64 wh = (u64)__reduce_add_sync(kFull, f_wh) - p * __umulhi(a0, a0);
+  cs.wrapsq = cs.sumsq - (wh << (32 - 2 * kShift));
   if (want_moi) {
-    cs.m10 = warp_sum64((u64)f_m10); cs.m01 = warp_sum64((u64)f_m01);
-    cs.m20 = warp_sum64(f_m20); cs.m02 = warp_sum64(f_m02);
+    cs.m10 = warp_sum64((u64)f_m10) - p * (u64)(v0 * c0);
+    cs.m01 = warp_sum64((u64)f_m01) - p * (u64)(v0 * r0);
+    cs.m20 = warp_sum64(f_q) - p * ((u64)v0 * (u64)(c0 * c0 + r0 * r0));  // m20 + m02 as one sum (finalize.cu)
+    cs.m02 = 0;
   } else {
     cs.m10 = cs.m01 = cs.m20 = cs.m02 = 0;
   }
   cs.vmin = __reduce_min_sync(kFull, a_min);
   cs.vmax = __reduce_max_sync(kFull, a_max);
+  v0_out = v0;
 }
 
-// The wide variant out of line.  Its results travel through the (still unused) histogram area of the slot, so that
-// the caller's ChanStats never has to live in local memory for the sake of a by-reference argument.
+// pass 1, wide values (Z reduction "add": up to 20 bits): 64-bit accumulators over the exact list, nothing staged.
+// Out of line; its results travel through the (still unused) histogram area of the slot, so that the caller's
+// ChanStats never has to live in local memory for the sake of a by-reference argument.
 template <typename PX>
-__device__ __noinline__ void moments_wide(u32 n, u32 slot_off, u32 hist_off, const PX* __restrict__ px, u32 rs, i64 z_stride,
-                                          int Z, int red, bool want_moi) {
-  ChanStats cs;
-  moments_pass<PX, true>(n, reinterpret_cast<const unsigned short*>(dyn + slot_off), nullptr, px, rs, z_stride, Z, red,
-                         want_moi, cs);
+__device__ __noinline__ void moments_wide(u32 n, u32 slot_off, const PX* __restrict__ px, u32 rs, i64 z_stride, int Z, int red,
+                                          bool want_moi) {
+  const unsigned short* offs = reinterpret_cast<const unsigned short*>(dyn + slot_off);
+  const u32 lane = lane_id();
+  u64 f_sum = 0, f_sq = 0, f_m10 = 0, f_m01 = 0, f_q = 0;
+  u32 a_min = kFull, a_max = 0;
+#pragma unroll 1
+  for (u32 i = lane; i < n; i += 32) {
+    const u32 k = offs[i];
+    const u32 c = k & 63u, r = k >> 6;
+    const u32 v = gather_reduced(px + (r * rs + c), Z, z_stride, red);
+    f_sum += v;
+    f_sq += (u64)v * (u64)v;
+    a_min = min(a_min, v);
+    a_max = max(a_max, v);
+    if (want_moi) {
+      f_m10 += (u64)v * c;
+      f_m01 += (u64)v * r;
+      f_q += (u64)v * (u64)(c * c + r * r);
+    }
+  }
+  const u64 sum = warp_sum64(f_sum), sq = warp_sum64(f_sq);
+  const u64 m10 = warp_sum64(f_m10), m01 = warp_sum64(f_m01), mq = warp_sum64(f_q);
+  const u32 vmin = __reduce_min_sync(kFull, a_min), vmax = __reduce_max_sync(kFull, a_max);
   __syncwarp();
-  if (lane_id() == 0) {
-    u64* o = reinterpret_cast<u64*>(dyn + hist_off);
-    o[0] = cs.sum; o[1] = cs.sumsq; o[2] = cs.wrapsq; o[3] = cs.m10; o[4] = cs.m01; o[5] = cs.m20; o[6] = cs.m02;
-    o[7] = (u64)cs.vmin | ((u64)cs.vmax << 32);
+  if (lane == 0) {
+    u64* o = reinterpret_cast<u64*>(dyn + slot_off + kStatsHistOff);
+    o[0] = sum; o[1] = sq; o[2] = sq; o[3] = m10; o[4] = m01; o[5] = mq; o[6] = 0;
+    o[7] = (u64)vmin | ((u64)vmax << 32);
   }
   __syncwarp();
 }
@@ -392,48 +249,71 @@ __device__ __noinline__ void moments_wide(u32 n, u32 slot_off, u32 hist_off, con
 // phase S: one (channel, reduction) request
 // ------------------------------------------------------------------------------------------------
 template <typename PX>
-__device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, const PX* __restrict__ px, u32 rs, i64 z_stride, int Z,
-                                           int reduction, u32 feats, ChanStats* __restrict__ dst) {
+__device__ __forceinline__ void request_stats(u32 n, u32 n_pad, u32 slot_off, const PX* __restrict__ px, u32 rs, i64 z_stride,
+                                              int Z, int reduction, u32 feats, ChanStats* __restrict__ dst) {
   const unsigned short* offs = reinterpret_cast<const unsigned short*>(dyn + slot_off);
-  unsigned short* vals = reinterpret_cast<unsigned short*>(dyn + slot_off) + cap;
-  u32* hist = reinterpret_cast<u32*>(vals + cap);
-  u32* t = hist + kBins / 2;
+  unsigned short* vals = reinterpret_cast<unsigned short*>(dyn + slot_off) + kCapSmall;
+  u32* hist = reinterpret_cast<u32*>(dyn + slot_off + kStatsHistOff);
+  u32* t = reinterpret_cast<u32*>(dyn + slot_off + kStatsTOff);
   const u32 lane = lane_id();
   const bool wide = reduction == ABX_RED_ADD && Z > 1;
+  const bool staged = !wide && n_pad <= (u32)kCapSmall;  // larger lists occupy the staging area themselves
   ChanStats cs;
+  u32 v0 = 0;
   if (wide) {
-    moments_wide<PX>(n, slot_off, slot_off + 4u * cap, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0);
+    moments_wide<PX>(n, slot_off, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0);
     const u64* o = reinterpret_cast<const u64*>(hist);
     cs.sum = o[0]; cs.sumsq = o[1]; cs.wrapsq = o[2]; cs.m10 = o[3]; cs.m01 = o[4]; cs.m20 = o[5]; cs.m02 = o[6];
     cs.vmin = (u32)o[7]; cs.vmax = (u32)(o[7] >> 32);
     __syncwarp();
+  } else {
+    moments_pass<PX>(n, n_pad, offs, vals, staged, px, rs, z_stride, Z, (feats & ABX_F_MOI) != 0, cs, v0);
   }
-  else moments_pass<PX, false>(n, offs, vals, px, rs, z_stride, Z, reduction, (feats & ABX_F_MOI) != 0, cs);
   cs.med_lo = cs.med_hi = 0;
   cs.top2p5_sum = cs.top5_sum = 0;
 
   if (feats & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) {
-    ValueSource<PX> value{vals, offs, px, z_stride, rs, Z, reduction, !wide};
+    ValueSource<PX> value{vals, offs, px, z_stride, rs, Z, reduction, staged};
     const u32 vmin = cs.vmin;
-    const unsigned short* h16 = reinterpret_cast<const unsigned short*>(hist);
     // ---- pass 2: range-adaptive histogram ----
     const u32 range = cs.vmax - vmin;
     int s0 = 0;
     while ((range >> s0) >= (u32)kBins) ++s0;
     const u32 nb = (range >> s0) + 1;
     __syncwarp();
-    hist_zero(hist);
+    hist_zero(hist, 32u * bins_per_lane(nb));
     __syncwarp();
-    if (!wide) {  // staged values, two per 32-bit shared-memory load
+    const u32 hbase = smem_addr(hist);
+    if (staged) {  // staged values, two per 32-bit shared-memory load
       const u32* v32 = reinterpret_cast<const u32*>(vals);
       const u32 pairs = n >> 1;
+      if (s0 == 0) {
+        const u32 base = hbase - 4u * vmin;  // bin address = 4 * value + base
 #pragma unroll 4
-      for (u32 w = lane; w < pairs; w += 32) {
-        const u32 xx = v32[w];
-        hist_add(hist, ((xx & 0xFFFFu) - vmin) >> s0);
-        hist_add(hist, ((xx >> 16) - vmin) >> s0);
+        for (u32 w = lane; w < pairs; w += 32) {
+          const u32 xx = v32[w];
+          hist_inc(4u * (xx & 0xFFFFu) + base);
+          hist_inc(4u * (xx >> 16) + base);
+        }
+      } else {
+#pragma unroll 4
+        for (u32 w = lane; w < pairs; w += 32) {
+          const u32 xx = v32[w];
+          hist_inc(hbase + 4u * (((xx & 0xFFFFu) - vmin) >> s0));
+          hist_inc(hbase + 4u * (((xx >> 16) - vmin) >> s0));
+        }
       }
-      if ((n & 1u) && lane == 0) hist_add(hist, ((u32)vals[n - 1] - vmin) >> s0);
+      if ((n & 1u) && lane == 0) hist_inc(hbase + 4u * (((u32)vals[n - 1] - vmin) >> s0));
+    } else if (!wide) {  // list too long to stage: gather again (the lines are in L1 / L2), padding taken out afterwards
+#pragma unroll 1
+      for (u32 i0 = lane; i0 < n_pad; i0 += 128) {
+        u32 xq[4];
+        gather4<PX>(i0, offs, px, rs, z_stride, Z, xq);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) hist_inc(hbase + 4u * ((xq[u] - vmin) >> s0));
+      }
+      __syncwarp();
+      if (lane == 0) hist[(v0 - vmin) >> s0] -= n_pad - n;
     } else {
 #pragma unroll 1
       for (u32 i = lane; i < n; i += 32) hist_add(hist, (value(i) - vmin) >> s0);
@@ -442,7 +322,7 @@ __device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, cons
     const u32 k2p5 = (u32)ceil((double)n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
     const u32 k5 = min(n, 5u);
     const u32 ranks[4] = {(n - 1) / 2, n / 2, n - k2p5, n - k5};
-    find_ranks16(h16, nb, ranks, t);
+    find_ranks32(hist, nb, ranks, t);
     u32 v2, v3;
     u64 below2, below3;
     if (s0 == 0) {
@@ -462,7 +342,7 @@ __device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, cons
         const int nxt = cur > 7 ? cur - 7 : 0;
         const u32 nsub = 1u << (cur - nxt);
         __syncwarp();
-        hist_zero(hist);
+        hist_zero(hist, 512u);
         __syncwarp();
 #pragma unroll 2
         for (u32 i = lane; i < n; i += 32) {
@@ -474,7 +354,7 @@ __device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, cons
             if (hi == key[j]) hist_add(hist, 128u * j + sb);
         }
         __syncwarp();
-        find_ranks16_x4(h16, t);
+        find_ranks32_x4(hist, t);
 #pragma unroll
         for (int j = 0; j < 4; ++j) key[j] = (key[j] << (cur - nxt)) | t[j];
         cur = nxt;
@@ -504,108 +384,70 @@ __device__ __forceinline__ void request_stats(u32 n, u32 slot_off, u32 cap, cons
   __syncwarp();
 }
 
-// L2 prefetch of the next object's windows: label rows, and one line pair per pixel row / request / z
-template <typename PX>
-__device__ __forceinline__ void prefetch_object(u32 n_px, int nh, int nw, u32 lo, u32 hi, const uint16_t* __restrict__ lab,
-                                                i64 lab_rs, const PX* __restrict__ px, i64 px_rs, i64 chan_stride,
-                                                i64 z_stride, int Z, const abx_request* __restrict__ requests,
-                                                int n_requests) {
-  if (n_px <= lo || n_px > hi || nh > kSide || nw > kSide) return;
-#ifdef ABX_NO_PREFETCH
-  return;
-#endif
-  const u32 lane = lane_id();
-  const i64 tail = (i64)nw - 1;
-  for (int r = lane; r < nh; r += 32) {
-    const uint16_t* lr = lab + (i64)r * lab_rs;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(lr));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(lr + tail));
-  }
-  const int zmax = Z < 16 ? Z : 16;
-  for (int q = 0; q < n_requests; ++q) {
-    const PX* cb = px + (i64)requests[q].channel * chan_stride;
-    for (int z = 0; z < zmax; ++z)
-      for (int r = lane; r < nh; r += 32) {
-        const PX* pr = cb + (i64)z * z_stride + (i64)r * px_rs;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + tail));
-      }
-  }
-}
-
-struct Common {  // kernel arguments shared by both kernels
-  const uint16_t* labels;
-  i64 lab_plane_stride, lab_row_stride;
-  const int32_t* plane_tile;
-  const int32_t* plane_base;
-  int n_planes, n_objects, n_total;
-  const abx_object_rec* recs;
-  u32* counters;  // [2] work counters of this kernel
-};
-
 template <typename PX>
 __global__ void __launch_bounds__(kStatsWarps * 32, 2)
 object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __restrict__ tile_offset, i64 chan_stride,
                   i64 z_stride, i64 px_row_stride, int Z, const abx_request* __restrict__ requests, int n_requests,
                   ChanStats* __restrict__ chan, int* __restrict__ stats_list, u32* __restrict__ stats_count) {
   const u32 lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  constexpr int kSmall = kStatsWarps - kLargeSlots;
-  constexpr u32 kSlotSmall = kCapSmall * 4 + kBins * 2 + 64, kSlotLarge = kCapLarge * 4 + kBins * 2 + 64;
-  const bool large_slot = warp >= kSmall;
-  const u32 cap = large_slot ? kCapLarge : kCapSmall;
-  // slot layout: offs u16[cap] | vals u16[cap] | hist u32[512] | t u32[16]
-  const u32 slot_off = large_slot ? kSmall * kSlotSmall + (warp - kSmall) * kSlotLarge : warp * kSlotSmall;
-
-  Queue qu{cm.counters, cm.n_total, large_slot ? 1 : 0};
+  const u32 slot_off = (threadIdx.x >> 5) * kStatsSlot;
+  Queue qu{cm.counters, cm.n_total, 0};
   int obj = qu.fetch();
-  if (obj >= cm.n_total && qu.phase == 1) { qu.phase = 0; obj = qu.fetch(); }
   int nxt = obj < cm.n_total ? qu.fetch() : cm.n_total;
   while (obj < cm.n_total) {
-    const u32 lo = qu.phase ? (u32)kCapSmall : 0u, hi = qu.phase ? (u32)kCapLarge : (u32)kCapSmall;
-    if (nxt < cm.n_total && nxt < cm.n_objects) {
-      const abx_object_rec nr = cm.recs[nxt];
-      const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
-      prefetch_object<PX>(nr.n, (int)(nr.rmax - nr.rmin) + 1, (int)(nr.cmax - nr.cmin) + 1, lo, hi,
-                          cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
-                          cm.lab_row_stride,
-                          pixels + tile_offset[cm.plane_tile[np]] + (i64)nr.rmin * px_row_stride + nr.cmin, px_row_stride,
-                          chan_stride, z_stride, Z, requests, n_requests);
-    }
     const abx_object_rec rec = cm.recs[obj];
     const bool is_bg = obj >= cm.n_objects;
     const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
-    const bool fits = !is_bg && rec.n > 0 && h <= kSide && w <= kSide;
-    if (qu.phase == 0 && rec.n == 0) {  // absent label (or empty background): zero records -> NaN in finalize
+    if (rec.n == 0) {  // absent label (or empty background): zero records -> NaN in finalize
       for (int q = lane; q < n_requests; q += 32) {
         ChanStats z;
         z.sum = z.sumsq = z.wrapsq = z.m10 = z.m01 = z.m20 = z.m02 = z.top2p5_sum = z.top5_sum = 0;
         z.vmin = z.vmax = z.med_lo = z.med_hi = 0;
         chan[(i64)obj * n_requests + q] = z;
       }
-    } else if (qu.phase == 0 && !fits) {  // hand over to the CTA-per-object kernel
+    } else if (is_bg || h > kSide || w > kSide) {  // hand over to the CTA-per-object kernel
       if (lane == 0) stats_list[atomicAdd(stats_count, 1u)] = obj;
-    } else if (fits && rec.n > lo && rec.n <= hi) {
+    } else {
       const int p = find_plane(cm.plane_base, cm.n_planes, obj);
       __syncwarp();
       build_list<false>(cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin,
                         cm.lab_row_stride, (u32)(obj - cm.plane_base[p] + 1), h, w, slot_off, 0, 0);
+      // pad the list to a whole number of 128-pixel steps with copies of its first entry
+      const u32 n_pad = (rec.n + (u32)kPad - 1u) & ~((u32)kPad - 1u);
+      {
+        unsigned short* offs = reinterpret_cast<unsigned short*>(dyn + slot_off);
+        const unsigned short first = offs[0];
+        for (u32 i = rec.n + lane; i < n_pad; i += 32) offs[i] = first;
+        __syncwarp();
+      }
       const PX* px0 = pixels + tile_offset[cm.plane_tile[p]] + (i64)rec.rmin * px_row_stride + rec.cmin;
 #pragma unroll 1
       for (int q = 0; q < n_requests; ++q) {
         const abx_request rq = requests[q];
+        // L2 prefetch one request ahead (a longer distance does not survive: at 2 TB/s the 126 MB L2 turns over in
+        // the time a warp spends on one object): the next request of this object, or the label window and the first
+        // request of the warp's next object
+        if (q + 1 < n_requests) {
+          prefetch_request<PX>(px0 + (i64)requests[q + 1].channel * chan_stride, px_row_stride, z_stride, Z, h, w);
+        } else if (nxt < cm.n_objects) {
+          const abx_object_rec nr = cm.recs[nxt];
+          const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
+          if (nr.n > 0 && nh <= kSide && nw <= kSide) {
+            const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
+            prefetch_rows(cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
+                          cm.lab_row_stride * 2, nh, (u32)nw * 2u);
+            prefetch_request<PX>(pixels + tile_offset[cm.plane_tile[np]] + (i64)nr.rmin * px_row_stride + nr.cmin +
+                                     (i64)requests[0].channel * chan_stride,
+                                 px_row_stride, z_stride, Z, nh, nw);
+          }
+        }
         if (rq.reduction == ABX_RED_DIV) continue;  // floating-point request: object_float.cu
-        request_stats<PX>(rec.n, slot_off, cap, px0 + (i64)rq.channel * chan_stride, (u32)px_row_stride, z_stride, Z,
+        request_stats<PX>(rec.n, n_pad, slot_off, px0 + (i64)rq.channel * chan_stride, (u32)px_row_stride, z_stride, Z,
                           rq.reduction, rq.features, chan + (i64)obj * n_requests + q);
       }
     }
     obj = nxt;
     nxt = obj < cm.n_total ? qu.fetch() : cm.n_total;
-    if (obj >= cm.n_total && qu.phase == 1) {  // large objects are done: help with the small ones
-      qu.phase = 0;
-      obj = qu.fetch();
-      nxt = obj < cm.n_total ? qu.fetch() : cm.n_total;
-    }
   }
 }
 
@@ -867,9 +709,10 @@ object_edt_warp(const Common cm, int want_conical, const double* __restrict__ sq
     if (nxt < cm.n_objects) {
       const abx_object_rec nr = cm.recs[nxt];
       const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
-      prefetch_object<uint16_t>(nr.n, (int)(nr.rmax - nr.rmin) + 1, (int)(nr.cmax - nr.cmin) + 1, lo, hi,
-                                cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
-                                cm.lab_row_stride, nullptr, 0, 0, 0, 0, nullptr, 0);
+      const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
+      if (nr.n > lo && nr.n <= hi && nh <= kSide && nw <= kSide)
+        prefetch_rows(cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
+                      cm.lab_row_stride * 2, nh, (u32)nw * 2u);
     }
     const abx_object_rec rec = cm.recs[obj];
     const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
@@ -915,8 +758,7 @@ int set_smem(K kernel, size_t smem, bool* done) {
 
 template <typename PX>
 int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& cm, cudaStream_t st) {
-  constexpr size_t smem = (kStatsWarps - kLargeSlots) * (kCapSmall * 4 + kBins * 2 + 64) +
-                          kLargeSlots * (kCapLarge * 4 + kBins * 2 + 64);
+  constexpr size_t smem = (size_t)kStatsWarps * kStatsSlot;
   static thread_local bool done[64] = {false};
   int rc = set_smem(object_stats_warp<PX>, smem, done);
   if (rc) return rc;

@@ -119,6 +119,7 @@ class ExtractArgs(C.Structure):
         ("workspace_bytes", C.c_size_t),
         ("stream", C.c_void_p),
         ("stage_events", C.POINTER(C.c_void_p)),
+        ("pixel_elems", C.c_int64),
     ]
 
 

@@ -116,6 +116,30 @@ extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* reco
   return launch_label_scan(args, records, static_cast<u32*>(args->workspace), static_cast<cudaStream_t>(args->stream));
 }
 
+// One helper stream and a fork / join event pair per (host thread, device), created on first use and kept.
+struct Helper {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+static Helper* helper_stream() {
+  static thread_local Helper helpers[64];
+  static thread_local bool made[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!made[dev]) {
+    Helper h;
+    if (cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    helpers[dev] = h;
+    made[dev] = true;
+  }
+  return &helpers[dev];
+}
+
 extern "C" int abx_extract(const abx_extract_args* args) {
   int rc = abx_validate(args);
   if (rc) return rc;
@@ -131,9 +155,23 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   mark(0);
   if ((rc = launch_label_scan(args, ws.recs, ws.err, st))) return rc;
   mark(1);
-  if ((rc = launch_object_stats_warp(args, ws, st))) return rc;  // objects with a window <= 64 x 64
+  // objects with a window <= 64 x 64: TMA-staged windows when the layout allows, plain gathers otherwise
+  bool tma = false;
+  if ((rc = launch_object_stats_tma(args, ws, st, &tma))) return rc;
+  if (!tma && (rc = launch_object_stats_warp(args, ws, st, false))) return rc;
   mark(2);
-  if ((rc = launch_object_edt_warp(args, ws, st))) return rc;
+  // The few objects the TMA kernel left over (about 1 %) go through the gather kernel on a helper stream, one warp per
+  // CTA, next to the shape kernel: their cost is one warp's latency, which hides behind the EDT launch.
+  Helper* hp = tma ? helper_stream() : nullptr;
+  if (tma && !hp && (rc = launch_object_stats_warp(args, ws, st, true))) return rc;
+  if (hp) cudaEventRecord(hp->fork, st);
+  if ((rc = launch_object_edt_warp(args, ws, st))) return rc;  // first: its CTAs take their two places per SM
+  if (hp) {
+    cudaStreamWaitEvent(hp->stream, hp->fork, 0);
+    if ((rc = launch_object_stats_warp(args, ws, hp->stream, true))) return rc;
+    cudaEventRecord(hp->join, hp->stream);
+    cudaStreamWaitEvent(st, hp->join, 0);
+  }
   mark(3);
   if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
   if ((rc = launch_big_background(args, ws, st))) return rc;  // backgrounds of large planes: streaming histogram

@@ -57,7 +57,8 @@ struct Workspace {
   u32* err;          // [0] error flags, [1] stats_list length, [2] edt_list length
   int* stats_list;   // objects the warp kernel handed to the CTA statistics kernel
   int* edt_list;     // objects the warp kernel handed to the CTA EDT kernel
-  u32* list_counts;  // = err + 1: [0] stats_list length, [1] edt_list length, [2..3] / [4..5] work counters
+  u32* list_counts;  // = err + 1: [0] stats_list length, [1] edt_list length, [2] statistics work counter, [3] length of the
+                     // second list of object_stats_tma (back of stats_list), [4..5] EDT work counters, [6] counter of that list
   double* sqrt_tab;  // sqrt(d2) of every squared distance the warp EDT can produce
   u32* bg_hist;      // [n_planes][n_requests][65536] value histograms of large-plane backgrounds (background.cu)
   size_t total;
@@ -69,7 +70,8 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws);
 int abx_validate(const abx_extract_args* a);
 
 int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err /* [3] */, cudaStream_t st);
-int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool todo);
+int launch_object_stats_tma(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool* launched);
 int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);

@@ -388,13 +388,25 @@ template <typename PX>
 __global__ void __launch_bounds__(kStatsWarps * 32, 2)
 object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __restrict__ tile_offset, i64 chan_stride,
                   i64 z_stride, i64 px_row_stride, int Z, const abx_request* __restrict__ requests, int n_requests,
-                  ChanStats* __restrict__ chan, int* __restrict__ stats_list, u32* __restrict__ stats_count) {
+                  ChanStats* __restrict__ chan, int* __restrict__ stats_list, u32* __restrict__ stats_count,
+                  const u32* __restrict__ todo_count, int list_cap) {
+  // Two modes.  todo_count == nullptr: every object of the launch, all its requests (the path for layouts TMA cannot
+  // address).  Otherwise: the objects object_stats_tma could not take (stored from the back of stats_list), one work
+  // item per (object, request) so that the few of them finish in the time of one request.
   const u32 lane = lane_id();
   const u32 slot_off = (threadIdx.x >> 5) * kStatsSlot;
-  Queue qu{cm.counters, cm.n_total, 0};
-  int obj = qu.fetch();
-  int nxt = obj < cm.n_total ? qu.fetch() : cm.n_total;
-  while (obj < cm.n_total) {
+  const bool by_list = todo_count != nullptr;
+  const int n_items = by_list ? (int)(*todo_count) * n_requests : cm.n_total;
+  Queue qu{cm.counters, n_items, 0};
+  int item = qu.fetch();
+  int nxt = item < n_items ? qu.fetch() : n_items;
+  while (item < n_items) {
+    int obj = item, q_lo = 0, q_hi = n_requests;
+    if (by_list) {
+      obj = stats_list[list_cap - 1 - item / n_requests];
+      q_lo = item % n_requests;
+      q_hi = q_lo + 1;
+    }
     const abx_object_rec rec = cm.recs[obj];
     const bool is_bg = obj >= cm.n_objects;
     const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
@@ -422,14 +434,14 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
       }
       const PX* px0 = pixels + tile_offset[cm.plane_tile[p]] + (i64)rec.rmin * px_row_stride + rec.cmin;
 #pragma unroll 1
-      for (int q = 0; q < n_requests; ++q) {
+      for (int q = q_lo; q < q_hi; ++q) {
         const abx_request rq = requests[q];
         // L2 prefetch one request ahead (a longer distance does not survive: at 2 TB/s the 126 MB L2 turns over in
         // the time a warp spends on one object): the next request of this object, or the label window and the first
         // request of the warp's next object
-        if (q + 1 < n_requests) {
+        if (q + 1 < q_hi) {
           prefetch_request<PX>(px0 + (i64)requests[q + 1].channel * chan_stride, px_row_stride, z_stride, Z, h, w);
-        } else if (nxt < cm.n_objects) {
+        } else if (!by_list && nxt < cm.n_objects) {
           const abx_object_rec nr = cm.recs[nxt];
           const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
           if (nr.n > 0 && nh <= kSide && nw <= kSide) {
@@ -446,8 +458,8 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
                           rq.reduction, rq.features, chan + (i64)obj * n_requests + q);
       }
     }
-    obj = nxt;
-    nxt = obj < cm.n_total ? qu.fetch() : cm.n_total;
+    item = nxt;
+    nxt = item < n_items ? qu.fetch() : n_items;
   }
 }
 
@@ -757,16 +769,20 @@ int set_smem(K kernel, size_t smem, bool* done) {
 }
 
 template <typename PX>
-int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& cm, cudaStream_t st) {
+int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& cm, cudaStream_t st, bool todo) {
   constexpr size_t smem = (size_t)kStatsWarps * kStatsSlot;
   static thread_local bool done[64] = {false};
   int rc = set_smem(object_stats_warp<PX>, smem, done);
   if (rc) return rc;
   int grid = (cm.n_total + kStatsWarps - 1) / kStatsWarps;
   if (grid > 148 * 2) grid = 148 * 2;  // persistent: 2 CTAs per SM, warps pull objects from a counter
-  object_stats_warp<PX><<<grid, kStatsWarps * 32, smem, st>>>(
+  // todo: the length of the list is only known on the device — a fixed grid of single-warp CTAs (12 KB of shared memory
+  // each, so that they fit next to the CTAs of the shape kernel running on the caller's stream)
+  if (todo) grid = 148;
+  object_stats_warp<PX><<<grid, todo ? 32 : kStatsWarps * 32, todo ? (size_t)kStatsSlot : smem, st>>>(
       cm, static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride,
-      a->row_stride, a->Z, a->requests, a->n_requests, ws.chan, ws.stats_list, ws.list_counts);
+      a->row_stride, a->Z, a->requests, a->n_requests, ws.chan, ws.stats_list, ws.list_counts,
+      todo ? ws.list_counts + 3 : nullptr, a->n_objects + a->n_planes);
   return abx_check_cuda(cudaGetLastError(), "object_stats_warp");
 }
 
@@ -796,13 +812,14 @@ static Common make_common(const abx_extract_args* a, const Workspace& ws, int n_
   return cm;
 }
 
-int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+// todo = false: every window-sized object; todo = true: the objects object_stats_tma left on its second list
+int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool todo) {
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0 || a->n_requests == 0) return ABX_OK;
   Common cm = make_common(a, ws, n_total);
-  cm.counters = ws.list_counts + 2;
-  if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st);
-  if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st);
+  cm.counters = ws.list_counts + (todo ? 6 : 2);
+  if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st, todo);
+  if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st, todo);
   return ABX_OK;  // float pixels: every request belongs to object_float.cu
 }
 

@@ -18,7 +18,7 @@ constexpr u32 kFull = 0xFFFFFFFFu;
 // Every device function derives its shared-memory pointers from this array plus a byte offset, so that the
 // compiler keeps them in the shared address space (generic pointers passed through __noinline__ calls
 // compiled to LD.E/ST.E with 64-bit address arithmetic: 24 instructions per EDT step instead of 8).
-extern __shared__ __align__(16) unsigned char dyn[];
+extern __shared__ __align__(128) unsigned char dyn[];
 
 // Sum of a 64-bit quantity over the warp from three independent 32-bit REDUX reductions of its
 // 24/24/16-bit slices (each slice sum < 2^29): shorter and far less latency than five dependent

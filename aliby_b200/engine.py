@@ -288,6 +288,8 @@ def run_planes(
     a.n_columns = n_cols
     a.need_edt = int(plan.need_edt)
     a.request_feature_union = nat.F_HAS_DIV if any(r[1] == nat.RED_DIV for r in plan.requests) else 0
+    if plan.requests:  # extent of the pixel buffer behind data_ptr(), for the TMA description of it
+        a.pixel_elems = (pixels.untyped_storage().nbytes() // pixels.element_size()) - pixels.storage_offset()
     a.table = out.data_ptr()
     a.stream = torch.cuda.current_stream(device).cuda_stream
     if stage_events is not None:  # 6 handles from abx_event_create (bench.py: live per-stage timing)

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define ABX_VERSION 1
+#define ABX_VERSION 2
 
 typedef enum abx_status {
   ABX_OK = 0,
@@ -158,6 +158,10 @@ typedef struct abx_extract_args {
   /* optional: 6 events made by abx_event_create, recorded on `stream` before the label scan and after the
    * label scan / object_stats_warp / object_edt_warp / large-object kernels / finalisation */
   void* const* stage_events;
+  /* elements of the caller's pixel buffer counted from `pixels` (0 = unknown).  Lets the library describe the buffer
+   * to the TMA unit (whole rows of row_stride elements, out-of-buffer parts of a box zero-filled); without it, or for
+   * layouts TMA cannot address (unaligned base / strides, Z stacks), the statistics kernel gathers with plain loads. */
+  int64_t pixel_elems;
 } abx_extract_args;
 
 int abx_version(void);

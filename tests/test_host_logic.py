@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(nat.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert nat.lib().abx_version() == 1
+    assert nat.lib().abx_version() == 2
     # struct mirrors: sizes must agree with the C side (48-byte records, 16-byte requests)
     assert ctypes.sizeof(nat.ObjectRec) == 48 and ctypes.sizeof(nat.Request) == 16 and ctypes.sizeof(nat.Column) == 8
 

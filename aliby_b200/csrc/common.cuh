@@ -71,7 +71,8 @@ int abx_validate(const abx_extract_args* a);
 
 int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err /* [3] */, cudaStream_t st);
 int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool todo);
-int launch_object_stats_tma(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool* launched);
+int launch_object_stats_tma(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool shared_sm, bool* launched);
+bool abx_stats_tma_ok(const abx_extract_args* a);
 int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);

@@ -1,0 +1,479 @@
+// Shape metrics of window-sized objects (bounding box <= 64 x 64): ONE WARP PER OBJECT, everything on bitmasks
+// and a 16-bit grid in shared memory — no pixel list.  The three chained exact EDTs of
+// src/extraction/core/functions/cell.py:176-229 (conical_volume, min_maj_approximation -> eccentricity, volume):
+//
+//   phase M  label window -> 64-bit row masks.  The window comes in by TMA (cp.async.bulk.tensor boxes of
+//            64 columns x 8 rows, started at a 16-byte aligned column left of the bbox) when the label layout
+//            qualifies and the shifted window still fits 64 columns; by plain loads otherwise.
+//   phase R  squared row distances g^2 (u16) of every cell, from the run ends of the row mask
+//   phase C  EDT 1, exact column pass with packed 16-bit arithmetic: a lane owns two adjacent columns and four
+//            rows at a time; one 32-bit shared-memory load brings a source row for both columns and one
+//            VIADDMNMX.U16x2 (min(g^2 + d^2, best) on both halves) updates a target row.  Four zero rows above
+//            and below the window bound every walk (a finished pixel's candidates are >= d^2 >= its best).
+//   phase T  cone top = pixels that attain the maximum, as a second set of row masks
+//   phase 2  EDT 2 only where it is needed, max over the object of the distance to the nearest top pixel:
+//            one top (half of all cells) -> the row ends decide; up to four -> packed column terms kept in
+//            registers; more -> per-row loop over the tops
+//   phase 3  EDT 3 on the (small) cone top, lanes over rows
+//
+// Slot: row masks 512 B | top masks 512 B | mbarrier 128 B | run ends 256 B | grid u16 [72][64] = 10 624 B per warp,
+// 10 warps per CTA, 2 CTAs per SM.  Larger windows go to the CTA-per-object kernel (shape_edt.cu).
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+#include "warp_common.cuh"
+#include "tma.cuh"
+
+constexpr int kGridWarps = 10;
+constexpr u32 kTopOff = 512, kGBarOff = 1024, kInfoOff = 1152, kGOff = 1408;
+constexpr u32 kMargin = 4;                       // zero rows above and below the window
+constexpr u32 kGRows = kSide + 2 * kMargin;      // 72
+constexpr u32 kGridSlot = kGOff + kGRows * 128;  // 10 624
+static_assert(kGOff % 128 == 0, "TMA destinations are 128-byte aligned");
+
+// squared distance of column c to the nearest set bit of m (0xFFFFFFFF if m == 0)
+__device__ __forceinline__ u32 nearest_bit_sq(u64 m, u32 c) {
+  if (m == 0) return kFull;
+  const u64 le = m & (~0ull >> (63 - c));  // bits <= c
+  const u64 ge = m >> c;                   // bits >= c, shifted
+  u32 d = 64;
+  if (le) d = c - (63u - (u32)__clzll((long long)le));
+  if (ge) d = min(d, (u32)__ffsll((long long)ge) - 1u);
+  return d * d;
+}
+
+// row distance of an object pixel at column c of row mask m (distance to the nearest zero bit, zeros beyond both ends)
+__device__ __forceinline__ u32 row_distance(u64 m, u32 c) {
+  const u64 z = ~m;
+  const u64 le = c ? (z & (~0ull >> (64 - c))) : 0ull;  // zeros at columns < c
+  const u32 dl = le ? (c - (63u - (u32)__clzll((long long)le))) : (c + 1u);
+  const u64 ge = c < 63u ? (z >> (c + 1u)) : 0ull;      // zeros at columns > c
+  const u32 dr = ge ? (u32)__ffsll((long long)ge) : (64u - c);
+  return min(dl, dr);
+}
+
+__device__ __forceinline__ void shape_object(const abx_object_rec& rec, int p, u32 label, const Common& cm,
+                                             const CUtensorMap* lab_map, bool use_tma, u32 slot_off, u32 bar, u32& parity,
+                                             bool want_conical, const double* __restrict__ sqrt_tab,
+                                             ShapeStats* __restrict__ dst) {
+  u64* rowmask = reinterpret_cast<u64*>(dyn + slot_off);
+  u64* topmask = reinterpret_cast<u64*>(dyn + slot_off + kTopOff);
+  const u32 g_off = slot_off + kGOff;  // grid row j of the window lives at row j + kMargin
+  const u32 lane = lane_id();
+  const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
+  const u32 n = rec.n;
+  // ---- phase M: row masks ----
+  u32 s_lab = rec.cmin & 7u;  // the TMA box starts at a 16-byte multiple: s_lab columns left of the bbox
+  const bool by_tma = use_tma && (u32)w + s_lab <= 64u;
+  if (!by_tma) s_lab = 0;
+  __syncwarp();
+  if (by_tma) {
+    const u32 h8 = ((u32)h + 7u) & ~7u;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the grid was written by generic stores
+      mbar_expect_tx(bar, h8 * 128u);
+      const u32 dst0 = smem_addr(dyn + g_off + kMargin * 128u);
+      for (u32 j = 0; j < h8; j += 8) tma_box_3d(dst0 + j * 128u, lab_map, (int)(rec.cmin - s_lab), (int)(rec.rmin + j), p, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    const unsigned short* lw = reinterpret_cast<const unsigned short*>(dyn + g_off + kMargin * 128u);
+#pragma unroll 4
+    for (int r = 0; r < h; ++r) {
+      // columns outside the bbox hold other labels (or the hardware's zero fill): they never match
+      const u32 b0 = __ballot_sync(kFull, (u32)lw[r * 64 + lane] == label);
+      const u32 b1 = __ballot_sync(kFull, (u32)lw[r * 64 + 32 + lane] == label);
+      if (lane == 0) rowmask[r] = (u64)b0 | ((u64)b1 << 32);
+    }
+  } else {
+    const uint16_t* lab = cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin;
+#pragma unroll 4
+    for (int r = 0; r < h; ++r) {
+      const uint16_t* lrow = lab + (i64)r * cm.lab_row_stride;
+      const u32 l0 = lane < (u32)w ? (u32)__ldg(lrow + lane) : kFull;
+      const u32 l1 = lane + 32u < (u32)w ? (u32)__ldg(lrow + lane + 32) : kFull;
+      const u32 b0 = __ballot_sync(kFull, l0 == label);
+      const u32 b1 = __ballot_sync(kFull, l1 == label);
+      if (lane == 0) rowmask[r] = (u64)b0 | ((u64)b1 << 32);
+    }
+  }
+  topmask[lane] = 0;
+  topmask[lane + 32] = 0;
+  __syncwarp();
+  // ---- phase R: squared row distances, two columns per lane ----
+  // lanes over rows first: the run ends of each row, a | b << 8 | kind << 16 (kind 0 empty, 1 one run, 2 several)
+  u32* rowinfo = reinterpret_cast<u32*>(dyn + slot_off + kInfoOff);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = (int)lane + 32 * k;
+    if (r < h) {
+      const u64 m = rowmask[r];
+      u32 info = 0;
+      if (m) {
+        const u32 a = (u32)__ffsll((long long)m) - 1u, b = 63u - (u32)__clzll((long long)m);
+        const u64 run = m >> a;
+        info = a | (b << 8) | (((run & (run + 1ull)) == 0ull) ? 0x10000u : 0x20000u);
+      }
+      rowinfo[r] = info;
+    }
+  }
+  __syncwarp();
+  const u32 c0 = 2u * lane;
+#pragma unroll 4
+  for (int r = 0; r < h; ++r) {
+    const u32 info = rowinfo[r];  // warp-uniform
+    const u32 a = info & 0xFFu, b = (info >> 8) & 0xFFu;
+    u32 g0 = 0, g1 = 0;
+    if (c0 >= a && c0 <= b) g0 = min(c0 - a, b - c0) + 1u;  // one run [a, b]: distances from its ends
+    if (c0 + 1u >= a && c0 + 1u <= b) g1 = min(c0 + 1u - a, b - c0 - 1u) + 1u;
+    if (info & 0x20000u) {  // several runs (rare)
+      const u64 m = rowmask[r];
+      g0 = ((m >> c0) & 1ull) ? row_distance(m, c0) : 0u;
+      g1 = ((m >> (c0 + 1u)) & 1ull) ? row_distance(m, c0 + 1u) : 0u;
+    } else if ((info & 0x10000u) == 0u) {
+      g0 = g1 = 0;
+    }
+    *reinterpret_cast<u32*>(dyn + g_off + ((u32)r + kMargin) * 128u + 4u * lane) = (g0 * g0) | ((g1 * g1) << 16);
+  }
+  // the frame row and the margin below the window (the label box may have left other labels there)
+  *reinterpret_cast<uint4*>(dyn + g_off + ((u32)h + kMargin) * 128u + 16u * lane) = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  // ---- phase C: EDT 1, exact column pass on packed pairs, four target rows per lane at a time ----
+  u32 lmax = 0;
+  double s_nn = 0.0;
+  u64 at_lo = 0, at_hi = 0;  // bit 8 * group + 2 * row-in-group + half: that pixel attains lmax
+  {
+    u32 grp = 0;
+#pragma unroll 1
+    for (int r0 = 0; r0 < h; r0 += 4, ++grp) {
+      const u32 base = g_off + ((u32)r0 + kMargin) * 128u + 4u * lane;  // byte offset of (row r0, this lane's pair)
+      const u32 q0 = *reinterpret_cast<const u32*>(dyn + base);
+      const u32 q1 = *reinterpret_cast<const u32*>(dyn + base + 128u);
+      const u32 q2 = *reinterpret_cast<const u32*>(dyn + base + 256u);
+      const u32 q3 = *reinterpret_cast<const u32*>(dyn + base + 384u);
+      constexpr u32 k1 = 0x00010001u, k4 = 0x00040004u, k9 = 0x00090009u;
+      // sources inside the group
+      u32 b0 = __viaddmin_u16x2(q1, k1, q0); b0 = __viaddmin_u16x2(q2, k4, b0); b0 = __viaddmin_u16x2(q3, k9, b0);
+      u32 b1 = __viaddmin_u16x2(q0, k1, q1); b1 = __viaddmin_u16x2(q2, k1, b1); b1 = __viaddmin_u16x2(q3, k4, b1);
+      u32 b2 = __viaddmin_u16x2(q0, k4, q2); b2 = __viaddmin_u16x2(q1, k1, b2); b2 = __viaddmin_u16x2(q3, k1, b2);
+      u32 b3 = __viaddmin_u16x2(q0, k9, q3); b3 = __viaddmin_u16x2(q1, k4, b3); b3 = __viaddmin_u16x2(q2, k1, b3);
+      // sources outside: step d brings row r0 - d (distances d .. d + 3 to the four targets) and row r0 + 3 + d
+      u32 e0 = k1, e1 = k4, e2 = k9, e3 = 0x00100010u;  // (d + j)^2 on both halves, d = 1
+      u32 inc = 0x00090009u;                             // 2 (d + 4) - 1: e3 of the next step = e3 + inc
+      u32 up = base - 128u, dn = base + 512u;
+      u32 lim = 1;                                       // d^2: nothing outside is closer than d
+      u32 mx = __vmaxu2(__vmaxu2(b0, b1), __vmaxu2(b2, b3));
+      mx = max(mx & 0xFFFFu, mx >> 16);
+      while (mx > lim) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {  // two steps per test: a surplus step reads one more zero-bounded row
+          const u32 ga = *reinterpret_cast<const u32*>(dyn + up);
+          const u32 gb = *reinterpret_cast<const u32*>(dyn + dn);
+          b0 = __viaddmin_u16x2(ga, e0, b0); b0 = __viaddmin_u16x2(gb, e3, b0);
+          b1 = __viaddmin_u16x2(ga, e1, b1); b1 = __viaddmin_u16x2(gb, e2, b1);
+          b2 = __viaddmin_u16x2(ga, e2, b2); b2 = __viaddmin_u16x2(gb, e1, b2);
+          b3 = __viaddmin_u16x2(ga, e3, b3); b3 = __viaddmin_u16x2(gb, e0, b3);
+          e0 = e1; e1 = e2; e2 = e3; e3 += inc; inc += 0x00020002u;
+          up -= 128u; dn += 128u;
+        }
+        lim = e0 & 0xFFFFu;  // (d + 1)^2 of the step that comes next
+        mx = __vmaxu2(__vmaxu2(b0, b1), __vmaxu2(b2, b3));
+        mx = max(mx & 0xFFFFu, mx >> 16);
+      }
+      // ---- this lane's eight results: running maximum and who attains it, sum of distances ----
+      if (mx > lmax) { lmax = mx; at_lo = at_hi = 0; }
+      if (mx == lmax && mx > 0) {
+        u32 bits = 0;
+        bits |= ((b0 & 0xFFFFu) == lmax) ? 1u : 0u;   bits |= ((b0 >> 16) == lmax) ? 2u : 0u;
+        bits |= ((b1 & 0xFFFFu) == lmax) ? 4u : 0u;   bits |= ((b1 >> 16) == lmax) ? 8u : 0u;
+        bits |= ((b2 & 0xFFFFu) == lmax) ? 16u : 0u;  bits |= ((b2 >> 16) == lmax) ? 32u : 0u;
+        bits |= ((b3 & 0xFFFFu) == lmax) ? 64u : 0u;  bits |= ((b3 >> 16) == lmax) ? 128u : 0u;
+        if (grp < 8) at_lo |= (u64)bits << (8u * grp); else at_hi |= (u64)bits << (8u * (grp - 8u));
+      }
+      if (want_conical) {  // non-object cells have distance 0
+        s_nn += sqrt_tab[b0 & 0xFFFFu] + sqrt_tab[b0 >> 16];
+        s_nn += sqrt_tab[b1 & 0xFFFFu] + sqrt_tab[b1 >> 16];
+        s_nn += sqrt_tab[b2 & 0xFFFFu] + sqrt_tab[b2 >> 16];
+        s_nn += sqrt_tab[b3 & 0xFFFFu] + sqrt_tab[b3 >> 16];
+      }
+    }
+  }
+  const u32 max_nn2 = __reduce_max_sync(kFull, lmax);
+  if (want_conical) {
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) s_nn += __shfl_xor_sync(kFull, s_nn, k);
+  }
+  // ---- phase T: cone top = pixels with nn2 == max ----
+  if (lmax == max_nn2) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      u64 m = half ? at_hi : at_lo;
+      while (m) {
+        const u32 b = (u32)__ffsll((long long)m) - 1u;
+        m &= m - 1;
+        const u32 row = 4u * ((b >> 3) + 8u * half) + ((b >> 1) & 3u), col = c0 + (b & 1u);
+        atomicOr(reinterpret_cast<unsigned long long*>(&topmask[row]), 1ull << col);
+      }
+    }
+  }
+  __syncwarp();
+  const u64 tm0 = topmask[lane], tm1 = topmask[lane + 32];
+  const u32 n_top = __reduce_add_sync(kFull, (u32)(__popcll(tm0) + __popcll(tm1)));
+  // ---- phase 2: max over the object of the squared distance to the nearest cone-top pixel ----
+  u32 lmax2 = 0;
+  if (n_top <= 32) {
+    u32 my_top = 0;  // lane k keeps top pixel k (row-major order), (r << 6) | c
+    {
+      u64 a = tm0, b = tm1;
+      u32 k = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        u64& cur = pass == 0 ? a : b;
+        u32 any = __ballot_sync(kFull, cur != 0);
+        while (any) {
+          const int src = __ffs(any) - 1;
+          const u64 mm = __shfl_sync(kFull, cur, src);
+          const u32 c = (u32)__ffsll((long long)mm) - 1u;
+          const u32 r = (u32)src + 32u * pass;
+          if (lane == k) my_top = (r << 6) | c;
+          ++k;
+          if ((int)lane == src) cur &= cur - 1;
+          any = __ballot_sync(kFull, cur != 0);
+        }
+      }
+    }
+    if (n_top == 1) {
+      // one top pixel: the farthest pixel of a row is one of the row's two ends
+      const u32 tp = __shfl_sync(kFull, my_top, 0);
+      const int tr = (int)(tp >> 6), tc = (int)(tp & 63u);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = (int)lane + 32 * k;
+        const u64 m = r < h ? rowmask[r] : 0ull;
+        if (m) {
+          const int a = __ffsll((long long)m) - 1, b = 63 - __clzll((long long)m);
+          const int dc = max(abs(a - tc), abs(b - tc)), dr = r - tr;
+          lmax2 = max(lmax2, (u32)(dr * dr + dc * dc));
+        }
+      }
+    } else if (n_top <= 4) {
+      // the column terms of the (up to) four tops stay in registers: one packed add-min per (row, top)
+      u32 pc[4];
+      int tr[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const u32 tp = __shfl_sync(kFull, my_top, (u32)t < n_top ? t : 0);  // unused entries repeat top 0
+        tr[t] = (int)(tp >> 6);
+        const int d = (int)c0 - (int)(tp & 63u);
+        pc[t] = (u32)(d * d) | ((u32)((d + 1) * (d + 1)) << 16);
+      }
+#pragma unroll 2
+      for (int r = 0; r < h; ++r) {
+        const u64 m = rowmask[r];
+        u32 best = kFull;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int dr = r - tr[t];
+          best = __viaddmin_u16x2(pc[t], (u32)(dr * dr) * 0x00010001u, best);
+        }
+        const u32 pair = (u32)(m >> c0) & 3u;
+        if (pair & 1u) lmax2 = max(lmax2, best & 0xFFFFu);
+        if (pair & 2u) lmax2 = max(lmax2, best >> 16);
+      }
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < h; ++r) {
+        const u64 m = rowmask[r];
+        if (m == 0) continue;
+        u32 best = kFull;
+#pragma unroll 1
+        for (u32 t = 0; t < n_top; ++t) {
+          const u32 tp = __shfl_sync(kFull, my_top, t);
+          const int dr = r - (int)(tp >> 6), d = (int)c0 - (int)(tp & 63u);
+          best = __viaddmin_u16x2((u32)(d * d) | ((u32)((d + 1) * (d + 1)) << 16), (u32)(dr * dr) * 0x00010001u, best);
+        }
+        const u32 pair = (u32)(m >> c0) & 3u;
+        if (pair & 1u) lmax2 = max(lmax2, best & 0xFFFFu);
+        if (pair & 2u) lmax2 = max(lmax2, best >> 16);
+      }
+    }
+  } else {
+    // plateau: rows of the cone-top mask, nearest set bit per row
+#pragma unroll 1
+    for (int r = 0; r < h; ++r) {
+      const u64 m = rowmask[r];
+      const u32 pair = (u32)(m >> c0) & 3u;
+      u32 best0 = kFull, best1 = kFull;
+#pragma unroll 1
+      for (int rr = 0; rr < h; ++rr) {
+        const u64 tm = topmask[rr];
+        if (tm == 0) continue;
+        const u32 dr2 = (u32)((r - rr) * (r - rr));
+        best0 = min(best0, nearest_bit_sq(tm, c0) + dr2);
+        best1 = min(best1, nearest_bit_sq(tm, c0 + 1u) + dr2);
+      }
+      if (pair & 1u) lmax2 = max(lmax2, best0);
+      if (pair & 2u) lmax2 = max(lmax2, best1);
+    }
+  }
+  const u32 max_dn2 = __reduce_max_sync(kFull, lmax2);
+  // ---- phase 3: size of the cone top = distance of each top pixel to the rest of the object ----
+  double s_top = 0.0;
+  if (n_top == n) {
+    // `dn == 0` has no zero at all: SciPy measures to index (-1, 0) of the padded plane
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = (int)lane + 32 * k;
+      u64 m = r < h ? rowmask[r] : 0ull;
+      while (m) {
+        const u32 cb = (u32)__ffsll((long long)m) - 1u;
+        m &= m - 1;
+        const double dr = (double)rec.rmin + (double)r + 2.0, dc = (double)rec.cmin + (double)(cb - s_lab) + 1.0;
+        s_top += sqrt(dr * dr + dc * dc);
+      }
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) s_top += __shfl_xor_sync(kFull, s_top, k);
+  } else {
+    // lanes over rows: q = object pixels that are not cone top
+    const u64 q0 = (lane < (u32)h) ? (rowmask[lane] & ~tm0) : 0ull;
+    const u64 q1 = (lane + 32 < (u32)h) ? (rowmask[lane + 32] & ~tm1) : 0ull;
+    u32 rows0 = __ballot_sync(kFull, tm0 != 0), rows1 = __ballot_sync(kFull, tm1 != 0);  // rows that hold top pixels
+#pragma unroll 1
+    while (rows0 | rows1) {
+      int r;
+      if (rows0) { r = __ffs(rows0) - 1; rows0 &= rows0 - 1; }
+      else { r = 32 + __ffs(rows1) - 1; rows1 &= rows1 - 1; }
+      u64 tm = topmask[r];  // warp-uniform
+      while (tm) {
+        const u32 c = (u32)__ffsll((long long)tm) - 1u;
+        tm &= tm - 1;
+        u32 best = kFull;
+        const u32 d0 = nearest_bit_sq(q0, c);
+        const int dr0 = r - (int)lane;
+        if (d0 != kFull) best = d0 + (u32)(dr0 * dr0);
+        const u32 d1 = nearest_bit_sq(q1, c);
+        const int dr1 = r - (int)lane - 32;
+        if (d1 != kFull) best = min(best, d1 + (u32)(dr1 * dr1));
+        best = __reduce_min_sync(kFull, best);
+        s_top += sqrt((double)best);  // same value in every lane
+      }
+    }
+  }
+  if (lane == 0) {
+    ShapeStats out;
+    out.sum_nn = s_nn; out.sum_top = s_top; out.max_nn2 = max_nn2; out.max_dn2 = max_dn2;
+    *dst = out;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kGridWarps * 32, 2)
+object_edt_grid(const __grid_constant__ CUtensorMap lab_map, int use_tma, const Common cm, int want_conical,
+                const double* __restrict__ sqrt_tab, ShapeStats* __restrict__ shape, int* __restrict__ edt_list,
+                u32* __restrict__ edt_count) {
+  const u32 lane = lane_id();
+  const u32 slot_off = (threadIdx.x >> 5) * kGridSlot;
+  const u32 bar = smem_addr(dyn + slot_off + kGBarOff);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the margin above the window stays zero for the life of the kernel
+  *reinterpret_cast<uint4*>(dyn + slot_off + kGOff + 16u * lane) = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  u32 parity = 0;
+  Queue qu{cm.counters, cm.n_objects, 0};
+  int obj = qu.fetch();
+  int nxt = obj < cm.n_objects ? qu.fetch() : cm.n_objects;
+  while (obj < cm.n_objects) {
+    if (nxt < cm.n_objects) {  // L2 prefetch of the next object's label window
+      const abx_object_rec nr = cm.recs[nxt];
+      const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
+      if (nr.n > 0 && nh <= kSide && nw <= kSide) {
+        const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
+        prefetch_rows(cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
+                      cm.lab_row_stride * 2, nh, (u32)nw * 2u);
+      }
+    }
+    const abx_object_rec rec = cm.recs[obj];
+    const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
+    if (rec.n == 0) {
+      if (lane == 0) { ShapeStats z; z.sum_nn = 0; z.sum_top = 0; z.max_nn2 = 0; z.max_dn2 = 0; shape[obj] = z; }
+    } else if (h > kSide || w > kSide) {
+      if (lane == 0) edt_list[atomicAdd(edt_count, 1u)] = obj;  // hand over to the CTA-per-object kernel
+    } else {
+      const int p = find_plane(cm.plane_base, cm.n_planes, obj);
+      shape_object(rec, p, (u32)(obj - cm.plane_base[p] + 1), cm, &lab_map, use_tma != 0, slot_off, bar, parity,
+                   want_conical != 0, sqrt_tab, shape + obj);
+    }
+    obj = nxt;
+    nxt = obj < cm.n_objects ? qu.fetch() : cm.n_objects;
+  }
+}
+
+// Label planes (W, H, P) with a box of 64 columns x 8 rows, or false when the layout does not qualify for TMA.
+bool make_label_map(const abx_extract_args* a, CUtensorMap* tm) {
+  EncodeFn encode = tensor_map_encoder();
+  if (!encode) return false;
+  const i64 lab_ps = a->n_planes > 1 ? a->label_plane_stride : (i64)a->H * a->label_row_stride;
+  if ((reinterpret_cast<uintptr_t>(a->labels) & 15u) || a->label_row_stride % 8 || lab_ps % 8 || a->W < 64 || a->H < 8 ||
+      a->label_row_stride < a->W || lab_ps < (i64)a->H * a->label_row_stride)
+    return false;
+  const cuuint64_t ldim[3] = {(cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->n_planes};
+  const cuuint64_t lstr[2] = {(cuuint64_t)a->label_row_stride * 2u, (cuuint64_t)lab_ps * 2u};
+  const cuuint32_t lbox[3] = {64u, 8u, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(a->labels), ldim, lstr, lbox, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__global__ void sqrt_table_kernel(double* tab, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tab[i] = sqrt((double)i);
+}
+
+}  // namespace
+
+// sqrt(d2) for every squared distance the first EDT of a 64 x 64 window can produce (exact: IEEE sqrt)
+int abx_sqrt_table_entries() { return (kSide / 2) * (kSide / 2) + 1; }  // row distances are <= 32
+
+int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+  if (!a->need_edt || a->n_objects == 0) return ABX_OK;
+  constexpr size_t smem = (size_t)kGridWarps * kGridSlot;
+  static thread_local bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(object_edt_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return abx_check_cuda(e, "object_edt_grid smem attribute");
+    done[dev] = true;
+  }
+  const int n_tab = abx_sqrt_table_entries();
+  sqrt_table_kernel<<<(n_tab + 255) / 256, 256, 0, st>>>(ws.sqrt_tab, n_tab);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  const int use_tma = make_label_map(a, &tm) ? 1 : 0;
+  Common cm;
+  cm.labels = static_cast<const uint16_t*>(a->labels);
+  cm.lab_plane_stride = a->label_plane_stride;
+  cm.lab_row_stride = a->label_row_stride;
+  cm.plane_tile = a->plane_tile;
+  cm.plane_base = a->plane_base;
+  cm.n_planes = a->n_planes;
+  cm.n_objects = a->n_objects;
+  cm.n_total = a->n_objects;
+  cm.recs = ws.recs;
+  cm.counters = ws.list_counts + 4;
+  int grid = (a->n_objects + kGridWarps - 1) / kGridWarps;
+  if (grid > 148 * 2) grid = 148 * 2;  // persistent: 2 CTAs per SM, warps pull objects from a counter
+  object_edt_grid<<<grid, kGridWarps * 32, smem, st>>>(tm, use_tma, cm, (a->need_edt & 2) != 0, ws.sqrt_tab, ws.shape,
+                                                       ws.edt_list, ws.list_counts + 1);
+  return abx_check_cuda(cudaGetLastError(), "object_edt_grid");
+}

@@ -27,35 +27,13 @@
 namespace {
 
 #include "warp_common.cuh"
+#include "tma.cuh"
 
 constexpr int kTmaWarps = 14;
 constexpr u32 kTmaSlot = 16384;
 constexpr u32 kTOff = kBins * 4, kBarOff = kTOff + 64, kFlexOff = kBarOff + 64, kFlex = kTmaSlot - kFlexOff;
 constexpr int kBoxRows = 8;
 static_assert(kFlexOff % 128 == 0, "TMA destinations are 128-byte aligned");
-
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  u32 done;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_box_2d(u32 dst, const CUtensorMap* tmap, int x, int y, u32 bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_box_3d(u32 dst, const CUtensorMap* tmap, int x, int y, int z, u32 bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
 
 // phase M from the staged label window: compact list of k = (r << sh) | c, row-major, no atomics
 __device__ __forceinline__ void build_list_smem(u32 lwin_off, u32 label, int h, int sh, u32 offs_off) {
@@ -367,21 +345,6 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
   }
 }
 
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeFn tensor_map_encoder() {
-  static EncodeFn encode = [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      fn = nullptr;
-    return reinterpret_cast<EncodeFn>(fn);
-  }();
-  return encode;
-}
-
 // The four tensor maps, or false when the layout does not qualify for TMA (the caller then takes object_stats_warp).
 bool make_maps(const abx_extract_args* a, TmaMaps* m) {
   EncodeFn encode = tensor_map_encoder();
@@ -419,19 +382,21 @@ bool make_maps(const abx_extract_args* a, TmaMaps* m) {
 }
 
 template <typename PX>
-int launch_tma(const abx_extract_args* a, const Workspace& ws, const TmaMaps& maps, const Common& cm, cudaStream_t st) {
-  constexpr size_t smem = (size_t)kTmaWarps * kTmaSlot;
+int launch_tma(const abx_extract_args* a, const Workspace& ws, const TmaMaps& maps, const Common& cm, cudaStream_t st,
+               int warps) {
+  constexpr size_t smem_max = (size_t)kTmaWarps * kTmaSlot;
+  const size_t smem = (size_t)warps * kTmaSlot;
   static thread_local bool done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(object_stats_tma<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(object_stats_tma<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return abx_check_cuda(e, "object_stats_tma smem attribute");
     done[dev] = true;
   }
-  int grid = (cm.n_total + kTmaWarps - 1) / kTmaWarps;
+  int grid = (cm.n_total + warps - 1) / warps;
   if (grid > 148) grid = 148;  // persistent: one CTA per SM, warps pull objects from a counter
-  object_stats_tma<PX><<<grid, kTmaWarps * 32, smem, st>>>(
+  object_stats_tma<PX><<<grid, warps * 32, smem, st>>>(
       maps, cm, static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride,
       a->row_stride, (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests, ws.chan, ws.stats_list,
       ws.list_counts, ws.list_counts + 3, a->n_objects + a->n_planes);
@@ -440,8 +405,20 @@ int launch_tma(const abx_extract_args* a, const Workspace& ws, const TmaMaps& ma
 
 }  // namespace
 
+// Whether abx_extract will take the TMA kernel for this call (layout and dtype qualify).
+bool abx_stats_tma_ok(const abx_extract_args* a) {
+  const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
+  if (n_total == 0 || a->n_requests == 0) return false;
+  if (a->pixel_dtype != ABX_U16 && a->pixel_dtype != ABX_U8) return false;
+  TmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  return make_maps(a, &maps);
+}
+
 // Returns ABX_OK and *launched = true when the TMA kernel took the statistics of the window-sized objects.
-int launch_object_stats_tma(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool* launched) {
+// shared_sm: the shape kernel runs at the same time on another stream — half the warps per CTA, so that one CTA of each
+// kernel fits an SM.
+int launch_object_stats_tma(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool shared_sm, bool* launched) {
   *launched = false;
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0 || a->n_requests == 0) return ABX_OK;
@@ -461,6 +438,7 @@ int launch_object_stats_tma(const abx_extract_args* a, const Workspace& ws, cuda
   cm.recs = ws.recs;
   cm.counters = ws.list_counts + 2;
   *launched = true;
-  if (a->pixel_dtype == ABX_U16) return launch_tma<uint16_t>(a, ws, maps, cm, st);
-  return launch_tma<uint8_t>(a, ws, maps, cm, st);
+  const int warps = shared_sm ? kTmaWarps / 2 : kTmaWarps;
+  if (a->pixel_dtype == ABX_U16) return launch_tma<uint16_t>(a, ws, maps, cm, st, warps);
+  return launch_tma<uint8_t>(a, ws, maps, cm, st, warps);
 }

@@ -422,6 +422,10 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
     } else {
       const int p = find_plane(cm.plane_base, cm.n_planes, obj);
       __syncwarp();
+      if (by_list)  // nothing was prefetched for this item: start its one request towards L2 before the label loads
+        prefetch_request<PX>(pixels + tile_offset[cm.plane_tile[p]] + (i64)rec.rmin * px_row_stride + rec.cmin +
+                                 (i64)requests[q_lo].channel * chan_stride,
+                             px_row_stride, z_stride, Z, h, w);
       build_list<false>(cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin,
                         cm.lab_row_stride, (u32)(obj - cm.plane_base[p] + 1), h, w, slot_off, 0, 0);
       // pad the list to a whole number of 128-pixel steps with copies of its first entry
@@ -463,299 +467,6 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// phase E: three chained exact EDTs on the 64-bit row masks
-// ------------------------------------------------------------------------------------------------
-// squared distance of column c to the nearest set bit of m (0xFFFFFFFF if m == 0)
-__device__ __forceinline__ u32 nearest_bit_sq(u64 m, u32 c) {
-  if (m == 0) return kFull;
-  const u64 le = m & (~0ull >> (63 - c));  // bits <= c
-  const u64 ge = m >> c;                   // bits >= c, shifted
-  u32 d = 64;
-  if (le) d = c - (63u - (u32)__clzll((long long)le));
-  if (ge) d = min(d, (u32)__ffsll((long long)ge) - 1u);
-  return d * d;
-}
-
-struct EdtSmem {
-  u64* rowmask;             // [64] bit c of rowmask[r]: window pixel (r, c) belongs to the object
-  u64* topmask;             // [64] cone top
-  unsigned char* g;         // [66][64] row distances, one all-zero frame row above and below
-  unsigned short* rowbase;  // [64] number of object pixels in rows < r; later the per-row run descriptor
-  unsigned short* offs;     // [cap]
-};
-// slot layout of the EDT kernel (byte offsets from the slot start)
-constexpr u32 kEdtTopOff = 512, kEdtGOff = 1024, kEdtRowbaseOff = 1024 + (kSide + 2) * kSide, kEdtOffsOff = kEdtRowbaseOff + 128;
-
-__device__ __forceinline__ void shape_edt_warp(u32 n, int h, int w, u32 slot_off, u32 rmin, u32 cmin, bool want_conical,
-                                            const double* __restrict__ sqrt_tab, ShapeStats* __restrict__ dst) {
-  EdtSmem s;
-  s.rowmask = reinterpret_cast<u64*>(dyn + slot_off);
-  s.topmask = reinterpret_cast<u64*>(dyn + slot_off + kEdtTopOff);
-  s.g = dyn + slot_off + kEdtGOff;
-  s.rowbase = reinterpret_cast<unsigned short*>(dyn + slot_off + kEdtRowbaseOff);
-  s.offs = reinterpret_cast<unsigned short*>(dyn + slot_off + kEdtOffsOff);
-  const u32 lane = lane_id();
-  unsigned char* g = s.g;
-  // zero g (non-object pixels and the frame rows have row distance 0) and the cone-top mask
-  {
-    uint4* g4 = reinterpret_cast<uint4*>(g);
-    for (int k = lane; k < ((kSide + 2) * kSide) / 16; k += 32) g4[k] = make_uint4(0, 0, 0, 0);
-    s.topmask[lane] = 0; s.topmask[lane + 32] = 0;
-  }
-  __syncwarp();
-  // ---- row distances of object pixels: nearest zero to the left / right (beyond the window = zero) ----
-  // Rows that are one run [a, b] (the common case) take their distances from the run ends; rowbase[]
-  // is reused for the per-row run descriptor a | b << 6 | single << 12.
-  for (u32 r = lane; r < (u32)h; r += 32) {
-    const u64 m = s.rowmask[r];
-    u32 info = 0;
-    if (m) {
-      const u32 a = (u32)__ffsll((long long)m) - 1u, b = 63u - (u32)__clzll((long long)m);
-      const u64 run = m >> a;
-      info = a | (b << 6) | (((run & (run + 1ull)) == 0ull) ? 0x1000u : 0u);
-    }
-    s.rowbase[r] = (unsigned short)info;
-  }
-  __syncwarp();
-#pragma unroll 2
-  for (u32 i = lane; i < n; i += 32) {
-    const u32 k = s.offs[i];
-    const u32 r = k >> 6, c = k & 63u;
-    const u32 info = s.rowbase[r];
-    u32 dl, dr;
-    if (info & 0x1000u) {
-      dl = c - (info & 63u) + 1u;
-      dr = ((info >> 6) & 63u) - c + 1u;
-    } else {
-      u64 z = ~s.rowmask[r];
-      if (w < 64) z |= (~0ull << w);
-      const u64 le = z & (~0ull >> (63 - c));  // zeros at columns <= c (never c itself)
-      dl = le ? (c - (63u - (u32)__clzll((long long)le))) : (c + 1u);
-      const u64 ge = z >> c;
-      dr = ge ? ((u32)__ffsll((long long)ge) - 1u) : (64u - c);
-    }
-    g[((r + 1u) << 6) | c] = (unsigned char)min(dl, dr);
-  }
-  __syncwarp();
-  // ---- EDT 1: column pass with early exit, four pixels per lane in flight ----
-  // The frame rows (g = 0) bound every walk: a pixel's candidate at the frame row is d^2, so its
-  // loop stops before it could leave the buffer; finished pixels are predicated off.
-  u32 lmax = 0;
-  double s_nn = 0.0;
-  u64 at_lo = 0, at_hi = 0;  // bit (4 * group + u) <-> pixel i0 + 32 u of the lane's group attains lmax
-  {
-    u32 grp = 0;
-#pragma unroll 1
-    for (u32 i0 = lane; i0 < n; i0 += 128, ++grp) {
-      u32 kk[4], best[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const u32 i = i0 + 32u * u;
-        const u32 k = (i < n) ? (u32)s.offs[i] : 0u;
-        kk[u] = k + 64u;  // ((r + 1) << 6) | c
-        const u32 g0 = (i < n) ? (u32)g[kk[u]] : 0u;
-        best[u] = g0 * g0;
-      }
-      u32 d64 = 64, dd = 1, step = 3;  // d * 64, d * d, 2 d + 1
-      while ((dd < best[0]) | (dd < best[1]) | (dd < best[2]) | (dd < best[3])) {
-        // branch-free: a finished pixel re-reads its own cell (candidate g0^2 + dd >= best, a no-op)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const u32 off = (dd < best[u]) ? d64 : 0u;
-          const u32 ga = g[kk[u] - off], gb = g[kk[u] + off];
-          u32 m2;  // plain 32-bit min: the compiler otherwise packs the two bytes into a 16x2 min + unpack
-          asm("min.u32 %0, %1, %2;" : "=r"(m2) : "r"(ga), "r"(gb));
-          best[u] = min(best[u], m2 * m2 + dd);
-        }
-        dd += step; step += 2; d64 += 64;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + 32u * u >= n) break;
-        const u32 d2 = best[u];
-        const u64 bit = 1ull << ((4u * grp + u) & 63u);
-        if (d2 > lmax) { lmax = d2; at_lo = at_hi = 0; }
-        if (d2 == lmax) { if (grp < 16) at_lo |= bit; else at_hi |= bit; }
-        if (want_conical) s_nn += sqrt_tab[d2];
-      }
-    }
-  }
-  const u32 max_nn2 = __reduce_max_sync(kFull, lmax);
-  if (want_conical) {
-#pragma unroll
-    for (int k = 16; k > 0; k >>= 1) s_nn += __shfl_xor_sync(kFull, s_nn, k);
-  }
-  // ---- cone top: pixels with nn2 == max ----
-  if (lmax == max_nn2) {
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      u64 m = half ? at_hi : at_lo;
-      while (m) {
-        const u32 b = (u32)__ffsll((long long)m) - 1u + 64u * half;
-        m &= m - 1;
-        const u32 k = s.offs[lane + 128u * (b >> 2) + 32u * (b & 3u)];
-        atomicOr(reinterpret_cast<unsigned long long*>(&s.topmask[k >> 6]), 1ull << (k & 63u));
-      }
-    }
-  }
-  __syncwarp();
-  const u64 tm0 = s.topmask[lane], tm1 = s.topmask[lane + 32];
-  const u32 n_top = __reduce_add_sync(kFull, (u32)(__popcll(tm0) + __popcll(tm1)));
-  // ---- EDT 2: distance of every object pixel to the nearest cone-top pixel ----
-  u32 lmax2 = 0;
-  if (n_top <= 32) {
-    // each lane keeps one top pixel; extraction in row-major order
-    u32 my_top = 0;
-    {
-      u64 a = tm0, b = tm1;
-      u32 k = 0;
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        u64& cur = pass == 0 ? a : b;
-        u32 any = __ballot_sync(kFull, cur != 0);
-        while (any) {
-          const int src = __ffs(any) - 1;
-          const u64 mm = __shfl_sync(kFull, cur, src);
-          const u32 c = (u32)__ffsll((long long)mm) - 1u;
-          const u32 r = (u32)src + 32u * pass;
-          if (lane == k) my_top = (r << 6) | c;
-          ++k;
-          if ((int)lane == src) cur &= cur - 1;
-          any = __ballot_sync(kFull, cur != 0);
-        }
-      }
-    }
-    const u32 iters = (n + 31) / 32;  // uniform trip count: all lanes take part in the shuffles
-#pragma unroll 1
-    for (u32 it = 0; it < iters; ++it) {
-      const u32 i = it * 32 + lane;
-      const bool ok = i < n;
-      const u32 k = ok ? (u32)s.offs[i] : 0u;
-      const int r = (int)(k >> 6), c = (int)(k & 63u);
-      u32 best = kFull;
-#pragma unroll 1
-      for (u32 tt = 0; tt < n_top; ++tt) {
-        const u32 tp = __shfl_sync(kFull, my_top, tt);
-        const int dr = r - (int)(tp >> 6), dc = c - (int)(tp & 63u);
-        best = min(best, (u32)(dr * dr + dc * dc));
-      }
-      if (ok) lmax2 = max(lmax2, best);
-    }
-  } else {
-    // plateau: rows of the cone-top mask, nearest set bit per row
-#pragma unroll 1
-    for (u32 i = lane; i < n; i += 32) {
-      const u32 k = s.offs[i];
-      const u32 r = k >> 6, c = k & 63u;
-      u32 best = kFull;
-      for (int rr = 0; rr < h; ++rr) {
-        const u64 tm = s.topmask[rr];
-        if (tm == 0) continue;
-        const int dr = (int)r - rr;
-        best = min(best, nearest_bit_sq(tm, c) + (u32)(dr * dr));
-      }
-      lmax2 = max(lmax2, best);
-    }
-  }
-  const u32 max_dn2 = __reduce_max_sync(kFull, lmax2);
-  // ---- EDT 3: size of the cone top = distance of each top pixel to the rest of the object ----
-  double s_top = 0.0;
-  if (n_top == n) {
-    // `dn == 0` has no zero at all: SciPy measures to index (-1, 0) of the padded plane
-#pragma unroll 1
-    for (u32 i = lane; i < n; i += 32) {
-      const u32 k = s.offs[i];
-      const double dr = (double)rmin + (double)(k >> 6) + 2.0, dc = (double)cmin + (double)(k & 63u) + 1.0;
-      s_top += sqrt(dr * dr + dc * dc);
-    }
-#pragma unroll
-    for (int k = 16; k > 0; k >>= 1) s_top += __shfl_xor_sync(kFull, s_top, k);
-  } else {
-    // lanes over rows: q = object pixels that are not cone top
-    const u64 q0 = (lane < (u32)h) ? (s.rowmask[lane] & ~tm0) : 0ull;
-    const u64 q1 = (lane + 32 < (u32)h) ? (s.rowmask[lane + 32] & ~tm1) : 0ull;
-#pragma unroll 1
-    for (int r = 0; r < h; ++r) {
-      u64 tm = s.topmask[r];  // warp-uniform
-      while (tm) {
-        const u32 c = (u32)__ffsll((long long)tm) - 1u;
-        tm &= tm - 1;
-        u32 best = kFull;
-        const u32 d0 = nearest_bit_sq(q0, c);
-        const int dr0 = r - (int)lane;
-        if (d0 != kFull) best = d0 + (u32)(dr0 * dr0);
-        const u32 d1 = nearest_bit_sq(q1, c);
-        const int dr1 = r - (int)lane - 32;
-        if (d1 != kFull) best = min(best, d1 + (u32)(dr1 * dr1));
-        best = __reduce_min_sync(kFull, best);
-        s_top += sqrt((double)best);  // same value in every lane
-      }
-    }
-  }
-  if (lane == 0) {
-    ShapeStats out;
-    out.sum_nn = s_nn; out.sum_top = s_top; out.max_nn2 = max_nn2; out.max_dn2 = max_dn2;
-    *dst = out;
-  }
-  __syncwarp();
-}
-
-__global__ void __launch_bounds__(kEdtWarps * 32, 2)
-object_edt_warp(const Common cm, int want_conical, const double* __restrict__ sqrt_tab, ShapeStats* __restrict__ shape,
-                int* __restrict__ edt_list, u32* __restrict__ edt_count) {
-  const u32 lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  constexpr int kSmall = kEdtWarps - kLargeSlots;
-  constexpr u32 kFixed = 512 + 128 + (kSide + 2) * kSide + 512;  // rowmask, topmask, g, rowbase
-  constexpr u32 kSlotSmall = kFixed + kCapSmall * 2, kSlotLarge = kFixed + kCapLarge * 2;
-  const bool large_slot = warp >= kSmall;
-  const u32 slot_off = large_slot ? kSmall * kSlotSmall + (warp - kSmall) * kSlotLarge : warp * kSlotSmall;
-
-  Queue qu{cm.counters, cm.n_objects, large_slot ? 1 : 0};
-  int obj = qu.fetch();
-  if (obj >= cm.n_objects && qu.phase == 1) { qu.phase = 0; obj = qu.fetch(); }
-  int nxt = obj < cm.n_objects ? qu.fetch() : cm.n_objects;
-  while (obj < cm.n_objects) {
-    const u32 lo = qu.phase ? (u32)kCapSmall : 0u, hi = qu.phase ? (u32)kCapLarge : (u32)kCapSmall;
-    if (nxt < cm.n_objects) {
-      const abx_object_rec nr = cm.recs[nxt];
-      const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
-      const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
-      if (nr.n > lo && nr.n <= hi && nh <= kSide && nw <= kSide)
-        prefetch_rows(cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
-                      cm.lab_row_stride * 2, nh, (u32)nw * 2u);
-    }
-    const abx_object_rec rec = cm.recs[obj];
-    const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
-    const bool fits = rec.n > 0 && h <= kSide && w <= kSide;
-    if (qu.phase == 0 && rec.n == 0) {
-      if (lane == 0) { ShapeStats z; z.sum_nn = 0; z.sum_top = 0; z.max_nn2 = 0; z.max_dn2 = 0; shape[obj] = z; }
-    } else if (qu.phase == 0 && !fits) {
-      if (lane == 0) edt_list[atomicAdd(edt_count, 1u)] = obj;
-    } else if (fits && rec.n > lo && rec.n <= hi) {
-      const int p = find_plane(cm.plane_base, cm.n_planes, obj);
-      __syncwarp();
-      build_list<true>(cm.labels + (i64)p * cm.lab_plane_stride + (i64)rec.rmin * cm.lab_row_stride + rec.cmin,
-                       cm.lab_row_stride, (u32)(obj - cm.plane_base[p] + 1), h, w, slot_off + kEdtOffsOff, slot_off,
-                       slot_off + kEdtRowbaseOff);
-      shape_edt_warp(rec.n, h, w, slot_off, rec.rmin, rec.cmin, want_conical != 0, sqrt_tab, shape + obj);
-    }
-    obj = nxt;
-    nxt = obj < cm.n_objects ? qu.fetch() : cm.n_objects;
-    if (obj >= cm.n_objects && qu.phase == 1) {
-      qu.phase = 0;
-      obj = qu.fetch();
-      nxt = obj < cm.n_objects ? qu.fetch() : cm.n_objects;
-    }
-  }
-}
-
-__global__ void sqrt_table_kernel(double* tab, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) tab[i] = sqrt((double)i);
-}
-
 template <typename K>
 int set_smem(K kernel, size_t smem, bool* done) {
   int dev = 0;
@@ -788,15 +499,6 @@ int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& c
 
 }  // namespace
 
-// sqrt(d2) for every squared distance the first EDT of a 64 x 64 window can produce (exact: IEEE sqrt)
-int abx_sqrt_table_entries() { return (kSide / 2) * (kSide / 2) + 1; }  // row distances are <= 32
-
-int launch_sqrt_table(double* tab, cudaStream_t st) {
-  const int n = abx_sqrt_table_entries();
-  sqrt_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(tab, n);
-  return abx_check_cuda(cudaGetLastError(), "sqrt_table");
-}
-
 static Common make_common(const abx_extract_args* a, const Workspace& ws, int n_total) {
   Common cm;
   cm.labels = static_cast<const uint16_t*>(a->labels);
@@ -821,21 +523,4 @@ int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cud
   if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st, todo);
   if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st, todo);
   return ABX_OK;  // float pixels: every request belongs to object_float.cu
-}
-
-int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
-  if (!a->need_edt || a->n_objects == 0) return ABX_OK;
-  constexpr size_t fixed = 512 + 128 + (kSide + 2) * kSide + 512;
-  constexpr size_t smem = (kEdtWarps - kLargeSlots) * (fixed + kCapSmall * 2) + kLargeSlots * (fixed + kCapLarge * 2);
-  static thread_local bool done[64] = {false};
-  int rc = set_smem(object_edt_warp, smem, done);
-  if (rc) return rc;
-  if ((rc = launch_sqrt_table(ws.sqrt_tab, st))) return rc;
-  Common cm = make_common(a, ws, a->n_objects);
-  cm.counters = ws.list_counts + 4;
-  int grid = (a->n_objects + kEdtWarps - 1) / kEdtWarps;
-  if (grid > 148 * 2) grid = 148 * 2;
-  object_edt_warp<<<grid, kEdtWarps * 32, smem, st>>>(cm, (a->need_edt & 2) != 0, ws.sqrt_tab, ws.shape, ws.edt_list,
-                                                      ws.list_counts + 1);
-  return abx_check_cuda(cudaGetLastError(), "object_edt_warp");
 }

@@ -4,7 +4,7 @@
 import csv, os, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-filt = sys.argv[4] if len(sys.argv) > 4 else "object_warp.cu"
+filt = sys.argv[4] if len(sys.argv) > 4 else ".cu"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 cur_fun, cur_file, hdr = "", "", None
 lines = []

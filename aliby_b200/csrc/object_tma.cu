@@ -7,7 +7,7 @@
 // through the tile offset).
 //
 //   slot (16 KB per warp, 14 warps per CTA, one CTA per SM):
-//     hist u32[1024] | t u32[16] | mbarrier | flex 12 160 B = offs u16[n_pad] | window [h8][32 or 64] PX
+//     t u32[16] | mbarrier | flex 16 256 B = offs u16[n_pad] | window [h8][32 or 64] PX | hist u32[1024 or 512]
 //   window pitch 32 elements for objects at most 32 columns wide, 64 otherwise, so that a list entry
 //   k = (r << shift) | c IS the element index of its pixel inside the window: no address arithmetic.
 //   phase M  label window by TMA (boxes of 8 rows) -> compact list of k, padded to a multiple of 128 entries
@@ -31,8 +31,9 @@ namespace {
 
 constexpr int kTmaWarps = 14;
 constexpr u32 kTmaSlot = 16384;
-constexpr u32 kTOff = kBins * 4, kBarOff = kTOff + 64, kFlexOff = kBarOff + 64, kFlex = kTmaSlot - kFlexOff;
+constexpr u32 kTOff = 0, kBarOff = 64, kFlexOff = 128, kFlex = kTmaSlot - kFlexOff;  // byte offsets inside a slot
 constexpr int kBoxRows = 8;
+constexpr u32 kBigFirst = 1536;  // objects above this many pixels are processed first
 static_assert(kFlexOff % 128 == 0, "TMA destinations are 128-byte aligned");
 
 // phase M from the staged label window: compact list of k = (r << sh) | c, row-major, no atomics
@@ -63,12 +64,12 @@ __device__ __forceinline__ void build_list_smem(u32 lwin_off, u32 label, int h, 
 // phase S: one request on the staged window
 // ------------------------------------------------------------------------------------------------
 template <typename PX>
-__device__ __forceinline__ void request_stats_win(u32 n, u32 n_pad, u32 slot_off, u32 win_off, int sh, u32 feats,
-                                                  ChanStats* __restrict__ dst) {
+__device__ __forceinline__ void request_stats_win(u32 n, u32 n_pad, u32 slot_off, u32 win_off, u32 hist_off, u32 bins, int sh,
+                                                  u32 feats, ChanStats* __restrict__ dst) {
   constexpr int kShift = (sizeof(PX) == 1) ? 12 : 8;  // (x << kShift)^2 >> 32 == x^2 >> bits(PX)
   const unsigned short* offs = reinterpret_cast<const unsigned short*>(dyn + slot_off + kFlexOff);
   const PX* win = reinterpret_cast<const PX*>(dyn + win_off);
-  u32* hist = reinterpret_cast<u32*>(dyn + slot_off);
+  u32* hist = reinterpret_cast<u32*>(dyn + hist_off);
   u32* t = reinterpret_cast<u32*>(dyn + slot_off + kTOff);
   const u32 lane = lane_id();
   const u32 cmask = (1u << sh) - 1u;
@@ -131,7 +132,7 @@ __device__ __forceinline__ void request_stats_win(u32 n, u32 n_pad, u32 slot_off
     // ---- pass 2: range-adaptive histogram ----
     const u32 range = cs.vmax - vmin;
     int s0 = 0;
-    while ((range >> s0) >= (u32)kBins) ++s0;
+    while ((range >> s0) >= bins) ++s0;
     const u32 nb = (range >> s0) + 1;
     __syncwarp();
     hist_zero(hist, 32u * bins_per_lane(nb));
@@ -245,11 +246,22 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
   }
   __syncwarp();
   u32 parity = 0;
-  Queue qu{cm.counters, cm.n_total, 0};
-  int obj = qu.fetch();
-  int nxt = obj < cm.n_total ? qu.fetch() : cm.n_total;
-  while (obj < cm.n_total) {
+  // Longest first: the queue runs over the objects twice — items [0, n_total) take only the big objects, items
+  // [n_total, 2 n_total) the others — so that the launch does not end on one warp working through a 2 500-pixel cell.
+  const int n_items = 2 * cm.n_total;
+  Queue qu{cm.counters, n_items, 0};
+  int item = qu.fetch();
+  int nxt_item = item < n_items ? qu.fetch() : n_items;
+  while (item < n_items) {
+    const bool big_pass = item < cm.n_total;
+    const int obj = big_pass ? item : item - cm.n_total;
+    const int nxt = nxt_item < cm.n_total ? nxt_item : nxt_item - cm.n_total;  // == n_total past the end
     const abx_object_rec rec = cm.recs[obj];
+    if ((rec.n > kBigFirst) != big_pass) {  // not this pass
+      item = nxt_item;
+      nxt_item = item < n_items ? qu.fetch() : n_items;
+      continue;
+    }
     const bool is_bg = obj >= cm.n_objects;
     const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
     constexpr u32 kAlign = 16u / (u32)sizeof(PX);  // a TMA box starts at a 16-byte multiple of its innermost coordinate
@@ -280,12 +292,16 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
       }
     } else if (!cand) {
       if (lane == 0) stats_list[atomicAdd(stats_count, 1u)] = obj;  // hand over to the CTA-per-object kernel
-    } else if (need > 64u || 2u * n_pad + ((h8 << sh) << 1) > kFlex) {
-      // window-sized but too wide for a 64-column box at this alignment, or list + window above the flex area (about
-      // 1 % of typical cells): second list, filled from the back of the same buffer, for object_stats_warp
+    } else if (need > 64u || 2u * n_pad + ((h8 << sh) << 1) + 2048u > kFlex) {
+      // window-sized but too wide for a 64-column box at this alignment, or list + window + a 512-bin histogram above
+      // the flex area (a few cells per thousand): second list, filled from the back of the same buffer, for
+      // object_stats_warp
       if (lane == 0) stats_list[list_cap - 1 - (int)atomicAdd(warp_count, 1u)] = obj;
     } else {
-      const u32 win_off = slot_off + kFlexOff + 2u * n_pad;  // n_pad is a multiple of 128: 256-byte aligned
+      const u32 win_off = slot_off + kFlexOff + 2u * n_pad;  // n_pad is a multiple of 128: 128-byte aligned
+      // the histogram takes what is left behind the window: 1024 bins, or 512 for the largest objects
+      const u32 hist_off = win_off + ((h8 << sh) << 1);
+      const u32 bins = (slot_off + kTmaSlot - hist_off >= (u32)kBins * 4u) ? (u32)kBins : 512u;
       const u32 win_addr = smem_addr(dyn + win_off);
       const int cls = sh - 5;
       // ---- label window -> list ----
@@ -317,7 +333,7 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
         } else if (nxt < cm.n_objects) {
           const abx_object_rec nr = cm.recs[nxt];
           const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
-          if (nr.n > 0 && nh <= kSide && nw <= kSide) {
+          if (nr.n > 0 && nh <= kSide && nw <= kSide && (nr.n > kBigFirst) == (nxt_item < cm.n_total)) {
             const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
             prefetch_rows(cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
                           cm.lab_row_stride * 2, nh, (u32)nw * 2u);
@@ -337,11 +353,11 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
-        request_stats_win<PX>(rec.n, n_pad, slot_off, win_off + (s_px - s_lab) * (u32)sizeof(PX), sh, rq.features, chan + (i64)obj * n_requests + q);
+        request_stats_win<PX>(rec.n, n_pad, slot_off, win_off + (s_px - s_lab) * (u32)sizeof(PX), hist_off, bins, sh, rq.features, chan + (i64)obj * n_requests + q);
       }
     }
-    obj = nxt;
-    nxt = obj < cm.n_total ? qu.fetch() : cm.n_total;
+    item = nxt_item;
+    nxt_item = item < n_items ? qu.fetch() : n_items;
   }
 }
 

@@ -38,9 +38,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # stages of abx_extract bracketed by its stage events, and the kernels each one launches
-STAGES = ["label_scan", "object_stats_warp", "object_edt_warp", "large_objects", "finalize"]
+# object_stats: object_stats_tma (TMA-staged windows; object_stats_warp when the layout does not qualify);
+# object_edt: object_edt_grid, with the statistics of the few objects the TMA kernel left over on a helper stream next to it
+STAGES = ["label_scan", "object_stats", "object_edt", "large_objects", "finalize"]
 N_STAGES = len(STAGES)
-LAUNCHES_PER_STEP = 9  # init_records, label_scan, object_stats_warp, sqrt_table, object_edt_warp, object_stats, shape_edt x2, finalize
+LAUNCHES_PER_STEP = 10  # init_records, label_scan, object_stats_tma, sqrt_table, object_edt_grid, object_stats_warp (left-overs),
+# object_stats, shape_edt x2, finalize
 FIELD = (2160, 2160)
 N_CHANNELS = 5
 N_OBJECTS = 2000

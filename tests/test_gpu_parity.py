@@ -469,6 +469,44 @@ def test_fuzz_random_label_planes(ab, seed):
     against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_tma_staged_windows(ab, seed):
+    """Planes whose layout qualifies for the TMA kernels (16-byte aligned rows, Z = 1): windows of every width up to 64
+    at every column alignment (58..64 columns wide at a bad alignment = the left-over path), cells that fill the slot
+    (512-bin histogram), full-range values (refinement sweeps), rings and ellipses (rows with several runs), thin and
+    square blocks (cone tops of 1, a few, more than 32 pixels), uint8 and uint16."""
+    from aliby_b200 import synth
+
+    rng = np.random.default_rng(7000 + seed)
+    H, W = int(rng.integers(64, 170)), 16 * int(rng.integers(4, 20))
+    n_tiles = int(rng.integers(1, 4))
+    dtype = np.uint8 if seed % 2 else np.uint16
+    top = np.iinfo(dtype).max
+    masks = []
+    for _ in range(n_tiles):
+        lab = synth.ellipse_labels(rng, (H, W), int(rng.integers(0, 10)), semi_axes=(3, 31)).astype(np.uint16)
+        next_id = int(lab.max()) + 1
+        for _ in range(int(rng.integers(2, 10))):
+            h, w = int(rng.integers(1, 65)), int(rng.choice([1, 2, 3, 7, 30, 33, 57, 58, 60, 63, 64, int(rng.integers(1, 65))]))
+            h, w = min(h, H), min(w, W)
+            r, c = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+            lab[r : r + h, c : c + w] = next_id
+            if h > 8 and w > 8 and rng.random() < 0.4:  # ring
+                lab[r + 3 : r + h - 3, c + 3 : c + w - 3] = 0
+            next_id += int(rng.integers(1, 3))
+        masks.append(lab)
+    if seed % 3 == 0:   # noise around a per-pixel level: narrow ranges, one-pass histogram
+        base = rng.integers(0, max(2, top // 2), size=(n_tiles, 3, 1, 1, 1))
+        pixels = np.clip(base + rng.poisson(40, size=(n_tiles, 3, 1, H, W)), 0, top).astype(dtype)
+    else:
+        pixels = rng.integers(0, top + 1, size=(n_tiles, 3, 1, H, W)).astype(dtype)
+    tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume",
+                              "min_maj_approximation"]},
+            0: {"max": INTENSITY + ["max", "min"]},
+            2: {"add": ["mean", "median", "total", "total_squared", "max2p5pc", "max5px_median", "std", "moment_of_inertia"]}}
+    against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)
+
+
 def test_out_of_frame_tiles_golden_and_extraction(ab):
     """if_out_of_bounds_pad (tiler.py:601-650): median-padded and NaN tiles, against the golden crops written by the
     real reference, then extraction through padded / NaN tiles against the oracle on the reference-shaped crop."""

@@ -22,8 +22,8 @@ PROF = os.path.join(ROOT, "profiles")
 rep = os.path.join(OUT, f"prof_{tag}.ncu-rep")
 launches = os.path.join(OUT, f"launches_{tag}.csv")
 bench = os.path.join(OUT, f"bench_{tag}.json")
-STAGE_OF = {"label_scan_kernel": "label_scan", "object_stats_warp": "object_stats_warp", "object_edt_warp": "object_edt_warp",
-            "finalize_kernel": "finalize"}
+STAGE_OF = {"label_scan_kernel": "label_scan", "object_stats_tma": "object_stats", "object_stats_warp": "object_stats",
+            "object_edt_grid": "object_edt", "finalize_kernel": "finalize"}
 
 md = [f"# ncu summary {tag}", "",
       "Produced by `tools/gpu_profile.sh` on a B200 (sm_100a) and `tools/make_profile_summary.py`; command profiled: "

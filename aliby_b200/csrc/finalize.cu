@@ -66,10 +66,14 @@ __global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const C
                                 int n_planes, int n_objects, const abx_request* __restrict__ requests,
                                 int n_requests, const abx_column* __restrict__ columns, int n_columns,
                                 int pixel_dtype, double* __restrict__ table) {
-  const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (i64)n_objects * n_columns) return;
-  const int obj = (int)(idx / n_columns);
-  const int col = (int)(idx - (i64)obj * n_columns);
+  // blockIdx.y walks the objects in chunks of 65 536 so that the cell index inside a chunk fits 32 bits (a 64-bit
+  // division per cell was a quarter of this kernel)
+  const u32 local = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 lobj = local / (u32)n_columns;
+  const int obj = (int)(blockIdx.y * 65536u + lobj);
+  if (lobj >= 65536u || obj >= n_objects) return;
+  const int col = (int)(local - lobj * (u32)n_columns);
+  const i64 idx = (i64)obj * n_columns + col;
   const abx_column cd = columns[col];
   const abx_object_rec r = recs[obj];
   const double n = (double)r.n;
@@ -153,8 +157,11 @@ int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t
   const i64 cells = (i64)a->n_objects * a->n_columns;
   if (cells == 0) return ABX_OK;
   const int threads = 256;
-  const i64 blocks = (cells + threads - 1) / threads;
-  finalize_kernel<<<(unsigned)blocks, threads, 0, st>>>(ws.recs, ws.chan, ws.shape, a->plane_base, a->n_planes,
+  if (a->n_columns > 32768) return abx_set_error(ABX_ERR_INVALID, "more than 32768 table columns");
+  const int chunks = (a->n_objects + 65535) / 65536;
+  const i64 chunk_cells = (i64)(a->n_objects < 65536 ? a->n_objects : 65536) * a->n_columns;
+  const dim3 blocks((unsigned)((chunk_cells + threads - 1) / threads), (unsigned)chunks);
+  finalize_kernel<<<blocks, threads, 0, st>>>(ws.recs, ws.chan, ws.shape, a->plane_base, a->n_planes,
                                                        a->n_objects, a->requests, a->n_requests, a->columns,
                                                        a->n_columns, a->pixel_dtype, a->table);
   return abx_check_cuda(cudaGetLastError(), "finalize");

@@ -106,18 +106,18 @@ __device__ __forceinline__ void shape_object(const abx_object_rec& rec, int p, u
   topmask[lane + 32] = 0;
   __syncwarp();
   // ---- phase R: squared row distances, two columns per lane ----
-  // lanes over rows first: the run ends of each row, a | b << 8 | kind << 16 (kind 0 empty, 1 one run, 2 several)
+  // lanes over rows first: the run ends of each row, a | b << 8 | several-runs << 16 (an empty row: a = 64, b = 0)
   u32* rowinfo = reinterpret_cast<u32*>(dyn + slot_off + kInfoOff);
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int r = (int)lane + 32 * k;
     if (r < h) {
       const u64 m = rowmask[r];
-      u32 info = 0;
+      u32 info = 64u;
       if (m) {
         const u32 a = (u32)__ffsll((long long)m) - 1u, b = 63u - (u32)__clzll((long long)m);
         const u64 run = m >> a;
-        info = a | (b << 8) | (((run & (run + 1ull)) == 0ull) ? 0x10000u : 0x20000u);
+        info = a | (b << 8) | (((run & (run + 1ull)) == 0ull) ? 0u : 0x10000u);
       }
       rowinfo[r] = info;
     }
@@ -127,16 +127,14 @@ __device__ __forceinline__ void shape_object(const abx_object_rec& rec, int p, u
 #pragma unroll 4
   for (int r = 0; r < h; ++r) {
     const u32 info = rowinfo[r];  // warp-uniform
-    const u32 a = info & 0xFFu, b = (info >> 8) & 0xFFu;
-    u32 g0 = 0, g1 = 0;
-    if (c0 >= a && c0 <= b) g0 = min(c0 - a, b - c0) + 1u;  // one run [a, b]: distances from its ends
-    if (c0 + 1u >= a && c0 + 1u <= b) g1 = min(c0 + 1u - a, b - c0 - 1u) + 1u;
-    if (info & 0x20000u) {  // several runs (rare)
+    const int a = (int)(info & 0xFFu), b = (int)((info >> 8) & 0xFFu);
+    // one run [a, b]: min(c - a, b - c) + 1 inside it, <= 0 outside
+    u32 g0 = (u32)max(min((int)c0 - a, b - (int)c0) + 1, 0);
+    u32 g1 = (u32)max(min((int)c0 + 1 - a, b - (int)c0 - 1) + 1, 0);
+    if (info & 0x10000u) {  // several runs (rare)
       const u64 m = rowmask[r];
       g0 = ((m >> c0) & 1ull) ? row_distance(m, c0) : 0u;
       g1 = ((m >> (c0 + 1u)) & 1ull) ? row_distance(m, c0 + 1u) : 0u;
-    } else if ((info & 0x10000u) == 0u) {
-      g0 = g1 = 0;
     }
     *reinterpret_cast<u32*>(dyn + g_off + ((u32)r + kMargin) * 128u + 4u * lane) = (g0 * g0) | ((g1 * g1) << 16);
   }
@@ -286,20 +284,36 @@ __device__ __forceinline__ void shape_object(const abx_object_rec& rec, int p, u
         if (pair & 2u) lmax2 = max(lmax2, best >> 16);
       }
     } else {
+      // 5 .. 32 tops: four at a time as above, the per-row minima of the earlier chunks wait in the grid (free by now)
 #pragma unroll 1
-      for (int r = 0; r < h; ++r) {
-        const u64 m = rowmask[r];
-        if (m == 0) continue;
-        u32 best = kFull;
-#pragma unroll 1
-        for (u32 t = 0; t < n_top; ++t) {
-          const u32 tp = __shfl_sync(kFull, my_top, t);
-          const int dr = r - (int)(tp >> 6), d = (int)c0 - (int)(tp & 63u);
-          best = __viaddmin_u16x2((u32)(d * d) | ((u32)((d + 1) * (d + 1)) << 16), (u32)(dr * dr) * 0x00010001u, best);
+      for (u32 t0 = 0; t0 < n_top; t0 += 4) {
+        u32 pc[4];
+        int tr[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const u32 tp = __shfl_sync(kFull, my_top, t0 + (u32)t < n_top ? t0 + (u32)t : t0);  // repeats fill the chunk
+          tr[t] = (int)(tp >> 6);
+          const int d = (int)c0 - (int)(tp & 63u);
+          pc[t] = (u32)(d * d) | ((u32)((d + 1) * (d + 1)) << 16);
         }
-        const u32 pair = (u32)(m >> c0) & 3u;
-        if (pair & 1u) lmax2 = max(lmax2, best & 0xFFFFu);
-        if (pair & 2u) lmax2 = max(lmax2, best >> 16);
+        const bool last = t0 + 4u >= n_top;
+#pragma unroll 2
+        for (int r = 0; r < h; ++r) {
+          u32* cell = reinterpret_cast<u32*>(dyn + g_off + ((u32)r + kMargin) * 128u + 4u * lane);
+          u32 best = t0 ? *cell : kFull;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int dr = r - tr[t];
+            best = __viaddmin_u16x2(pc[t], (u32)(dr * dr) * 0x00010001u, best);
+          }
+          if (last) {
+            const u32 pair = (u32)(rowmask[r] >> c0) & 3u;
+            if (pair & 1u) lmax2 = max(lmax2, best & 0xFFFFu);
+            if (pair & 2u) lmax2 = max(lmax2, best >> 16);
+          } else {
+            *cell = best;
+          }
+        }
       }
     }
   } else {

@@ -317,22 +317,36 @@ __device__ __forceinline__ void shape_object(const abx_object_rec& rec, int p, u
       }
     }
   } else {
-    // plateau: rows of the cone-top mask, nearest set bit per row
+    // plateau (more than 32 top pixels, e.g. a cell cut straight by the image border): per row that holds top pixels,
+    // the squared distance of every column to the row's nearest top pixel — packed pairs, parked in the grid (free by
+    // now) — then one packed add-min per (object row, top row)
+    u32* toprow = reinterpret_cast<u32*>(dyn + slot_off + kInfoOff);  // the run ends are no longer needed
+    u32 rows0 = __ballot_sync(kFull, tm0 != 0), rows1 = __ballot_sync(kFull, tm1 != 0);
+    int nt = 0;
+#pragma unroll 1
+    while (rows0 | rows1) {
+      int r;
+      if (rows0) { r = __ffs(rows0) - 1; rows0 &= rows0 - 1; }
+      else { r = 32 + __ffs(rows1) - 1; rows1 &= rows1 - 1; }
+      const u64 tm = topmask[r];  // warp-uniform
+      *reinterpret_cast<u32*>(dyn + g_off + ((u32)nt + kMargin) * 128u + 4u * lane) =
+          nearest_bit_sq(tm, c0) | (nearest_bit_sq(tm, c0 + 1u) << 16);
+      if (lane == 0) toprow[nt] = (u32)r;
+      ++nt;
+    }
+    __syncwarp();
 #pragma unroll 1
     for (int r = 0; r < h; ++r) {
-      const u64 m = rowmask[r];
-      const u32 pair = (u32)(m >> c0) & 3u;
-      u32 best0 = kFull, best1 = kFull;
-#pragma unroll 1
-      for (int rr = 0; rr < h; ++rr) {
-        const u64 tm = topmask[rr];
-        if (tm == 0) continue;
-        const u32 dr2 = (u32)((r - rr) * (r - rr));
-        best0 = min(best0, nearest_bit_sq(tm, c0) + dr2);
-        best1 = min(best1, nearest_bit_sq(tm, c0 + 1u) + dr2);
+      const u32 pair = (u32)(rowmask[r] >> c0) & 3u;
+      u32 best = kFull;
+#pragma unroll 2
+      for (int j = 0; j < nt; ++j) {
+        const int dr = r - (int)toprow[j];
+        best = __viaddmin_u16x2(*reinterpret_cast<const u32*>(dyn + g_off + ((u32)j + kMargin) * 128u + 4u * lane),
+                                (u32)(dr * dr) * 0x00010001u, best);
       }
-      if (pair & 1u) lmax2 = max(lmax2, best0);
-      if (pair & 2u) lmax2 = max(lmax2, best1);
+      if (pair & 1u) lmax2 = max(lmax2, best & 0xFFFFu);
+      if (pair & 2u) lmax2 = max(lmax2, best >> 16);
     }
   }
   const u32 max_dn2 = __reduce_max_sync(kFull, lmax2);

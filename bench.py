@@ -96,7 +96,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 os.environ.get("ABX_CLOCK_PERIOD_MS", "20")],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -304,7 +305,7 @@ def ours(args):
 
     # ---- synthetic batch (distinct per rank) ----
     workers = max(1, (os.cpu_count() or 1) // max(1, world))
-    px_np, lab_np = make_fields(F, 5000 + 100 * rank, workers=min(F, workers))
+    px_np, lab_np = make_fields(F, int(os.environ.get("ABX_SEED_BASE", "5000")) + 100 * rank, workers=min(F, workers))
     n_labels = lab_np.reshape(F, -1).max(axis=1).astype(np.int64)
     n_objects = int(n_labels.sum())
     H, W = FIELD
@@ -349,8 +350,10 @@ def ours(args):
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
+    h0 = time.perf_counter()
     for k in range(args.steps):
         step(stage_ev[k])
+    host_ms = 1e3 * (time.perf_counter() - h0) / args.steps  # host time to enqueue one step (no GPU wait inside)
     t_end.record()
     barrier()
     ms_total = t_start.elapsed_time(t_end)
@@ -388,6 +391,12 @@ def ours(args):
     clocks["window"] = "warm-up + timed steps + e2e leg"
 
     # ---- reduce over ranks: max time, sum of units ----
+    per_rank = [ms_total / args.steps]
+    if dist is not None:  # every rank's own step time and stage sum, for the record (the reported time is their maximum)
+        mine = torch.tensor([ms_total / args.steps, float(stage_ms.sum())], dtype=torch.float64, device=device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(x[0]), 4), round(float(x[1]), 4)] for x in allr]
     t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=device)
     units = torch.tensor([float(n_objects * n_feat_cols), float(algo_bytes)], dtype=torch.float64, device=device)
     if dist is not None:
@@ -440,6 +449,9 @@ def ours(args):
                 "api": "aliby_b200.extract.extract_table(tree, masks, pixels) with pinned host arrays",
             },
             "gpu_launches": args.steps * LAUNCHES_PER_STEP,
+            "host_enqueue_ms_per_step": host_ms,
+            "ms_per_step_by_rank": per_rank,  # N > 1: [step time, sum of the stage times] of every rank
+            "host_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -7,7 +7,8 @@ from aliby_b200 import engine, _native as nat
 
 lib = nat.lib()
 F = int(os.environ.get("F", 8))
-px, lab = bench.make_fields(F, 5000)
+import os
+px, lab = bench.make_fields(F, int(os.environ.get("ABX_SEED_BASE", "5000")))
 dev = torch.device("cuda")
 pxd = torch.from_numpy(px).to(dev); labd = torch.from_numpy(lab).to(dev)
 nl = lab.reshape(F, -1).max(axis=1).astype(np.int64)

@@ -61,21 +61,12 @@ __device__ double float_metric(const FloatStats& f, int metric, u32 n_px, int pi
   }
 }
 
-__global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __restrict__ chan,
-                                const ShapeStats* __restrict__ shape, const int32_t* __restrict__ plane_base,
-                                int n_planes, int n_objects, const abx_request* __restrict__ requests,
-                                int n_requests, const abx_column* __restrict__ columns, int n_columns,
-                                int pixel_dtype, double* __restrict__ table) {
-  // blockIdx.y walks the objects in chunks of 65 536 so that the cell index inside a chunk fits 32 bits (a 64-bit
-  // division per cell was a quarter of this kernel)
-  const u32 local = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32 lobj = local / (u32)n_columns;
-  const int obj = (int)(blockIdx.y * 65536u + lobj);
-  if (lobj >= 65536u || obj >= n_objects) return;
-  const int col = (int)(local - lobj * (u32)n_columns);
-  const i64 idx = (i64)obj * n_columns + col;
+__device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const abx_object_rec* __restrict__ recs,
+                                const ChanStats* __restrict__ chan, const ShapeStats* __restrict__ shape,
+                                const int32_t* __restrict__ plane_base, int n_planes, int n_objects,
+                                const abx_request* __restrict__ requests, int n_requests,
+                                const abx_column* __restrict__ columns, int pixel_dtype) {
   const abx_column cd = columns[col];
-  const abx_object_rec r = recs[obj];
   const double n = (double)r.n;
   const double kNaN = nan("");
   double v = kNaN;
@@ -148,7 +139,42 @@ __global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const C
       case ABX_M_RATIO: default: break;  // cell.py:268-279: NaN for any 2-D image
     }
   }
-  table[idx] = v;
+  return v;
+}
+
+// Thread mapping: a CTA of 256 threads takes 32 objects; lane <-> object, warp w walks the columns w, w + 8, ... — so a
+// warp evaluates ONE metric for 32 objects (no divergence in the switch below; one column per lane cost every warp the
+// union of all metric bodies).  Results go through a shared-memory tile so that the table rows are written coalesced.
+constexpr int kFinObjects = 32, kFinWarps = 8, kFinColChunk = 64;
+
+__global__ void __launch_bounds__(kFinWarps * 32)
+finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __restrict__ chan,
+                                const ShapeStats* __restrict__ shape, const int32_t* __restrict__ plane_base,
+                                int n_planes, int n_objects, const abx_request* __restrict__ requests,
+                                int n_requests, const abx_column* __restrict__ columns, int n_columns,
+                                int pixel_dtype, double* __restrict__ table) {
+  __shared__ double tile[kFinObjects][kFinColChunk + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int obj0 = blockIdx.x * kFinObjects;
+  const int obj = obj0 + lane;
+  const bool live = obj < n_objects;
+  const abx_object_rec r = recs[live ? obj : 0];
+  for (int cbase = 0; cbase < n_columns; cbase += kFinColChunk) {
+    const int ncol = min(kFinColChunk, n_columns - cbase);
+    for (int cl = warp; cl < ncol; cl += kFinWarps) {
+      const int col = cbase + cl;
+      tile[lane][cl] = live ? finalize_cell(r, obj, col, recs, chan, shape, plane_base, n_planes, n_objects, requests,
+                                            n_requests, columns, pixel_dtype)
+                            : 0.0;
+    }
+    __syncthreads();
+    // coalesced write-out: consecutive threads -> consecutive columns of one object
+    for (int e = threadIdx.x; e < kFinObjects * ncol; e += kFinWarps * 32) {
+      const int o = e / ncol, c = e - o * ncol;
+      if (obj0 + o < n_objects) table[(i64)(obj0 + o) * n_columns + cbase + c] = tile[o][c];
+    }
+    __syncthreads();
+  }
 }
 
 }  // namespace
@@ -156,13 +182,9 @@ __global__ void finalize_kernel(const abx_object_rec* __restrict__ recs, const C
 int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
   const i64 cells = (i64)a->n_objects * a->n_columns;
   if (cells == 0) return ABX_OK;
-  const int threads = 256;
-  if (a->n_columns > 32768) return abx_set_error(ABX_ERR_INVALID, "more than 32768 table columns");
-  const int chunks = (a->n_objects + 65535) / 65536;
-  const i64 chunk_cells = (i64)(a->n_objects < 65536 ? a->n_objects : 65536) * a->n_columns;
-  const dim3 blocks((unsigned)((chunk_cells + threads - 1) / threads), (unsigned)chunks);
-  finalize_kernel<<<blocks, threads, 0, st>>>(ws.recs, ws.chan, ws.shape, a->plane_base, a->n_planes,
-                                                       a->n_objects, a->requests, a->n_requests, a->columns,
-                                                       a->n_columns, a->pixel_dtype, a->table);
+  const unsigned blocks = (unsigned)((a->n_objects + kFinObjects - 1) / kFinObjects);
+  finalize_kernel<<<blocks, kFinWarps * 32, 0, st>>>(ws.recs, ws.chan, ws.shape, a->plane_base, a->n_planes,
+                                                   a->n_objects, a->requests, a->n_requests, a->columns,
+                                                   a->n_columns, a->pixel_dtype, a->table);
   return abx_check_cuda(cudaGetLastError(), "finalize");
 }

@@ -507,6 +507,21 @@ def test_fuzz_tma_staged_windows(ab, seed):
     against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)
 
 
+def test_border_cut_cell_long_cone_top(ab):
+    """A cell cut straight by the image border: the EDT maximum is a line of 34 pixels (> 32: the plateau path of the
+    shape kernel, which once took 0.3 ms on one warp and set the step time of a whole batch)."""
+    yy, xx = np.mgrid[0:96, 0:128]
+    labels = np.zeros((96, 128), np.uint16)
+    labels[14:70, 0:10] = 1                                               # a 56 x 10 cell on the left border ...
+    labels[14:20, 6:10] = 0; labels[64:70, 5:10] = 0                      # ... with trimmed corners
+    labels[((yy - 70) / 6.0) ** 2 + ((xx - 100) / 27.0) ** 2 <= 1.0] = 2  # flat ellipse: a horizontal line of maxima
+    labels[10:14, 40:104] = 3                                             # 4 x 64 bar
+    rng = np.random.default_rng(5)
+    pixels = rng.integers(0, 4000, size=(1, 1, 1, 96, 128)).astype(np.uint16)
+    tree = {"None": {"None": SHAPE}, 0: {"max": INTENSITY}}
+    against_oracle(ab, tree, labels, pixels)
+
+
 def test_out_of_frame_tiles_golden_and_extraction(ab):
     """if_out_of_bounds_pad (tiler.py:601-650): median-padded and NaN tiles, against the golden crops written by the
     real reference, then extraction through padded / NaN tiles against the oracle on the reference-shaped crop."""

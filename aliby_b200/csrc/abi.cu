@@ -59,11 +59,22 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   off = align_up(off + (a->need_edt ? (size_t)a->n_objects * sizeof(ShapeStats) : 0));
   ws->err = reinterpret_cast<u32*>(b + off);
   ws->list_counts = ws->err + 1;
-  off = align_up(off + 8 * sizeof(u32));
+  off = align_up(off + 12 * sizeof(u32));
   ws->sqrt_tab = reinterpret_cast<double*>(b + off);
   off = align_up(off + (a->need_edt ? (size_t)abx_sqrt_table_entries() * sizeof(double) : 0));
   ws->bg_hist = reinterpret_cast<u32*>(b + off);
   off = align_up(off + abx_big_background_bytes(a));
+  ws->zplanes = b + off;
+  off = align_up(off + abx_zreduce_bytes(a));
+  const bool zr = abx_zreduce_ok(a);
+  ws->req_tma = reinterpret_cast<abx_request*>(b + off);
+  off = align_up(off + (zr ? (size_t)a->n_requests * sizeof(abx_request) : 0));
+  ws->req_rest = reinterpret_cast<abx_request*>(b + off);
+  off = align_up(off + (zr ? (size_t)a->n_requests * sizeof(abx_request) : 0));
+  ws->ztile_offset = reinterpret_cast<i64*>(b + off);
+  off = align_up(off + (zr ? (size_t)a->n_tiles * sizeof(i64) : 0));
+  ws->zflags = reinterpret_cast<u32*>(b + off);
+  off = align_up(off + (zr ? 16 : 0));
   ws->stats_list = reinterpret_cast<int*>(b + off);
   off = align_up(off + n_rec * sizeof(int));
   ws->edt_list = reinterpret_cast<int*>(b + off);
@@ -111,8 +122,8 @@ extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* reco
   int rc = abx_validate(args);
   if (rc) return rc;
   if (!records) return abx_set_error(ABX_ERR_INVALID, "records is NULL");
-  if (!args->workspace || args->workspace_bytes < 8 * sizeof(u32))
-    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 32-byte workspace for its flags");
+  if (!args->workspace || args->workspace_bytes < 16 * sizeof(u32))
+    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 64-byte workspace for its flags");
   return launch_label_scan(args, records, static_cast<u32*>(args->workspace), static_cast<cudaStream_t>(args->stream));
 }
 
@@ -155,10 +166,26 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   mark(0);
   if ((rc = launch_label_scan(args, ws.recs, ws.err, st))) return rc;
   mark(1);
+  // Z stacks: every requested (tile, channel) stack is max-reduced once, streaming, into planes of the workspace, and
+  // the window-sized objects then see a Z = 1 problem on those planes (zreduce.cu); `add` requests keep the stack.
+  abx_extract_args red = *args;  // what the per-object statistics kernels of window-sized objects work on
+  const bool zred = abx_zreduce_ok(args);
+  if (zred) {
+    if ((rc = launch_zreduce(args, ws, st))) return rc;
+    red.pixels = ws.zplanes;
+    red.tile_offset = reinterpret_cast<const int64_t*>(ws.ztile_offset);
+    red.requests = ws.req_tma;
+    red.C = args->n_requests;
+    red.Z = 1;
+    red.chan_stride = red.z_stride = (i64)args->H * args->W;
+    red.row_stride = args->W;
+    red.pixel_elems = (i64)args->n_tiles * args->n_requests * args->H * args->W;
+  }
   // objects with a window <= 64 x 64: TMA-staged windows when the layout allows, plain gathers otherwise
   bool tma = false;
-  if ((rc = launch_object_stats_tma(args, ws, st, false, &tma))) return rc;
-  if (!tma && (rc = launch_object_stats_warp(args, ws, st, false))) return rc;
+  if ((rc = launch_object_stats_tma(&red, ws, st, false, &tma))) return rc;
+  if (!tma && (rc = launch_object_stats_warp(&red, ws, st, false))) return rc;
+  if (zred && (rc = launch_object_stats_rest(args, ws, st))) return rc;  // the Z-add requests, from the stack itself
   mark(2);
   // The few objects the TMA kernel left over (about 1 %) go through the gather kernel on a helper stream, one warp per
   // CTA, next to the shape kernel: their cost is one warp's latency, which hides behind the EDT launch.  (Running
@@ -166,12 +193,12 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   // against 0.27 + 0.25 ms one after the other.)
   const bool edt = args->need_edt && args->n_objects > 0;
   Helper* hp = (tma && edt) ? helper_stream() : nullptr;
-  if (tma && !hp && (rc = launch_object_stats_warp(args, ws, st, true))) return rc;
+  if (tma && !hp && (rc = launch_object_stats_warp(&red, ws, st, true))) return rc;
   if (hp) cudaEventRecord(hp->fork, st);
   if ((rc = launch_object_edt_warp(args, ws, st))) return rc;  // first: its CTAs take their two places per SM
   if (hp) {
     cudaStreamWaitEvent(hp->stream, hp->fork, 0);
-    if ((rc = launch_object_stats_warp(args, ws, hp->stream, true))) return rc;
+    if ((rc = launch_object_stats_warp(&red, ws, hp->stream, true))) return rc;
     cudaEventRecord(hp->join, hp->stream);
     cudaStreamWaitEvent(st, hp->join, 0);
   }

@@ -61,6 +61,12 @@ struct Workspace {
                      // second list of object_stats_tma (back of stats_list), [4..5] EDT work counters, [6] counter of that list
   double* sqrt_tab;  // sqrt(d2) of every squared distance the warp EDT can produce
   u32* bg_hist;      // [n_planes][n_requests][65536] value histograms of large-plane backgrounds (background.cu)
+  // Z stacks reduced up front (zreduce.cu); all null / unused when abx_zreduce_ok() is false
+  void* zplanes;            // [n_tiles][n_requests][H][W] pixel dtype: the Z-max plane of request q of every tile
+  abx_request* req_tma;     // [n_requests] requests as the kernels on the reduced planes see them
+  abx_request* req_rest;    // [n_requests] requests as the gather pass over the original stack sees them
+  i64* ztile_offset;        // [n_tiles] tile offsets inside zplanes
+  u32* zflags;              // [0]: some request is left to the gather pass (Z-add)
   size_t total;
 };
 
@@ -81,6 +87,10 @@ int launch_big_background(const abx_extract_args* a, const Workspace& ws, cudaSt
 bool abx_big_background(const abx_extract_args* a);
 size_t abx_big_background_bytes(const abx_extract_args* a);
 int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+bool abx_zreduce_ok(const abx_extract_args* a);
+size_t abx_zreduce_bytes(const abx_extract_args* a);
+int launch_zreduce(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_object_stats_rest(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int abx_sqrt_table_entries();
 
 constexpr int kEdtLargeCtas = 8;           // CTAs that own a whole-plane EDT scratch slot

@@ -22,7 +22,7 @@ constexpr int kScanWarps = kScanThreads / 32;
 
 __global__ void init_records_kernel(abx_object_rec* recs, int n_objects, int n_planes, int H, int W, u32* err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 8) err[i] = 0;  // error flags, the two work-list lengths, the two object counters
+  if (i < 12) err[i] = 0;  // error flags, the work-list lengths, the work counters of the per-object kernels
   if (i < n_objects + n_planes) {
     abx_object_rec r;
     r.sum_row = 0; r.sum_col = 0; r.n = 0;

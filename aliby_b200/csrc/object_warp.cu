@@ -389,7 +389,10 @@ __global__ void __launch_bounds__(kStatsWarps * 32, 2)
 object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __restrict__ tile_offset, i64 chan_stride,
                   i64 z_stride, i64 px_row_stride, int Z, const abx_request* __restrict__ requests, int n_requests,
                   ChanStats* __restrict__ chan, int* __restrict__ stats_list, u32* __restrict__ stats_count,
-                  const u32* __restrict__ todo_count, int list_cap) {
+                  const u32* __restrict__ todo_count, int list_cap, const u32* __restrict__ gate, int bookkeeping) {
+  // gate: the launch has nothing to do when *gate == 0 (zreduce.cu: no request left to the stack).  bookkeeping = 0:
+  // another kernel already zero-filled the absent labels and handed the large objects over.
+  if (gate != nullptr && *gate == 0u) return;
   // Two modes.  todo_count == nullptr: every object of the launch, all its requests (the path for layouts TMA cannot
   // address).  Otherwise: the objects object_stats_tma could not take (stored from the back of stats_list), one work
   // item per (object, request) so that the few of them finish in the time of one request.
@@ -411,14 +414,14 @@ object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __r
     const bool is_bg = obj >= cm.n_objects;
     const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
     if (rec.n == 0) {  // absent label (or empty background): zero records -> NaN in finalize
-      for (int q = lane; q < n_requests; q += 32) {
+      for (int q = lane; bookkeeping && q < n_requests; q += 32) {
         ChanStats z;
         z.sum = z.sumsq = z.wrapsq = z.m10 = z.m01 = z.m20 = z.m02 = z.top2p5_sum = z.top5_sum = 0;
         z.vmin = z.vmax = z.med_lo = z.med_hi = 0;
         chan[(i64)obj * n_requests + q] = z;
       }
     } else if (is_bg || h > kSide || w > kSide) {  // hand over to the CTA-per-object kernel
-      if (lane == 0) stats_list[atomicAdd(stats_count, 1u)] = obj;
+      if (bookkeeping && lane == 0) stats_list[atomicAdd(stats_count, 1u)] = obj;
     } else {
       const int p = find_plane(cm.plane_base, cm.n_planes, obj);
       __syncwarp();
@@ -480,7 +483,8 @@ int set_smem(K kernel, size_t smem, bool* done) {
 }
 
 template <typename PX>
-int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& cm, cudaStream_t st, bool todo) {
+int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& cm, cudaStream_t st, bool todo,
+                 const abx_request* requests, const u32* gate, int bookkeeping) {
   constexpr size_t smem = (size_t)kStatsWarps * kStatsSlot;
   static thread_local bool done[64] = {false};
   int rc = set_smem(object_stats_warp<PX>, smem, done);
@@ -492,8 +496,8 @@ int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& c
   if (todo) grid = 148;
   object_stats_warp<PX><<<grid, todo ? 32 : kStatsWarps * 32, todo ? (size_t)kStatsSlot : smem, st>>>(
       cm, static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride,
-      a->row_stride, a->Z, a->requests, a->n_requests, ws.chan, ws.stats_list, ws.list_counts,
-      todo ? ws.list_counts + 3 : nullptr, a->n_objects + a->n_planes);
+      a->row_stride, a->Z, requests, a->n_requests, ws.chan, ws.stats_list, ws.list_counts,
+      todo ? ws.list_counts + 3 : nullptr, a->n_objects + a->n_planes, gate, bookkeeping);
   return abx_check_cuda(cudaGetLastError(), "object_stats_warp");
 }
 
@@ -520,7 +524,19 @@ int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cud
   if (n_total == 0 || a->n_requests == 0) return ABX_OK;
   Common cm = make_common(a, ws, n_total);
   cm.counters = ws.list_counts + (todo ? 6 : 2);
-  if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st, todo);
-  if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st, todo);
+  if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st, todo, a->requests, nullptr, 1);
+  if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st, todo, a->requests, nullptr, 1);
   return ABX_OK;  // float pixels: every request belongs to object_float.cu
+}
+
+// After a Z-reduced launch (zreduce.cu): the requests that stay on the stack itself (Z-add), for every window-sized
+// object, from the caller's own pixel layout.  Does nothing (one gate load per CTA) when there is no such request.
+int launch_object_stats_rest(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+  const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
+  if (n_total == 0 || a->n_requests == 0) return ABX_OK;
+  Common cm = make_common(a, ws, n_total);
+  cm.counters = ws.list_counts + 8;
+  if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st, false, ws.req_rest, ws.zflags, 0);
+  if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st, false, ws.req_rest, ws.zflags, 0);
+  return ABX_OK;
 }

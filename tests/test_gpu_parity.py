@@ -469,7 +469,7 @@ def test_fuzz_random_label_planes(ab, seed):
     against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(12))
 def test_fuzz_tma_staged_windows(ab, seed):
     """Planes whose layout qualifies for the TMA kernels (16-byte aligned rows, Z = 1): windows of every width up to 64
     at every column alignment (58..64 columns wide at a bad alignment = the left-over path), cells that fill the slot
@@ -495,14 +495,16 @@ def test_fuzz_tma_staged_windows(ab, seed):
                 lab[r + 3 : r + h - 3, c + 3 : c + w - 3] = 0
             next_id += int(rng.integers(1, 3))
         masks.append(lab)
+    Z = 1 if seed < 6 else int(rng.integers(2, 5))  # Z stacks: max requests are reduced up front (zreduce.cu), add are not
     if seed % 3 == 0:   # noise around a per-pixel level: narrow ranges, one-pass histogram
         base = rng.integers(0, max(2, top // 2), size=(n_tiles, 3, 1, 1, 1))
-        pixels = np.clip(base + rng.poisson(40, size=(n_tiles, 3, 1, H, W)), 0, top).astype(dtype)
+        pixels = np.clip(base + rng.poisson(40, size=(n_tiles, 3, Z, H, W)), 0, top).astype(dtype)
     else:
-        pixels = rng.integers(0, top + 1, size=(n_tiles, 3, 1, H, W)).astype(dtype)
+        pixels = rng.integers(0, top + 1, size=(n_tiles, 3, Z, H, W)).astype(dtype)
     tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume",
                               "min_maj_approximation"]},
             0: {"max": INTENSITY + ["max", "min"]},
+            1: {"max": ["median", "mean"], "add": ["total", "median"]},
             2: {"add": ["mean", "median", "total", "total_squared", "max2p5pc", "max5px_median", "std", "moment_of_inertia"]}}
     against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)
 

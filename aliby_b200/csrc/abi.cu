@@ -72,7 +72,7 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   ws->req_rest = reinterpret_cast<abx_request*>(b + off);
   off = align_up(off + (zr ? (size_t)a->n_requests * sizeof(abx_request) : 0));
   ws->ztile_offset = reinterpret_cast<i64*>(b + off);
-  off = align_up(off + (zr ? (size_t)a->n_tiles * sizeof(i64) : 0));
+  off = align_up(off + (zr ? 2 * (size_t)a->n_tiles * sizeof(i64) : 0));
   ws->zflags = reinterpret_cast<u32*>(b + off);
   off = align_up(off + (zr ? 16 : 0));
   ws->stats_list = reinterpret_cast<int*>(b + off);
@@ -166,8 +166,8 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   mark(0);
   if ((rc = launch_label_scan(args, ws.recs, ws.err, st))) return rc;
   mark(1);
-  // Z stacks: every requested (tile, channel) stack is max-reduced once, streaming, into planes of the workspace, and
-  // the window-sized objects then see a Z = 1 problem on those planes (zreduce.cu); `add` requests keep the stack.
+  // Z stacks: every requested (tile, channel) stack is reduced once, streaming, into planes of the workspace (max: pixel
+  // dtype, add: uint32), and the window-sized objects then see a Z = 1 problem on those planes (zreduce.cu).
   abx_extract_args red = *args;  // what the per-object statistics kernels of window-sized objects work on
   const bool zred = abx_zreduce_ok(args);
   if (zred) {
@@ -177,15 +177,16 @@ extern "C" int abx_extract(const abx_extract_args* args) {
     red.requests = ws.req_tma;
     red.C = args->n_requests;
     red.Z = 1;
-    red.chan_stride = red.z_stride = (i64)args->H * args->W;
+    const i64 slot = (i64)args->H * args->W * (args->pixel_dtype == ABX_U8 ? 4 : 2);  // a uint32-sized slot in pixel elements
+    red.chan_stride = red.z_stride = slot;
     red.row_stride = args->W;
-    red.pixel_elems = (i64)args->n_tiles * args->n_requests * args->H * args->W;
+    red.pixel_elems = (i64)args->n_tiles * args->n_requests * slot;
   }
   // objects with a window <= 64 x 64: TMA-staged windows when the layout allows, plain gathers otherwise
   bool tma = false;
   if ((rc = launch_object_stats_tma(&red, ws, st, false, &tma))) return rc;
   if (!tma && (rc = launch_object_stats_warp(&red, ws, st, false))) return rc;
-  if (zred && (rc = launch_object_stats_rest(args, ws, st))) return rc;  // the Z-add requests, from the stack itself
+  if (zred && (rc = launch_object_stats_rest(args, ws, st))) return rc;  // the Z-add requests, from their uint32 sum planes
   mark(2);
   // The few objects the TMA kernel left over (about 1 %) go through the gather kernel on a helper stream, one warp per
   // CTA, next to the shape kernel: their cost is one warp's latency, which hides behind the EDT launch.  (Running

@@ -62,11 +62,12 @@ struct Workspace {
   double* sqrt_tab;  // sqrt(d2) of every squared distance the warp EDT can produce
   u32* bg_hist;      // [n_planes][n_requests][65536] value histograms of large-plane backgrounds (background.cu)
   // Z stacks reduced up front (zreduce.cu); all null / unused when abx_zreduce_ok() is false
-  void* zplanes;            // [n_tiles][n_requests][H][W] pixel dtype: the Z-max plane of request q of every tile
+  void* zplanes;            // [n_tiles][n_requests] slots of H x W x 4 bytes: the Z-max plane (pixel dtype) or the Z-add
+                            // plane (uint32) of request q of every tile
   abx_request* req_tma;     // [n_requests] requests as the kernels on the reduced planes see them
   abx_request* req_rest;    // [n_requests] requests as the gather pass over the original stack sees them
-  i64* ztile_offset;        // [n_tiles] tile offsets inside zplanes
-  u32* zflags;              // [0]: some request is left to the gather pass (Z-add)
+  i64* ztile_offset;        // [2][n_tiles] tile offsets inside zplanes, in pixel-dtype elements and in uint32 elements
+  u32* zflags;              // [0]: some request is a Z-add (the gather pass on the uint32 planes has work)
   size_t total;
 };
 

@@ -256,7 +256,7 @@ __device__ __forceinline__ void request_stats(u32 n, u32 n_pad, u32 slot_off, co
   u32* hist = reinterpret_cast<u32*>(dyn + slot_off + kStatsHistOff);
   u32* t = reinterpret_cast<u32*>(dyn + slot_off + kStatsTOff);
   const u32 lane = lane_id();
-  const bool wide = reduction == ABX_RED_ADD && Z > 1;
+  const bool wide = (reduction == ABX_RED_ADD && Z > 1) || sizeof(PX) == 4;  // uint32 pixels: Z-add sum planes (zreduce.cu)
   const bool staged = !wide && n_pad <= (u32)kCapSmall;  // larger lists occupy the staging area themselves
   ChanStats cs;
   u32 v0 = 0;
@@ -529,14 +529,18 @@ int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cud
   return ABX_OK;  // float pixels: every request belongs to object_float.cu
 }
 
-// After a Z-reduced launch (zreduce.cu): the requests that stay on the stack itself (Z-add), for every window-sized
-// object, from the caller's own pixel layout.  Does nothing (one gate load per CTA) when there is no such request.
+// After a Z-reduced launch (zreduce.cu): the Z-add requests of every window-sized object, from their uint32 sum planes
+// (one value per pixel instead of Z).  Does nothing (one gate load per CTA) when there is no such request.
 int launch_object_stats_rest(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0 || a->n_requests == 0) return ABX_OK;
+  abx_extract_args sums = *a;  // the sum planes as a dense (tiles, requests, 1, H, W) uint32 array
+  sums.pixels = ws.zplanes;
+  sums.tile_offset = reinterpret_cast<const int64_t*>(ws.ztile_offset + a->n_tiles);
+  sums.chan_stride = sums.z_stride = (i64)a->H * a->W;
+  sums.row_stride = a->W;
+  sums.Z = 1;
   Common cm = make_common(a, ws, n_total);
   cm.counters = ws.list_counts + 8;
-  if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st, false, ws.req_rest, ws.zflags, 0);
-  if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st, false, ws.req_rest, ws.zflags, 0);
-  return ABX_OK;
+  return launch_stats<uint32_t>(&sums, ws, cm, st, false, ws.req_rest, ws.zflags, 0);
 }

@@ -51,3 +51,25 @@ for name, fn in (("one call per time point", per_tp), ("one call per 25 time poi
     dt = (time.perf_counter() - t0) / 5
     print(f"{name}: {1e3 * dt / T:.3f} ms per time point, {int(n_labels.sum())} cells in {T} time points, "
           f"{algo / 1e9 / dt:.1f} GB/s of the {algo / T / 1e6:.2f} MB per time point the tiles hold")
+
+# stage breakdown of one per-time-point call
+import ctypes as C_  # noqa: E402
+
+from aliby_b200 import _native as nat  # noqa: E402
+
+lib = nat.lib()
+evs = []
+for _ in range(6):
+    h = C_.c_void_p()
+    nat.check(lib.abx_event_create(C_.byref(h)), "ev")
+    evs.append(h)
+acc = np.zeros(5)
+for t in range(T):
+    engine.run_planes(plan, lab[t * NT:(t + 1) * NT], np.arange(NT, dtype=np.int32), n_labels[t * NT:(t + 1) * NT], fr[t],
+                      tile_off1, H * W, H * W, W, C, 1, stage_events=evs)
+    torch.cuda.synchronize()
+    for i in range(5):
+        ms = C_.c_float()
+        nat.check(lib.abx_event_elapsed_ms(evs[i], evs[i + 1], C_.byref(ms)), "el")
+        acc[i] += ms.value
+print("per-time-point stages ms (scan, stats, edt, large, finalize):", [round(x / T, 3) for x in acc])

@@ -128,7 +128,7 @@ bg_tile_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i64 la
   __shared__ u32 s_lo[kThreads / 32], s_hi[kThreads / 32];
   __shared__ u32 s_med[2], s_total;
   __shared__ u64 s_top;
-  const int p = blockIdx.y, q = blockIdx.x, tid = threadIdx.x;
+  const int p = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
   const abx_request rq = requests[q];
   if (rq.bg_features == 0 || rq.reduction == ABX_RED_DIV || (rq.reduction == ABX_RED_ADD && Z > 1)) return;
   const u32 n = recs[n_objects + p].n;
@@ -278,8 +278,8 @@ static int launch_tile_background(const abx_extract_args* a, const Workspace& ws
     if (e != cudaSuccess) return abx_check_cuda(e, "bg_tile smem attribute");
     done[dev] = true;
   }
-  if (a->n_planes > 65535) return abx_set_error(ABX_ERR_INVALID, "more than 65535 planes with a background request");
-  bg_tile_kernel<PX><<<dim3(a->n_requests, a->n_planes), kThreads, smem, st>>>(
+  if (a->n_requests > 65535) return abx_set_error(ABX_ERR_INVALID, "more than 65535 requests with a background metric");
+  bg_tile_kernel<PX><<<dim3(a->n_planes, a->n_requests), kThreads, smem, st>>>(
       static_cast<const uint16_t*>(a->labels), a->label_plane_stride, a->label_row_stride, a->plane_tile, a->H, a->W,
       static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride,
       a->row_stride, a->Z, a->requests, a->n_requests, a->n_objects, ws.recs, ws.chan);

@@ -108,6 +108,7 @@ bool abx_zreduce_ok(const abx_extract_args* a) {
   if (a->Z <= 1 || a->n_requests <= 0 || a->n_tiles <= 0 || a->n_objects <= 0) return false;
   if (a->pixel_dtype != ABX_U16 && a->pixel_dtype != ABX_U8) return false;
   const int es = a->pixel_dtype == ABX_U8 ? 1 : 2;
+  if ((i64)a->n_tiles * a->n_requests > 65535) return false;  // grid.y of the reduction; such calls keep the fused gathers
   return (a->W * es) % 16 == 0 && a->W >= 64 && a->H >= 8 && ((i64)a->H * a->W * 4) % 256 == 0;
 }
 
@@ -130,7 +131,6 @@ int launch_zreduce(const abx_extract_args* a, const Workspace& ws, cudaStream_t 
   i64 bx = (n_vec + 255) / 256;
   if (bx > 148 * 8) bx = 148 * 8;
   const dim3 grid((unsigned)bx, (unsigned)(a->n_tiles * a->n_requests));
-  if (grid.y > 65535u) return abx_set_error(ABX_ERR_INVALID, "tiles x requests above 65535 with a Z stack");
   if (a->pixel_dtype == ABX_U16)
     zreduce_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset),
                                                 a->chan_stride, a->z_stride, a->row_stride, a->Z, a->H, a->W, a->requests,

@@ -58,15 +58,14 @@ __device__ __forceinline__ void emit_piece(abx_object_rec* __restrict__ recs, in
 // bit j of the result <-> halfword j of (w0..w3) equals `label`
 __device__ __forceinline__ u32 eq_mask8(const u32 (&w)[4], u32 label) {
   const u32 pair = label | (label << 16);
-  // carry-free "halfword != 0" test: bit 15 / 31 of nz is set iff the low / high halfword of x is non-zero
+  // "halfword != 0" as min(halfword, 1) on both halves at once (VIMNMX.U16x2): bit 0 / 16 of nz[j] is set iff the low /
+  // high halfword of word j differs from the label
   u32 nz[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const u32 x = w[j] ^ pair;
-    nz[j] = (((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) & 0x80008000u;
-  }
-  // gather the eight flag bits: low halfwords -> even positions, high halfwords -> odd positions
-  const u32 a = (nz[0] >> 15) | (nz[1] >> 13) | (nz[2] >> 11) | (nz[3] >> 9);  // bits {0,16},{2,18},{4,20},{6,22}
+  for (int j = 0; j < 4; ++j) nz[j] = __vminu2(w[j] ^ pair, 0x00010001u);
+  // gather the eight flag bits (disjoint, so sums are ors — and the multiply-adds run on the FMA pipe, not the ALU):
+  // low halfwords -> even positions, high halfwords -> odd positions
+  const u32 a = nz[0] + 4u * nz[1] + 16u * nz[2] + 64u * nz[3];  // bits {0,16},{2,18},{4,20},{6,22}
   const u32 ne = (a & 0x55u) | ((a >> 15) & 0xAAu);
   return ne ^ 0xFFu;
 }

@@ -231,12 +231,14 @@ struct TmaMaps {
   CUtensorMap px[2];   // the pixel buffer as rows of row_stride elements, box 32 | 64 columns x 8 rows
 };
 
-template <typename PX>
+template <typename PX, bool kSplit>
 __global__ void __launch_bounds__(kTmaWarps * 32, 1)
 object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX* __restrict__ pixels,
                  const i64* __restrict__ tile_offset, i64 chan_stride, i64 px_row_stride, int chan_rows,
                  const abx_request* __restrict__ requests, int n_requests, ChanStats* __restrict__ chan,
-                 int* __restrict__ stats_list, u32* __restrict__ stats_count, u32* __restrict__ warp_count, int list_cap) {
+                 int* __restrict__ stats_list, u32* __restrict__ stats_count, u32* __restrict__ warp_count, int list_cap,
+                 int split_log2_arg) {
+  const int split_log2 = kSplit ? split_log2_arg : 0;  // the unsplit instantiation folds all of this away
   const u32 lane = lane_id();
   const u32 slot_off = (threadIdx.x >> 5) * kTmaSlot;
   const u32 bar = smem_addr(dyn + slot_off + kBarOff);
@@ -248,14 +250,22 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
   u32 parity = 0;
   // Longest first: the queue runs over the objects twice — items [0, n_total) take only the big objects, items
   // [n_total, 2 n_total) the others — so that the launch does not end on one warp working through a 2 500-pixel cell.
-  const int n_items = 2 * cm.n_total;
+  // Short queues (one small field: fewer objects than resident warps) are split: `split` work items per object, each
+  // with its share of the requests (the label window and the list are then rebuilt per item, which a launch that would
+  // otherwise last one object's latency can afford).
+  const int split = 1 << split_log2;  // a power of two: no divisions below
+  const int n_half = cm.n_total << split_log2;
+  const int n_items = 2 * n_half;
   Queue qu{cm.counters, n_items, 0};
   int item = qu.fetch();
   int nxt_item = item < n_items ? qu.fetch() : n_items;
   while (item < n_items) {
-    const bool big_pass = item < cm.n_total;
-    const int obj = big_pass ? item : item - cm.n_total;
-    const int nxt = nxt_item < cm.n_total ? nxt_item : nxt_item - cm.n_total;  // == n_total past the end
+    const bool big_pass = item < n_half;
+    const int unit = big_pass ? item : item - n_half;
+    const int obj = unit >> split_log2, part = unit & (split - 1);
+    const int q_lo = (part * n_requests) >> split_log2, q_hi = ((part + 1) * n_requests) >> split_log2;  // this item's requests
+    const int nxt_unit = nxt_item < n_half ? nxt_item : nxt_item - n_half;
+    const int nxt = nxt_item < n_items ? nxt_unit >> split_log2 : cm.n_total;
     const abx_object_rec rec = cm.recs[obj];
     if ((rec.n > kBigFirst) != big_pass) {  // not this pass
       item = nxt_item;
@@ -284,19 +294,19 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
     const u32 h8 = ((u32)h + kBoxRows - 1u) & ~(u32)(kBoxRows - 1);
     const u32 n_pad = (rec.n + (u32)kPad - 1u) & ~((u32)kPad - 1u);
     if (rec.n == 0) {  // absent label (or empty background): zero records -> NaN in finalize
-      for (int q = lane; q < n_requests; q += 32) {
+      for (int q = q_lo + (int)lane; q < q_hi; q += 32) {
         ChanStats z;
         z.sum = z.sumsq = z.wrapsq = z.m10 = z.m01 = z.m20 = z.m02 = z.top2p5_sum = z.top5_sum = 0;
         z.vmin = z.vmax = z.med_lo = z.med_hi = 0;
         chan[(i64)obj * n_requests + q] = z;
       }
     } else if (!cand) {
-      if (lane == 0) stats_list[atomicAdd(stats_count, 1u)] = obj;  // hand over to the CTA-per-object kernel
+      if (lane == 0 && part == 0) stats_list[atomicAdd(stats_count, 1u)] = obj;  // hand over to the CTA-per-object kernel
     } else if (need > 64u || 2u * n_pad + ((h8 << sh) << 1) + 2048u > kFlex) {
       // window-sized but too wide for a 64-column box at this alignment, or list + window + a 512-bin histogram above
       // the flex area (a few cells per thousand): second list, filled from the back of the same buffer, for
       // object_stats_warp
-      if (lane == 0) stats_list[list_cap - 1 - (int)atomicAdd(warp_count, 1u)] = obj;
+      if (lane == 0 && part == 0) stats_list[list_cap - 1 - (int)atomicAdd(warp_count, 1u)] = obj;
     } else {
       const u32 win_off = slot_off + kFlexOff + 2u * n_pad;  // n_pad is a multiple of 128: 128-byte aligned
       // the histogram takes what is left behind the window: 1024 bins, or 512 for the largest objects
@@ -324,21 +334,21 @@ object_stats_tma(const __grid_constant__ TmaMaps maps, const Common cm, const PX
       }
       const PX* px0 = pixels + org;
 #pragma unroll 1
-      for (int q = 0; q < n_requests; ++q) {
+      for (int q = q_lo; q < q_hi; ++q) {
         const abx_request rq = requests[q];
         // L2 prefetch one request ahead: the next request of this object, or the label window and the first
         // request of the warp's next object (a longer distance does not survive in L2 at these rates)
-        if (q + 1 < n_requests) {
+        if (q + 1 < q_hi) {
           prefetch_request<PX>(px0 + (i64)requests[q + 1].channel * chan_stride, px_row_stride, 0, 1, h, w);
         } else if (nxt < cm.n_objects) {
           const abx_object_rec nr = cm.recs[nxt];
           const int nh = (int)(nr.rmax - nr.rmin) + 1, nw = (int)(nr.cmax - nr.cmin) + 1;
-          if (nr.n > 0 && nh <= kSide && nw <= kSide && (nr.n > kBigFirst) == (nxt_item < cm.n_total)) {
+          if (nr.n > 0 && nh <= kSide && nw <= kSide && (nr.n > kBigFirst) == (nxt_item < n_half)) {
             const int np = find_plane(cm.plane_base, cm.n_planes, nxt);
             prefetch_rows(cm.labels + (i64)np * cm.lab_plane_stride + (i64)nr.rmin * cm.lab_row_stride + nr.cmin,
                           cm.lab_row_stride * 2, nh, (u32)nw * 2u);
             prefetch_request<PX>(pixels + tile_offset[cm.plane_tile[np]] + (i64)nr.rmin * px_row_stride + nr.cmin +
-                                     (i64)requests[0].channel * chan_stride,
+                                     (i64)requests[((nxt_unit & (split - 1)) * n_requests) >> split_log2].channel * chan_stride,
                                  px_row_stride, 0, 1, nh, nw);
           }
         }
@@ -406,16 +416,26 @@ int launch_tma(const abx_extract_args* a, const Workspace& ws, const TmaMaps& ma
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(object_stats_tma<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    cudaError_t e = cudaFuncSetAttribute(object_stats_tma<PX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(object_stats_tma<PX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return abx_check_cuda(e, "object_stats_tma smem attribute");
     done[dev] = true;
   }
-  int grid = (cm.n_total + warps - 1) / warps;
+  // fewer objects than two rounds of resident warps: several work items per object
+  int split_log2 = 0;
+  while (split_log2 < 3 && (cm.n_total << split_log2) < 2 * 148 * warps && (2 << split_log2) <= a->n_requests) ++split_log2;
+  const int split = 1 << split_log2;
+  int grid = (cm.n_total * split + warps - 1) / warps;
   if (grid > 148) grid = 148;  // persistent: one CTA per SM, warps pull objects from a counter
-  object_stats_tma<PX><<<grid, warps * 32, smem, st>>>(
-      maps, cm, static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride,
-      a->row_stride, (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests, ws.chan, ws.stats_list,
-      ws.list_counts, ws.list_counts + 3, a->n_objects + a->n_planes);
+#define ABX_LAUNCH_TMA(SPLIT)                                                                                          \
+  object_stats_tma<PX, SPLIT><<<grid, warps * 32, smem, st>>>(                                                          \
+      maps, cm, static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride,        \
+      a->row_stride, (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests, ws.chan, ws.stats_list,         \
+      ws.list_counts, ws.list_counts + 3, a->n_objects + a->n_planes, split_log2)
+  if (split_log2) ABX_LAUNCH_TMA(true);
+  else ABX_LAUNCH_TMA(false);
+#undef ABX_LAUNCH_TMA
   return abx_check_cuda(cudaGetLastError(), "object_stats_tma");
 }
 

@@ -2,7 +2,8 @@
 // its label window and then, request by request, its pixel window — is brought into the warp's shared-memory
 // slot by cp.async.bulk.tensor boxes (one elected lane, mbarrier completion) and all the arithmetic reads shared
 // memory.  This is the fast path of object_stats_warp (object_warp.cu, which stays as the path for layouts
-// TMA cannot address: unaligned bases / strides, Z stacks).  Same outputs, same reference semantics
+// TMA cannot address: unaligned bases / strides; Z stacks reach this kernel as reduced planes, zreduce.cu).  Same
+// outputs, same reference semantics
 // (src/extraction/extract.py:346-359 loop; cell.py:43-157,232-265; tile crop of tiler.py:309-366 fused
 // through the tile offset).
 //
@@ -16,8 +17,9 @@
 //            histogram (ATOMS.POPC.INC) and the four ranks by warp scans; 7-bit refinement when range > 1023
 //   While request q is processed, the window of request q + 1 (or the label window and first request of the
 //   warp's next object) is prefetched into L2, so that the TMA reads hit L2.
-// Objects whose list and window do not fit the flex area, windows above 64 x 64 and the per-plane background go
-// to the CTA-per-object kernel (object_stats.cu) through the hand-over list.
+// Windows above 64 x 64 and the per-plane background go to the CTA-per-object kernel (object_stats.cu) through the
+// hand-over list; window-sized objects that do not fit a slot or a 64-column box go to object_stats_warp through a
+// second list.  Big objects are taken first, and short queues are split into several work items per object.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cstring>

@@ -1,32 +1,28 @@
-// Per-object kernels for objects whose bounding box fits 64 x 64: ONE WARP PER OBJECT.
+// Per-object statistics of objects whose bounding box fits 64 x 64, by PLAIN GATHERS: one warp per object.
 //
-// Two persistent kernels share the front end (phase M) and cover, for one object, everything the
-// reference computes with |instructions| full-plane passes (src/extraction/extract.py:346-359):
+// object_stats_warp covers, for one object, everything the reference computes with |instructions| full-plane passes
+// (src/extraction/extract.py:346-359): the intensity statistics of every (channel, Z-reduction) request
+// (cell.py:43-157,232-265; distributors.py:19-21 fused into the load; tile crop of tiler.py:309-366 fused through the
+// tile offset).  It is the twin of object_stats_tma (object_tma.cu, TMA-staged windows) and runs
+//   (a) for whole launches whose layout TMA cannot address (unaligned bases / row strides, planes narrower than 64,
+//       Z stacks whose rows are not 16-byte multiples),
+//   (b) as one work item per (object, request) for the few objects object_stats_tma leaves over,
+//   (c) on the uint32 sum planes of Z-add requests (zreduce.cu).
 //
-//   object_stats_warp   the intensity statistics of every (channel, Z-reduction) request
-//                       (cell.py:43-157,232-265; distributors.py:19-21 fused into the load; tile
-//                       crop of tiler.py:309-366 fused through the tile offset)
-//   object_edt_warp     the three chained exact EDTs of the shape metrics (cell.py:176-229)
+//   phase M  label window -> compact list of the object's pixel offsets ((r << 6) | c, row-major) from warp ballots:
+//            no atomics, deterministic order; padded to a multiple of 128 with copies of entry 0
+//   phase S  per request: gather through the list (coalesced along rows, a software pipeline of four loads per lane
+//            and stage), moments in registers, values staged in shared memory when they fit, range-adaptive 1024-bin
+//            histogram (ATOMS.POPC.INC), the four ranks located by warp scans; 7-bit refinement sweeps only when the
+//            value range exceeds 1023
 //
-//   phase M  label window -> 64-bit row bitmasks from warp ballots + the compact list of the
-//            object's pixel offsets ((r << 6) | c, row-major): no atomics, deterministic order
-//   phase S  per request: gather through the offset list (coalesced along rows, 8 loads in flight
-//            per lane), moments in registers, values staged in shared memory, range-adaptive
-//            1024-bin histogram (packed 16-bit counters), the four ranks located by warp scans;
-//            7-bit refinement sweeps only when the value range exceeds 1023
-//   phase E  row distances from the bitmasks (clz/ffs), exact column pass with early exit (four
-//            pixels per lane in flight), cone top as a second bitmask, plateau distances
-//
-// Both kernels are written for a SMALL CODE FOOTPRINT (one path per phase, loops not unrolled
-// beyond what memory-level parallelism needs, only the cold variants — wide sums, re-gather —
-// out of line): the first version of this file compiled to 165 KB of SASS per kernel and stalled on
-// instruction fetch (ncu: stall_no_instruction 4 of 11 cycles per issue, profiles/r01e_summary.md);
-// hot phases are inlined at their single call site, because a __noinline__ call cost a frame in
-// local memory (profiles/r01_final_summary.md).  A CTA mixes two slot sizes — most warps own a slot for
-// objects of <= 2048 pixels, two own a slot for <= 4096 — so that one launch serves every object
-// of the window class without a tail.  No __syncthreads: the warps of a CTA are independent.
-// Larger windows and the per-plane background go to work lists that the CTA-per-object kernels
-// (object_stats.cu, shape_edt.cu) consume.
+// SMALL CODE FOOTPRINT matters more than anything else here (one path per phase, loops not unrolled beyond what
+// memory-level parallelism needs, only the cold variants — wide sums, re-gather — out of line): the first version of
+// this file compiled to 165 KB of SASS and stalled on instruction fetch (profiles/r01e_summary.md), and a five-deep
+// gather pipeline did so again.  Hot phases are inlined at their single call site, because
+// a __noinline__ call cost a frame in local memory (profiles/r01_final_summary.md).  No __syncthreads: the warps of a
+// CTA are independent.  Larger windows and the per-plane background go to work lists that the CTA-per-object kernels
+// (object_stats.cu, shape_edt.cu) and background.cu consume.
 #include <type_traits>
 
 #include "common.cuh"

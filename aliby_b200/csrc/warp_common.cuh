@@ -3,13 +3,11 @@
 #pragma once
 
 constexpr int kSide = 64;        // maximum window side
-constexpr int kCapSmall = 2048;  // pixels per object: EDT small slot; statistics: objects up to here stage their values
+constexpr int kCapSmall = 2048;  // gather kernel: objects up to this many pixels stage their values
 constexpr int kCapLarge = 4096;  // pixels per object, large slot (= kSide * kSide)
 constexpr int kBins = 1024;      // level-0 histogram bins (32-bit counters)
-constexpr int kLargeSlots = 2;   // EDT warps per CTA that own a large slot (the last ones)
 constexpr int kStatsWarps = 9;   // nine identical 12.1 KB slots: 109 KB per CTA, 2 CTAs per SM
 constexpr int kDepth = 3;        // gathers of four pixels per lane in the pass-1 pipeline (code size: the I-cache is the limit)
-constexpr int kEdtWarps = 10;    // 8 small + 2 large slots: 103 KB per CTA, 2 CTAs per SM
 constexpr int kPad = 128;        // the offset list is padded to a multiple of this (four pixels per lane)
 // statistics slot: offs u16[4096] (objects <= kCapSmall pixels: offs u16[2048] | vals u16[2048]) | hist u32[1024] | t u32[16]
 constexpr u32 kStatsHistOff = kCapLarge * 2, kStatsTOff = kStatsHistOff + kBins * 4, kStatsSlot = kStatsTOff + 64;
@@ -31,15 +29,13 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Work distribution: one atomic per object; a warp always holds the NEXT object too and prefetches
-// its windows into L2 while it works.  Small-slot warps walk counter 0 and take the objects of
-// <= kCapSmall pixels (plus the bookkeeping: empty objects, hand-over lists); large-slot warps walk
-// counter 1 for the bigger ones first and then help with counter 0.
+// Work distribution: persistent warps pull work items from a global counter, one atomic per item; a warp always
+// holds the NEXT item too, so that it can prefetch that item's windows into L2 while it works.
 // ------------------------------------------------------------------------------------------------
 struct Queue {
   u32* counters;  // [2]
   int n_total;
-  int phase;      // 1: large objects (counter 1), 0: small objects (counter 0)
+  int phase;      // which of the two counters (always 0 since the slots became uniform)
   __device__ __forceinline__ int fetch() {
     int v = 0;
     if (lane_id() == 0) v = (int)atomicAdd(&counters[phase], 1u);

@@ -45,6 +45,14 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     a.pixel_dtype = nat.U16
     assert lib.abx_extract_workspace_bytes(ctypes.byref(a), ctypes.byref(need)) == 0
     assert need.value > 8004 * 48
+    # Z stacks with 16-byte rows are reduced into planes of the workspace: one H x W x 4-byte slot per (tile, request)
+    flat = need.value
+    a.n_tiles, a.Z = 4, 16
+    assert lib.abx_extract_workspace_bytes(ctypes.byref(a), ctypes.byref(need)) == 0
+    assert 4 * 5 * 2160 * 2160 * 4 <= need.value - flat < 4 * 5 * 2160 * 2160 * 4 + 8192
+    a.W, a.row_stride = 2161, 2161  # rows that are not 16-byte multiples keep the fused gathers: no planes
+    assert lib.abx_extract_workspace_bytes(ctypes.byref(a), ctypes.byref(need)) == 0
+    assert need.value < flat + (1 << 20)
     with pytest.raises(NotImplementedError):
         nat.check(-2, "x")
 

@@ -59,7 +59,18 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   off = align_up(off + (a->need_edt ? (size_t)a->n_objects * sizeof(ShapeStats) : 0));
   ws->err = reinterpret_cast<u32*>(b + off);
   ws->list_counts = ws->err + 1;
-  off = align_up(off + 12 * sizeof(u32));
+  off = align_up(off + kCounterWords * sizeof(u32));
+  // torus bitmaps of the label scan (+ one dummy for out-of-range labels), routing of the plan kernel
+  ws->bitmaps = reinterpret_cast<u64*>(b + off);
+  off = align_up(off + ((size_t)a->n_objects + 1) * 512);
+  ws->plan = reinterpret_cast<ObjPlan*>(b + off);
+  off = align_up(off + n_rec * sizeof(ObjPlan));
+  ws->order_stats = reinterpret_cast<int*>(b + off);
+  off = align_up(off + n_rec * sizeof(int));
+  ws->order_edt = reinterpret_cast<int*>(b + off);
+  off = align_up(off + n_rec * sizeof(int));
+  ws->pair_list = reinterpret_cast<int*>(b + off);
+  off = align_up(off + n_rec * (size_t)(a->n_requests > 0 ? a->n_requests : 1) * sizeof(int));
   ws->sqrt_tab = reinterpret_cast<double*>(b + off);
   off = align_up(off + (a->need_edt ? (size_t)abx_sqrt_table_entries() * sizeof(double) : 0));
   ws->bg_hist = reinterpret_cast<u32*>(b + off);
@@ -122,9 +133,9 @@ extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* reco
   int rc = abx_validate(args);
   if (rc) return rc;
   if (!records) return abx_set_error(ABX_ERR_INVALID, "records is NULL");
-  if (!args->workspace || args->workspace_bytes < 16 * sizeof(u32))
-    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 64-byte workspace for its flags");
-  return launch_label_scan(args, records, static_cast<u32*>(args->workspace), static_cast<cudaStream_t>(args->stream));
+  if (!args->workspace || args->workspace_bytes < kCounterWords * sizeof(u32))
+    return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 128-byte workspace for its flags");
+  return launch_label_scan(args, records, static_cast<u32*>(args->workspace), nullptr, static_cast<cudaStream_t>(args->stream));
 }
 
 // One helper stream and a fork / join event pair per (host thread, device), created on first use and kept.
@@ -164,7 +175,7 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   void* const* ev = args->stage_events;
   auto mark = [&](int i) { if (ev && ev[i]) cudaEventRecord(static_cast<cudaEvent_t>(ev[i]), st); };
   mark(0);
-  if ((rc = launch_label_scan(args, ws.recs, ws.err, st))) return rc;
+  if ((rc = launch_label_scan(args, ws.recs, ws.err, ws.bitmaps, st))) return rc;
   mark(1);
   // Z stacks: every requested (tile, channel) stack is reduced once, streaming, into planes of the workspace (max: pixel
   // dtype, add: uint32), and the window-sized objects then see a Z = 1 problem on those planes (zreduce.cu).
@@ -182,21 +193,25 @@ extern "C" int abx_extract(const abx_extract_args* args) {
     red.row_stride = args->W;
     red.pixel_elems = (i64)args->n_tiles * args->n_requests * slot;
   }
-  // objects with a window <= 64 x 64: TMA-staged windows when the layout allows, plain gathers otherwise
-  bool tma = false;
-  if ((rc = launch_object_stats_tma(&red, ws, st, false, &tma))) return rc;
-  if (!tma && (rc = launch_object_stats_warp(&red, ws, st, false))) return rc;
+  // objects with a window <= 64 x 64: the sweep kernel (TMA-staged windows, lists from the label scan's bitmaps) when
+  // the pixel layout allows, plain gathers otherwise.  The plan kernel routes every object first.
+  const bool sweep = abx_sweep_ok(&red);
+  if ((rc = launch_plan(&red, ws, st, sweep))) return rc;
+  if (sweep) {
+    if ((rc = launch_object_sweep(&red, ws, st))) return rc;
+  } else if ((rc = launch_object_stats_warp(&red, ws, st, false))) {
+    return rc;
+  }
   if (zred && (rc = launch_object_stats_rest(args, ws, st))) return rc;  // the Z-add requests, from their uint32 sum planes
   mark(2);
-  // The few objects the TMA kernel left over (about 1 %) go through the gather kernel on a helper stream, one warp per
-  // CTA, next to the shape kernel: their cost is one warp's latency, which hides behind the EDT launch.  (Running
-  // the whole shape kernel next to the statistics kernel, one CTA of each per SM, was measured and is slower: 0.79 ms
-  // against 0.27 + 0.25 ms one after the other.)
+  // The few (object, request) pairs the sweep kernel left over (windows too wide at their alignment, wide value ranges
+  // of chunked windows) go through the gather kernel on a helper stream, one warp per CTA, next to the shape kernel:
+  // their cost is one warp's latency, which hides behind the EDT launch.
   const bool edt = args->need_edt && args->n_objects > 0;
-  Helper* hp = (tma && edt) ? helper_stream() : nullptr;
-  if (tma && !hp && (rc = launch_object_stats_warp(&red, ws, st, true))) return rc;
+  Helper* hp = (sweep && edt) ? helper_stream() : nullptr;
+  if (sweep && !hp && (rc = launch_object_stats_warp(&red, ws, st, true))) return rc;
   if (hp) cudaEventRecord(hp->fork, st);
-  if ((rc = launch_object_edt_warp(args, ws, st))) return rc;  // first: its CTAs take their two places per SM
+  if ((rc = launch_object_edt_warp(args, ws, st))) return rc;  // first: its CTAs take their places on the SMs
   if (hp) {
     cudaStreamWaitEvent(hp->stream, hp->fork, 0);
     if ((rc = launch_object_stats_warp(&red, ws, hp->stream, true))) return rc;

@@ -48,8 +48,28 @@ struct ShapeStats {
   u32 max_dn2;     // max squared distance to the cone top
 };
 
+// What the plan kernel (object_sweep.cu) hands the statistics kernel for one window-sized object: where its pixel window
+// starts in the caller's buffer seen as rows of row_stride elements (the TMA coordinates of channel 0), and the window
+// geometry.  geom = (h - 1) | (w - 1) << 6 | (rmin & 63) << 12 | (cmin & 63) << 18 | s_px << 24, with s_px the number
+// of columns between the 16-byte aligned start of the TMA box and the bounding box.
+struct ObjPlan {
+  int32_t tma_x, tma_y;
+  u32 n;
+  u32 geom;
+};
+
+constexpr int kCounterWords = 32;  // err[0] + list_counts[31], zeroed by the label scan
+// indices into Workspace::list_counts
+constexpr int kCntStatsList = 0, kCntEdtList = 1, kCntGather = 2, kCntLeftover = 3, kCntEdtWork = 4, kCntLeftoverWork = 6,
+              kCntRest = 8, kCntOrderBig = 12, kCntOrderSmall = 13, kCntSweepWork = 14, kCntEdtBig = 15, kCntEdtSmall = 16;
+
 struct Workspace {
   abx_object_rec* recs;  // [n_objects + n_planes]
+  u64* bitmaps;          // [n_objects + 1][64] torus bitmaps written by the label scan (label_scan.cu)
+  ObjPlan* plan;         // [n_objects + n_planes]
+  int* order_stats;      // [n_objects + n_planes] work order of the statistics kernel: big objects from the front, others from the back
+  int* order_edt;        // [n_objects] the same for the shape kernel
+  int* pair_list;        // [(n_objects + n_planes) * n_requests] (object * n_requests + request) pairs left to object_stats_warp
   ChanStats* chan;       // [(n_objects + n_planes) * n_requests]
   ShapeStats* shape;     // [n_objects]
   unsigned char* edt_scratch;
@@ -57,8 +77,7 @@ struct Workspace {
   u32* err;          // [0] error flags, [1] stats_list length, [2] edt_list length
   int* stats_list;   // objects the warp kernel handed to the CTA statistics kernel
   int* edt_list;     // objects the warp kernel handed to the CTA EDT kernel
-  u32* list_counts;  // = err + 1: [0] stats_list length, [1] edt_list length, [2] statistics work counter, [3] length of the
-                     // second list of object_stats_tma (back of stats_list), [4..5] EDT work counters, [6] counter of that list
+  u32* list_counts;  // = err + 1, indexed by the kCnt* constants above
   double* sqrt_tab;  // sqrt(d2) of every squared distance the warp EDT can produce
   u32* bg_hist;      // [n_planes][n_requests][65536] value histograms of large-plane backgrounds (background.cu)
   // Z stacks reduced up front (zreduce.cu); all null / unused when abx_zreduce_ok() is false
@@ -76,10 +95,11 @@ int abx_check_cuda(cudaError_t e, const char* what);
 int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws);
 int abx_validate(const abx_extract_args* a);
 
-int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err /* [3] */, cudaStream_t st);
+int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err /* [kCounterWords] */, u64* bitmaps, cudaStream_t st);
+int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool sweep_ok);
+int launch_object_sweep(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+bool abx_sweep_ok(const abx_extract_args* a);
 int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool todo);
-int launch_object_stats_tma(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool shared_sm, bool* launched);
-bool abx_stats_tma_ok(const abx_extract_args* a);
 int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);

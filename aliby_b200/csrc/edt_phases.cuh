@@ -1,7 +1,6 @@
 // The shape phases of one window-sized object, from its 64-bit row masks to ShapeStats (the three chained exact EDTs of
-// src/extraction/core/functions/cell.py:176-229).  Shared by object_edt_grid (object_edt.cu) and the fused
-// statistics + shape kernel (object_tma.cu).  Include inside the translation unit's anonymous namespace after
-// warp_common.cuh.  Shared-memory regions (byte offsets into dyn): rowmask u64[64] (filled by the caller, bit c of
+// src/extraction/core/functions/cell.py:176-229), used by object_edt_grid (object_edt.cu).  Include inside the
+// translation unit's anonymous namespace after warp_common.cuh.  Shared-memory regions (byte offsets into dyn): rowmask u64[64] (filled by the caller, bit c of
 // row r <-> window pixel (r, c), columns may be shifted right by s_lab), topmask u64[64], info u32[64],
 // grid u16 [kEdtGridRows][64] (128-byte rows; the caller need not initialise it).
 #pragma once

@@ -1,5 +1,8 @@
 // Label scan: one streaming pass over the uint16 label planes that produces, per
-// (plane, label), the area, the bounding box and the 1-based coordinate sums.
+// (plane, label), the area, the bounding box, the 1-based coordinate sums and a 64 x 64
+// "torus" BITMAP of the object: bit (c & 63) of word (r & 63) <-> pixel (r, c).  An object whose bounding box fits
+// 64 x 64 maps one-to-one into its bitmap, so the per-object kernels (object_sweep.cu, object_edt.cu) rebuild
+// their row masks from 512 bytes instead of re-reading label windows: the label planes leave HBM once.
 //
 // Replaces the one-hot expansion of src/agora/utils/masks.py:35-37 (L*Y*X bytes) and
 // the full-plane products of cell.py:18-27 (area) and cell.py:282-303 (centroid).
@@ -17,12 +20,14 @@
 
 namespace {
 
+#include "tma.cuh"
+
 constexpr int kScanThreads = 128;  // 4 warps x 8 KB of staging = 32 KB static shared memory per CTA
 constexpr int kScanWarps = kScanThreads / 32;
 
 __global__ void init_records_kernel(abx_object_rec* recs, int n_objects, int n_planes, int H, int W, u32* err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 12) err[i] = 0;  // error flags, the work-list lengths, the work counters of the per-object kernels
+  if (i < kCounterWords) err[i] = 0;  // error flags, the work-list lengths, the work counters of the per-object kernels
   if (i < n_objects + n_planes) {
     abx_object_rec r;
     r.sum_row = 0; r.sum_col = 0; r.n = 0;
@@ -41,6 +46,26 @@ struct Piece {
   u32 label, n, sum_row, sum_col;  // sums of (row + 1) and (col + 1)
   u32 rmin, rmax, cmask;           // cmask: bit j <-> column c0 + j holds a pixel of the piece
 };
+
+// The 32-bit word of the object's torus bitmap that holds (row 0, the 8-pixel strip at c0), and the strip's bit offset
+// inside it: strips are 8-aligned, so the eight pixels of a strip row are exactly one byte.  The byte is OR-ed in
+// (red.global.or, no return value): a cell 58 to 64 pixels wide can touch nine strips, and then its first and its
+// last strip share a byte column.  Labels above n_labels (caller error, flagged by emit_piece) land in the dummy
+// bitmap behind the last object.
+struct BitCol {
+  u32* word;  // row r lives 2 * (r & 63) words further
+  u32 shift;
+};
+__device__ __forceinline__ BitCol bitmap_col(u64* __restrict__ bitmaps, int base, u32 n_labels, int n_objects, u32 label,
+                                             u32 c0) {
+  const u32 row = label <= n_labels ? (u32)base + label - 1u : (u32)n_objects;
+  const u32 byte = (c0 >> 3) & 7u;
+  BitCol b;
+  b.word = reinterpret_cast<u32*>(bitmaps + (size_t)row * 64u) + (byte >> 2);
+  b.shift = (byte & 3u) << 3;
+  return b;
+}
+__device__ __forceinline__ void bitmap_or(const BitCol& b, u32 r, u32 m) { atomicOr(b.word + ((r & 63u) << 1), m << b.shift); }
 
 __device__ __forceinline__ void emit_piece(abx_object_rec* __restrict__ recs, int base, u32 n_labels, const Piece& p,
                                            u32 c0, u32* err) {
@@ -90,34 +115,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// ---- TMA (cp.async.bulk.tensor) plumbing: one elected lane brings a [kRowBatch rows x 256 columns] box of the
-// label plane into the warp's staging buffer and the 32 lanes wait on the buffer's mbarrier.  Boxes that stick out
-// of the plane are zero-filled by the hardware (label 0 = background), so ragged edges need no special case.
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  u32 done;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_box(u32 dst, const CUtensorMap* tmap, int x, int y, int z, u32 bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
-
-template <bool kTma>
+template <bool kTma, bool kBits>
 __global__ void __launch_bounds__(kScanThreads)
 label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __restrict__ labels, int n_planes, int H, int W,
                   i64 plane_stride, i64 row_stride, const int32_t* __restrict__ plane_base,
-                  abx_object_rec* __restrict__ recs, int n_objects, int vec_ok, u32* err) {
+                  abx_object_rec* __restrict__ recs, int n_objects, int vec_ok, u32* err, u64* __restrict__ bitmaps) {
   __shared__ __align__(128) uint4 stage_all[kScanWarps][2][kRowBatch][32];  // 8 KB per warp
   __shared__ __align__(8) u64 bars[kScanWarps][2];
   const u32 lane = lane_id();
@@ -131,8 +133,8 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
   u32 parity0 = 0, parity1 = 0;  // phase of the two mbarriers (warp-uniform)
   if (kTma) {
     if (lane == 0) {
-      mbar_init(smem_u32(&bars[warp][0]), 1);
-      mbar_init(smem_u32(&bars[warp][1]), 1);
+      mbar_init(smem_addr_of(&bars[warp][0]), 1);
+      mbar_init(smem_addr_of(&bars[warp][1]), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -156,9 +158,9 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
       if constexpr (kTma) {
         __syncwarp();  // every lane has finished reading the buffer that is overwritten
         if (lane == 0) {
-          const u32 bar = smem_u32(&bars[warp][buf]);
+          const u32 bar = smem_addr_of(&bars[warp][buf]);
           mbar_expect_tx(bar, kRowBatch * 512u);
-          tma_load_box(smem_u32(&stage[buf][0][0]), &tmap, cg * 256, r0, p, bar);
+          tma_box_3d(smem_addr_of(&stage[buf][0][0]), &tmap, cg * 256, r0, p, bar);
         }
       } else {
       // fallback (unaligned strides, planes smaller than a box): the lane copies what it will read back itself
@@ -180,8 +182,8 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
     };
     auto wait_for = [&](int buf, bool more_in_flight) {
       if (kTma) {
-        if (buf == 0) { mbar_wait(smem_u32(&bars[warp][0]), parity0); parity0 ^= 1u; }
-        else { mbar_wait(smem_u32(&bars[warp][1]), parity1); parity1 ^= 1u; }
+        if (buf == 0) { mbar_wait(smem_addr_of(&bars[warp][0]), parity0); parity0 ^= 1u; }
+        else { mbar_wait(smem_addr_of(&bars[warp][1]), parity1); parity1 ^= 1u; }
       } else if (more_in_flight) {
         cp_async_wait<1>();
       } else {
@@ -191,6 +193,7 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
 
     Piece cur;
     cur.label = 0; cur.n = 0; cur.sum_row = 0; cur.sum_col = 0; cur.rmin = 0; cur.rmax = 0; cur.cmask = 0;
+    BitCol cur_bits{nullptr, 0};  // the tracked object's bitmap column for this strip
     issue(r_begin, 0);
     int buf = 0;
 #pragma unroll 1
@@ -209,6 +212,7 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
           if (cur.label) {
             cur.n += 8u; cur.sum_row += 8u * (r + 1u); cur.sum_col += 8u * c0 + 36u;
             cur.cmask = 0xFFu; cur.rmax = r;
+            if (kBits) bitmap_or(cur_bits, r, 0xFFu);
           }
           continue;
         }
@@ -220,6 +224,7 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
             cur.n += k; cur.sum_row += k * (r + 1u); cur.sum_col += k * (c0 + 1u) + bitpos_sum8(m);
             cur.cmask |= m; cur.rmax = r;
             rest &= ~m;
+            if (kBits) bitmap_or(cur_bits, r, m);
           } else {  // the object ended above this row
             emit_piece(recs, base, n_labels, cur, c0, err);
             cur.label = 0;
@@ -234,7 +239,12 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
           Piece np;
           np.label = lbl; np.n = k; np.sum_row = k * (r + 1u); np.sum_col = k * (c0 + 1u) + bitpos_sum8(m);
           np.rmin = r; np.rmax = r; np.cmask = m;
-          if (cur.label == 0) cur = np;                           // becomes the tracked object
+          BitCol bits{nullptr, 0};
+          if (kBits) {
+            bits = bitmap_col(bitmaps, base, n_labels, n_objects, lbl, c0);
+            bitmap_or(bits, r, m);
+          }
+          if (cur.label == 0) { cur = np; cur_bits = bits; }      // becomes the tracked object
           else emit_piece(recs, base, n_labels, np, c0, err);     // second object in the strip: per-row piece
           rest &= ~m;
         }
@@ -261,18 +271,33 @@ __global__ void background_count_kernel(abx_object_rec* __restrict__ recs, const
   }
 }
 
+// per-plane maximum label: one warp per row at a time, 128-bit loads when the layout allows
 __global__ void label_max_kernel(const uint16_t* __restrict__ labels, int n_planes, int H, int W, i64 plane_stride,
-                                 i64 row_stride, int32_t* out_max) {
+                                 i64 row_stride, int vec_ok, int32_t* out_max) {
   // grid: (blocks_per_plane, n_planes); out_max zeroed by the caller
   const int p = blockIdx.y;
-  const i64 n = (i64)H * W;
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  const u32 lane = lane_id();
+  const uint16_t* plane = labels + (i64)p * plane_stride;
   u32 m = 0;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-    const i64 r = i / W, c = i - r * W;
-    m = max(m, (u32)__ldg(labels + (i64)p * plane_stride + r * row_stride + c));
+  for (int r = blockIdx.x * warps + warp; r < H; r += gridDim.x * warps) {
+    const uint16_t* row = plane + (i64)r * row_stride;
+    int c = 0;
+    if (vec_ok) {
+      u32 a = 0, b = 0;
+      for (c = (int)lane * 8; c + 8 <= W; c += 256) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + c));
+        a = __vmaxu2(a, __vmaxu2(q.x, q.y));
+        b = __vmaxu2(b, __vmaxu2(q.z, q.w));
+      }
+      a = __vmaxu2(a, b);
+      m = max(m, max(a & 0xFFFFu, a >> 16));
+      c = W & ~7;  // the ragged tail below
+    }
+    for (int x = c + (int)lane; x < W; x += 32) m = max(m, (u32)__ldg(row + x));
   }
   m = __reduce_max_sync(0xFFFFFFFFu, m);
-  if (lane_id() == 0 && m) atomicMax(out_max + p, (int32_t)m);
+  if (lane == 0 && m) atomicMax(out_max + p, (int32_t)m);
 }
 
 }  // namespace
@@ -280,17 +305,7 @@ __global__ void label_max_kernel(const uint16_t* __restrict__ labels, int n_plan
 // The tensor map of the label planes (u16, dims W x H x P, box 256 x kRowBatch x 1), or false when the layout
 // does not qualify for TMA (unaligned base / strides, planes smaller than one box) or the driver lacks the encoder.
 static bool make_label_tensor_map(const abx_extract_args* a, CUtensorMap* tm) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      fn = nullptr;
-    return reinterpret_cast<EncodeFn>(fn);
-  }();
+  EncodeFn encode = tensor_map_encoder();
   if (!encode) return false;
   const i64 plane_stride = a->n_planes > 1 ? a->label_plane_stride : (i64)a->H * a->label_row_stride;
   if ((reinterpret_cast<uintptr_t>(a->labels) & 15u) || a->label_row_stride % 8 || plane_stride % 8 || a->W < 256 ||
@@ -305,9 +320,14 @@ static bool make_label_tensor_map(const abx_extract_args* a, CUtensorMap* tm) {
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, cudaStream_t st) {
+// bitmaps: [n_objects + 1][64] u64 torus bitmaps (the last one is a dummy for out-of-range labels), or nullptr
+int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, u64* bitmaps, cudaStream_t st) {
   const int n_rec = a->n_objects + a->n_planes;
   init_records_kernel<<<(n_rec + 255) / 256, 256, 0, st>>>(recs, a->n_objects, a->n_planes, a->H, a->W, err);
+  if (bitmaps) {
+    cudaError_t e = cudaMemsetAsync(bitmaps, 0, ((size_t)a->n_objects + 1) * 512, st);
+    if (e != cudaSuccess) return abx_check_cuda(e, "bitmap memset");
+  }
   const i64 units = (i64)a->n_planes * ((a->H + kBandRows - 1) / kBandRows) * ((a->W + 255) / 256);
   if (units == 0) return abx_check_cuda(cudaGetLastError(), "init_records");
   i64 blocks = (units + kScanWarps - 1) / kScanWarps;
@@ -317,14 +337,16 @@ int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err,
                      (a->label_plane_stride % 8 == 0);
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  if (make_label_tensor_map(a, &tm))
-    label_scan_kernel<true><<<(int)blocks, kScanThreads, 0, st>>>(
-        tm, static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,
-        a->plane_base, recs, a->n_objects, vec_ok, err);
-  else
-    label_scan_kernel<false><<<(int)blocks, kScanThreads, 0, st>>>(
-        tm, static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,
-        a->plane_base, recs, a->n_objects, vec_ok, err);
+  const bool tma = make_label_tensor_map(a, &tm);
+#define ABX_SCAN(TMA, BITS)                                                                                              \
+  label_scan_kernel<TMA, BITS><<<(int)blocks, kScanThreads, 0, st>>>(                                                     \
+      tm, static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,  \
+      a->plane_base, recs, a->n_objects, vec_ok, err, bitmaps)
+  if (tma && bitmaps) ABX_SCAN(true, true);
+  else if (tma) ABX_SCAN(true, false);
+  else if (bitmaps) ABX_SCAN(false, true);
+  else ABX_SCAN(false, false);
+#undef ABX_SCAN
   if (a->with_background)
     background_count_kernel<<<a->n_planes, 256, 0, st>>>(recs, a->plane_base, a->n_objects, a->H, a->W);
   return abx_check_cuda(cudaGetLastError(), "label_scan");
@@ -339,10 +361,11 @@ extern "C" int abx_label_max(const void* labels, int32_t label_dtype, int32_t n_
   if (n_planes == 0) return ABX_OK;
   cudaError_t e = cudaMemsetAsync(out_max, 0, sizeof(int32_t) * n_planes, st);
   if (e != cudaSuccess) return abx_check_cuda(e, "label_max memset");
-  const i64 n = (i64)H * W;
-  int bx = (int)min((i64)64, (n + 1023) / 1024);
+  int bx = (H + 7) / 8;  // 8 warps per CTA, a row per warp at a time
+  if (bx > 64) bx = 64;
   dim3 grid(bx < 1 ? 1 : bx, n_planes);
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(labels) & 15u) == 0) && (row_stride % 8 == 0) && (plane_stride % 8 == 0);
   label_max_kernel<<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(labels), n_planes, H, W, plane_stride,
-                                         row_stride, out_max);
+                                         row_stride, vec_ok, out_max);
   return abx_check_cuda(cudaGetLastError(), "label_max");
 }

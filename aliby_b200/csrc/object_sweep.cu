@@ -1,0 +1,815 @@
+// Per-object intensity statistics, ONE SWEEP per (object, request): one warp per object in its own single-warp CTA,
+// the object's pixel window staged by TMA (cp.async.bulk.tensor boxes of 8 rows, mbarrier completion), the object's
+// pixels addressed through a list built from the 64 x 64 torus bitmap the label scan wrote (label_scan.cu) — the label
+// planes are not read here at all.  Same outputs and reference semantics as before
+// (src/extraction/extract.py:346-359 loop; cell.py:43-157,232-265; tile crop of tiler.py:309-366 fused through the
+// tile offset).
+//
+//   plan kernel   one thread per object: window geometry and TMA coordinates (ObjPlan), the work order (big objects
+//                 first), zero records for absent labels, hand-over lists for what this kernel does not take
+//                 (windows above 64 x 64 and backgrounds -> object_stats.cu; windows too wide at their alignment ->
+//                 object_stats_warp), and the same routing for the shape kernel (object_edt.cu)
+//   sweep kernel  slot of 16.5 KB per CTA, 13 CTAs per SM:
+//                   flex: window chunk [rows][pitch] PX | list u16[n]   (list entry = SHARED ADDRESS of the pixel)
+//                   hist u32[1024], 4 KB aligned in the shared window (bin address = base | (v << 2) & 0xFFC)
+//                   scratch u32[32], mbarrier
+//                 per request ONE pass over the list: moments, extrema and a histogram of the LOW 10 BITS of every
+//                 value.  When max - min < 1021 (checked afterwards) that circular histogram is exact — bin
+//                 (v & 1023) holds one value only — and the four ranks (two medians, top 2.5 %, top 5) come out of
+//                 it by warp scans; wider ranges take a coarse histogram + 7-bit refinement sweeps on the window
+//                 that is still resident.  The TMA copy of the NEXT window (next request, or first request of the
+//                 warp's next object) is issued right after the sweep, so that it runs under the rank search, and
+//                 the window after that one is prefetched into L2 by cp.async.bulk.prefetch.tensor.
+//                 Windows that do not fit the flex area next to their list are swept in row chunks.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+#include "warp_common.cuh"
+#include "tma.cuh"
+
+constexpr u32 kSwSlot = 16896;   // dynamic shared memory per single-warp CTA: 13 CTAs (+ 1 KB reserved each) per SM
+constexpr int kSwCtasPerSm = 13;
+constexpr u32 kBigFirst = 1536;  // objects above this many pixels are processed first
+constexpr int kMaxPitch = 8;     // tensor maps for box widths of 16, 32, ... 128 bytes
+
+struct SweepMaps {
+  CUtensorMap px[kMaxPitch];  // the pixel buffer as rows of row_stride elements, box (16 * (i + 1)) bytes x 8 rows
+};
+
+// ---- shared-memory accessors on 32-bit shared addresses (no generic-pointer arithmetic in the hot loops) ----
+__device__ __forceinline__ u32 lds_u16(u32 a) { u32 v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+template <int kOff>
+__device__ __forceinline__ u32 lds_u16_off(u32 a) {
+  u32 v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(kOff));
+  return v;
+}
+__device__ __forceinline__ u32 lds_u8(u32 a) { u32 v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u16(u32 a, u32 v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+template <typename PX>
+__device__ __forceinline__ u32 lds_px(u32 a) { return sizeof(PX) == 1 ? lds_u8(a) : lds_u16(a); }
+
+// ------------------------------------------------------------------------------------------------
+// plan kernel
+// ------------------------------------------------------------------------------------------------
+// Appends `item` to a list that is filled from the front (front = true) or from the back, one atomic per warp.
+__device__ __forceinline__ void append(bool want, bool front, int item, int* __restrict__ list, int cap, u32* cnt_front,
+                                       u32* cnt_back) {
+  const u32 lane = lane_id();
+  const u32 mf = __ballot_sync(kFull, want && front), mb = __ballot_sync(kFull, want && !front);
+  u32 bf = 0, bb = 0;
+  if (lane == 0) {
+    if (mf) bf = atomicAdd(cnt_front, (u32)__popc(mf));
+    if (mb) bb = atomicAdd(cnt_back, (u32)__popc(mb));
+  }
+  bf = __shfl_sync(kFull, bf, 0);
+  bb = __shfl_sync(kFull, bb, 0);
+  const u32 lt = (1u << lane) - 1u;
+  if (want && front) list[bf + (u32)__popc(mf & lt)] = item;
+  if (want && !front) list[cap - 1 - (int)(bb + (u32)__popc(mb & lt))] = item;
+}
+
+struct PlanArgs {
+  const abx_object_rec* recs;
+  const int32_t* plane_base;
+  const int32_t* plane_tile;
+  const i64* tile_offset;
+  int n_planes, n_objects, n_total;
+  i64 row_stride;
+  int align;       // elements per 16 bytes of the pixel dtype
+  int n_requests;
+  int sweep;       // the sweep kernel takes the statistics (otherwise object_stats_warp does its own bookkeeping)
+  int need_edt;
+  ChanStats* chan;
+  ShapeStats* shape;
+  ObjPlan* plan;
+  int* order_stats;
+  int* order_edt;
+  int* stats_list;  // hand-over to the CTA-per-object statistics kernel
+  int* pair_list;   // (object, request) pairs for object_stats_warp
+  int* edt_list;    // hand-over to the CTA-per-object shape kernel
+  u32* counts;      // Workspace::list_counts
+};
+
+__global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < a.n_total;
+  abx_object_rec rec;
+  rec.n = 0; rec.rmin = rec.rmax = rec.cmin = rec.cmax = 0;
+  if (live) rec = a.recs[i];
+  const bool is_bg = i >= a.n_objects;
+  const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
+  const bool windowed = live && rec.n > 0 && !is_bg && h <= kSide && w <= kSide;
+  // ---- statistics ----
+  if (a.sweep) {
+    bool take = false, too_wide = false;
+    if (live && rec.n == 0) {  // absent label (or empty background): zero records -> NaN in finalize
+      ChanStats z;
+      z.sum = z.sumsq = z.wrapsq = z.m10 = z.m01 = z.m20 = z.m02 = z.top2p5_sum = z.top5_sum = 0;
+      z.vmin = z.vmax = z.med_lo = z.med_hi = 0;
+      for (int q = 0; q < a.n_requests; ++q) a.chan[(i64)i * a.n_requests + q] = z;
+    }
+    if (windowed) {
+      const int p = find_plane(a.plane_base, a.n_planes, i);
+      const i64 org = a.tile_offset[a.plane_tile[p]] + (i64)rec.rmin * a.row_stride + rec.cmin;
+      const i64 row0 = org / a.row_stride;
+      const int col0 = (int)(org - row0 * a.row_stride);
+      const u32 s_px = (u32)col0 & (u32)(a.align - 1);
+      if (org < 0 || (u32)w + s_px > (u32)kSide) {
+        too_wide = true;  // (or a window that starts in front of the buffer): the gather kernel addresses anything
+      } else {
+        ObjPlan pl;
+        pl.tma_x = col0 - (int)s_px;
+        pl.tma_y = (int)row0;
+        pl.n = rec.n;
+        pl.geom = (u32)(h - 1) | ((u32)(w - 1) << 6) | ((rec.rmin & 63u) << 12) | ((rec.cmin & 63u) << 18) | (s_px << 24);
+        a.plan[i] = pl;
+        take = true;
+      }
+    }
+    append(take, rec.n > kBigFirst, i, a.order_stats, a.n_total, a.counts + kCntOrderBig, a.counts + kCntOrderSmall);
+    const bool hand = live && rec.n > 0 && !windowed;
+    {
+      const u32 m = __ballot_sync(kFull, hand);
+      u32 b = 0;
+      if (lane_id() == 0 && m) b = atomicAdd(a.counts + kCntStatsList, (u32)__popc(m));
+      b = __shfl_sync(kFull, b, 0);
+      if (hand) a.stats_list[b + (u32)__popc(m & ((1u << lane_id()) - 1u))] = i;
+    }
+    if (too_wide) {
+      const u32 b = atomicAdd(a.counts + kCntLeftover, (u32)a.n_requests);  // rare: no aggregation
+      for (int q = 0; q < a.n_requests; ++q) a.pair_list[b + q] = i * a.n_requests + q;
+    }
+  }
+  // ---- shape ----
+  if (a.need_edt) {
+    const bool obj = live && !is_bg;
+    if (obj && rec.n == 0) {
+      ShapeStats z;
+      z.sum_nn = 0; z.sum_top = 0; z.max_nn2 = 0; z.max_dn2 = 0;
+      a.shape[i] = z;
+    }
+    const bool take = obj && rec.n > 0 && h <= kSide && w <= kSide;
+    append(take, rec.n > kBigFirst, i, a.order_edt, a.n_objects, a.counts + kCntEdtBig, a.counts + kCntEdtSmall);
+    const bool hand = obj && rec.n > 0 && !take;
+    if (hand) a.edt_list[atomicAdd(a.counts + kCntEdtList, 1u)] = i;  // rare
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep kernel
+// ------------------------------------------------------------------------------------------------
+struct Geo {  // one object's window as the kernel sees it (warp-uniform)
+  int obj;
+  int tma_x, tma_y;  // box coordinates of the window in channel 0
+  u32 n, h, w, s_px;
+  u32 rot, row0;     // bitmap rotation (columns) and first bitmap row
+  u32 pitchB, pidx;  // window row pitch in bytes (a multiple of 16), tensor map index
+  u32 h8, R;         // rows rounded up to whole boxes; rows per chunk (a multiple of 8; == h8: one chunk)
+  u32 list_bytes;
+};
+
+template <typename PX>
+__device__ __forceinline__ Geo make_geo(const ObjPlan& pl, int obj, u32 flex_bytes) {
+  Geo g;
+  g.obj = obj;
+  g.tma_x = pl.tma_x; g.tma_y = pl.tma_y;
+  g.n = pl.n;
+  g.h = (pl.geom & 63u) + 1u;
+  g.w = ((pl.geom >> 6) & 63u) + 1u;
+  g.row0 = (pl.geom >> 12) & 63u;
+  g.s_px = pl.geom >> 24;
+  g.rot = (((pl.geom >> 18) & 63u) - g.s_px) & 63u;
+  g.pitchB = ((g.w + g.s_px) * (u32)sizeof(PX) + 15u) & ~15u;
+  g.pidx = (g.pitchB >> 4) - 1u;
+  g.h8 = (g.h + 7u) & ~7u;
+  g.list_bytes = ((g.n + 1u) & ~1u) * 2u;
+  g.R = g.h8;
+  if (g.h8 * g.pitchB + g.list_bytes > flex_bytes) g.R = ((flex_bytes - g.list_bytes) / g.pitchB) & ~7u;
+  return g;
+}
+
+struct Acc {  // per-lane partial sums of one request
+  u32 sum, wh, vmin, vmax, m10, m01;
+  u64 sq, q;
+};
+
+template <typename PX, bool kWrap>
+__device__ __forceinline__ void accumulate(Acc& a, u32 v, u32 hbase) {
+  constexpr int kShift = (sizeof(PX) == 1) ? 12 : 8;  // (x << kShift)^2 >> 32 == x^2 >> bits(PX)
+  a.sum += v;
+  a.sq += (u64)v * (u64)v;
+  if (kWrap) {
+    const u32 s = v << kShift;
+    a.wh += __umulhi(s, s);
+  }
+  a.vmin = min(a.vmin, v);
+  a.vmax = max(a.vmax, v);
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase | ((v << 2) & 0xFFCu)) : "memory");
+}
+
+// moment-of-inertia terms of one pixel: (r, c) are window coordinates recovered from the entry's offset inside the window
+template <typename PX>
+__device__ __forceinline__ void accumulate_moi(Acc& a, u32 v, u32 off, u32 inv_pitch, u32 pitchB) {
+  // off = r * pitchB + c * sizeof(PX), off < 8192: r = off / pitchB by a reciprocal multiply, inv = 2^32 / pitchB + 1
+  // (exact for off < 2^13 and pitchB = 16, 32 ... 128: checked exhaustively in tests/test_host_logic.py)
+  const u32 r = __umulhi(off, inv_pitch);
+  const u32 c = (off - r * pitchB) >> (sizeof(PX) == 1 ? 0 : 1);
+  a.m10 += v * c;
+  a.m01 += v * r;
+  a.q += (u64)v * (u64)(c * c + r * r);
+}
+
+// One pass over list entries [first, first + cnt) (shared addresses of the object's pixels inside the resident window
+// chunk): blocks of 128 entries unpredicated, the last partial block predicated.  win_base: the shared address window
+// row 0 WOULD have (rows of later chunks count on from the rows before them), for the moment-of-inertia coordinates.
+template <typename PX, bool kMoi, bool kWrap>
+__device__ __forceinline__ void sweep_chunk(Acc& a, u32 list_addr, u32 cnt, u32 hbase, u32 win_base, u32 inv_pitch, u32 pitchB) {
+  const u32 lane = lane_id();
+  u32 p = list_addr + 2u * lane;
+  const u32 pend = list_addr + 2u * (cnt & ~127u);
+  if (p < pend) {
+    // three-stage software pipeline: entries of block i + 1 and pixels of block i are loaded while block i - 1 is added up
+    u32 k[4], v[4], kn[4];
+    k[0] = lds_u16_off<0>(p); k[1] = lds_u16_off<64>(p); k[2] = lds_u16_off<128>(p); k[3] = lds_u16_off<192>(p);
+    p += 256u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = lds_px<PX>(k[u]);
+#pragma unroll 2
+    while (p < pend) {
+      kn[0] = lds_u16_off<0>(p); kn[1] = lds_u16_off<64>(p); kn[2] = lds_u16_off<128>(p); kn[3] = lds_u16_off<192>(p);
+      p += 256u;
+      u32 vn[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vn[u] = lds_px<PX>(kn[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        accumulate<PX, kWrap>(a, v[u], hbase);
+        if (kMoi) accumulate_moi<PX>(a, v[u], k[u] - win_base, inv_pitch, pitchB);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { k[u] = kn[u]; v[u] = vn[u]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      accumulate<PX, kWrap>(a, v[u], hbase);
+      if (kMoi) accumulate_moi<PX>(a, v[u], k[u] - win_base, inv_pitch, pitchB);
+    }
+  }
+  // the last partial block
+  const u32 rem = cnt & 127u;
+  if (rem) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (lane + 32u * u < rem) {
+        const u32 k = lds_u16(pend + 2u * (lane + 32u * u));
+        const u32 v = lds_px<PX>(k);
+        accumulate<PX, kWrap>(a, v, hbase);
+        if (kMoi) accumulate_moi<PX>(a, v, k - win_base, inv_pitch, pitchB);
+      }
+    }
+  }
+}
+
+// Locate four ranks in the circular histogram: relative bin j lives at h[(j + rot) & 1023], rot a multiple of 4, bins
+// [nb, 1024) relative are zero.  Same scheme and outputs as find_ranks32 (warp_common.cuh).
+__device__ __forceinline__ void find_ranks_rot(const u32* h, u32 rot, u32 nb, const u32 (&ranks)[4], u32* t) {
+  const u32 lane = lane_id();
+  const u32 per = bins_per_lane(nb);
+  const u32 b0 = lane * per;
+  u32 cnt = 0, cb = 0;
+#pragma unroll 1
+  for (u32 k = 0; k < per; k += 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(h + ((b0 + k + rot) & 1023u));
+    const uint4 w = *reinterpret_cast<const uint4*>(h + ((b0 + k + 4u + rot) & 1023u));
+    const u32 sv = v.x + v.y + v.z + v.w, sw = w.x + w.y + w.z + w.w;
+    cnt += sv + sw;
+    cb += (b0 + k) * (sv + sw) + v.y + 2u * v.z + 3u * v.w + 4u * sw + w.y + 2u * w.z + 3u * w.w;
+  }
+  u32 icnt = cnt, icb = cb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 c = __shfl_up_sync(kFull, icnt, o);
+    const u32 q = __shfl_up_sync(kFull, icb, o);
+    if (lane >= (u32)o) { icnt += c; icb += q; }
+  }
+  const u32 ecnt = icnt - cnt, ecb = icb - cb;
+  const u32 grp = lane >> 3, sub = lane & 7u;
+  u32 own = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u32 o = (u32)__ffs(__ballot_sync(kFull, ranks[j] >= ecnt && ranks[j] < ecnt + cnt)) - 1u;
+    if (grp == (u32)j) own = o;
+  }
+  const u32 tr = grp == 0 ? ranks[0] : (grp == 1 ? ranks[1] : (grp == 2 ? ranks[2] : ranks[3]));
+  const u32 e = __shfl_sync(kFull, ecnt, own), eb = __shfl_sync(kFull, ecb, own);
+  const u32 nper = per >> 3;              // bins per lane of the group: 1..4
+  const u32 lb = own * per + sub * nper;  // first (relative) bin of this lane
+  u32 c4[4], lc = 0, lq = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    c4[k] = ((u32)k < nper) ? h[(lb + k + rot) & 1023u] : 0u;
+    lc += c4[k];
+    lq += c4[k] * (lb + k);
+  }
+  u32 ic = lc, iq = lq;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const u32 a = __shfl_up_sync(kFull, ic, o, 8);
+    const u32 b = __shfl_up_sync(kFull, iq, o, 8);
+    if (sub >= (u32)o) { ic += a; iq += b; }
+  }
+  u32 acc = e + ic - lc, accq = eb + iq - lq;
+  if (tr >= acc && tr < acc + lc) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (tr >= acc && tr < acc + c4[k]) {
+        t[grp] = lb + k;        // key (relative bin)
+        t[4 + grp] = tr - acc;  // rank inside the bin
+        t[8 + grp] = acc;       // count below
+        t[12 + grp] = accq;     // sum(count * relative bin) below
+      }
+      acc += c4[k];
+      accq += c4[k] * (lb + k);
+    }
+  }
+  __syncwarp();
+}
+
+struct Ranked {
+  u32 med_lo, med_hi;
+  u64 top2p5_sum, top5_sum;
+};
+
+// Order statistics of a request whose values span more than the circular histogram resolves: coarse histogram of
+// (v - vmin) >> s0, then 7 more bits per sweep inside the four target bins (the window is still resident).
+template <typename PX>
+__device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32 vmax, u64 sum, u32 feats, u32* hist, u32* t,
+                                             const u32 (&ranks)[4]) {
+  const u32 lane = lane_id();
+  const u32 range = vmax - vmin;
+  int s0 = 0;
+  while ((range >> s0) >= 1024u) ++s0;
+  const u32 nb = (range >> s0) + 1;
+  __syncwarp();
+  hist_zero(hist, 1024u);
+  __syncwarp();
+#pragma unroll 1
+  for (u32 i = lane; i < n; i += 32) hist_add(hist, (lds_px<PX>(lds_u16(list_addr + 2u * i)) - vmin) >> s0);
+  __syncwarp();
+  find_ranks32(hist, nb, ranks, t);
+  int cur = s0;
+  u32 key[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) key[j] = t[j];
+#pragma unroll 1
+  while (cur > 0) {
+    const int nxt = cur > 7 ? cur - 7 : 0;
+    const u32 nsub = 1u << (cur - nxt);
+    __syncwarp();
+    hist_zero(hist, 512u);
+    __syncwarp();
+#pragma unroll 1
+    for (u32 i = lane; i < n; i += 32) {
+      const u32 d = lds_px<PX>(lds_u16(list_addr + 2u * i)) - vmin;
+      const u32 hi = d >> cur;
+      const u32 sb = (d >> nxt) & (nsub - 1u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (hi == key[j]) hist_add(hist, 128u * j + sb);
+    }
+    __syncwarp();
+    find_ranks32_x4(hist, t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) key[j] = (key[j] << (cur - nxt)) | t[j];
+    cur = nxt;
+  }
+  Ranked r;
+  r.med_lo = vmin + key[0]; r.med_hi = vmin + key[1];
+  const u32 v2 = vmin + key[2], v3 = vmin + key[3];
+  u64 below2 = 0, below3 = 0;
+  if (feats & (ABX_F_TOP2P5 | ABX_F_TOP5)) {
+    u64 sb2 = 0, sb3 = 0;
+    u32 cb2 = 0, cb3 = 0;
+#pragma unroll 1
+    for (u32 i = lane; i < n; i += 32) {
+      const u32 x = lds_px<PX>(lds_u16(list_addr + 2u * i));
+      if (x < v2) { sb2 += x; ++cb2; }
+      if (x < v3) { sb3 += x; ++cb3; }
+    }
+    sb2 = warp_sum64(sb2); sb3 = warp_sum64(sb3);
+    cb2 = __reduce_add_sync(kFull, cb2); cb3 = __reduce_add_sync(kFull, cb3);
+    below2 = sb2 + (u64)(ranks[2] - cb2) * (u64)v2;
+    below3 = sb3 + (u64)(ranks[3] - cb3) * (u64)v3;
+  }
+  r.top2p5_sum = sum - below2;
+  r.top5_sum = sum - below3;
+  __syncwarp();
+  hist_zero(hist, 1024u);  // the next sweep expects a clean circular histogram
+  __syncwarp();
+  return r;
+}
+
+// One TMA load = the rows [c * R, c * R + rows) of the window of request channel `chan`.
+struct LoadDesc {
+  int x, y;      // box coordinates of the first box
+  u32 rows;      // a multiple of 8; 0 = no load
+  u32 pitchB, pidx;
+};
+
+template <typename PX>
+__global__ void __launch_bounds__(32, kSwCtasPerSm)
+object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__ plan, const int* __restrict__ order,
+             const u32* __restrict__ order_counts /* [0] big, [1] small */, int n_total, u32* __restrict__ work_counter,
+             const u64* __restrict__ bitmaps, int chan_rows, const abx_request* __restrict__ requests, int n_requests,
+             ChanStats* __restrict__ chan, int* __restrict__ pair_list, u32* __restrict__ pair_count, int split_log2) {
+  const u32 lane = lane_id();
+  const u32 sbase = smem_addr_of(dyn);
+  // layout inside the slot (shared addresses): flex [sbase, hist) | hist 4 KB, 4 KB aligned | scratch, mbarrier
+  u32 hbase = (sbase + kSwSlot - 4096u) & ~4095u;
+  if (((sbase + kSwSlot) & 4095u) < 256u) hbase -= 4096u;
+  const u32 flex_bytes = hbase - sbase;
+  u32* hist = reinterpret_cast<u32*>(dyn + (hbase - sbase));
+  u32* t = reinterpret_cast<u32*>(dyn + (hbase + 4096u - sbase));
+  const u32 bar = hbase + 4096u + 128u;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  hist_zero(hist, 1024u);
+  __syncwarp();
+  u32 parity = 0;
+
+  const u32 n_big = order_counts[0], n_small = order_counts[1];
+  const int n_items = (int)(n_big + n_small) << split_log2;
+  const int split = 1 << split_log2;
+  auto fetch = [&]() {
+    int v = 0;
+    if (lane == 0) v = (int)atomicAdd(work_counter, 1u);
+    return __shfl_sync(kFull, v, 0);
+  };
+  // work item -> object: the big objects from the front of the order array, then the others from its back
+  auto object_of = [&](int item) {
+    const u32 idx = (u32)(item >> split_log2);
+    return order[idx < n_big ? (int)idx : n_total - 1 - (int)(idx - n_big)];
+  };
+  // first / next request of a work item that this kernel computes (div requests belong to object_float.cu)
+  auto next_request = [&](int q, int q_hi) {
+    while (q < q_hi && requests[q].reduction == ABX_RED_DIV) ++q;
+    return q;
+  };
+  auto item_requests = [&](int item, int& q_lo, int& q_hi) {
+    const int part = item & (split - 1);
+    q_lo = (part * n_requests) >> split_log2;
+    q_hi = ((part + 1) * n_requests) >> split_log2;
+  };
+  auto make_load = [&](const Geo& g, int q, u32 c) {
+    LoadDesc d;
+    d.x = g.tma_x;
+    d.y = g.tma_y + requests[q].channel * chan_rows + (int)(c * g.R);
+    d.rows = min(g.R, g.h8 - c * g.R);
+    d.pitchB = g.pitchB; d.pidx = g.pidx;
+    return d;
+  };
+  auto issue = [&](const LoadDesc& d) {  // by lane 0, after every lane is done with the window
+    if (lane == 0 && d.rows) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, d.rows * d.pitchB);
+      const u32 box = 8u * d.pitchB;
+      u32 dst = sbase;
+      for (u32 j = 0; j < d.rows; j += 8, dst += box) tma_box_2d(dst, &maps.px[d.pidx], d.x, d.y + (int)j, bar);
+    }
+  };
+  auto prefetch = [&](const LoadDesc& d) {
+#ifndef ABX_NO_PREFETCH
+    if (lane == 0 && d.rows)
+      for (u32 j = 0; j < d.rows; j += 8) tma_prefetch_2d(&maps.px[d.pidx], d.x, d.y + (int)j);
+#endif
+  };
+
+  int item = fetch();
+  int nxt_item = item < n_items ? fetch() : n_items;
+  Geo g, gn;
+  int q_lo = 0, q_hi = 0, nq_lo = 0, nq_hi = 0;
+  bool have = false;
+  if (item < n_items) {
+    const int obj = object_of(item);
+    g = make_geo<PX>(plan[obj], obj, flex_bytes);
+    item_requests(item, q_lo, q_hi);
+    q_lo = next_request(q_lo, q_hi);
+    have = true;
+    if (q_lo < q_hi) issue(make_load(g, q_lo, 0));
+  }
+  while (have) {
+    // the warp's next object (its first load is issued by this object's last sweep)
+    bool have_next = nxt_item < n_items;
+    if (have_next) {
+      const int nobj = object_of(nxt_item);
+      gn = make_geo<PX>(plan[nobj], nobj, flex_bytes);
+      item_requests(nxt_item, nq_lo, nq_hi);
+      nq_lo = next_request(nq_lo, nq_hi);
+    }
+    const int after_item = have_next ? fetch() : n_items;
+
+    if (q_lo < q_hi) {
+      // ---- pixel list from the torus bitmap (while the first window is in flight) ----
+      const u32 win_base = sbase;
+      const u32 list_addr = sbase + g.R * g.pitchB;
+      const u64* bm = bitmaps + (size_t)g.obj * 64u;
+      u64 m0 = bm[(g.row0 + lane) & 63u], m1 = bm[(g.row0 + lane + 32u) & 63u];
+      m0 = (m0 >> g.rot) | (g.rot ? (m0 << (64u - g.rot)) : 0ull);
+      m1 = (m1 >> g.rot) | (g.rot ? (m1 << (64u - g.rot)) : 0ull);
+      const u32 c0 = (u32)__popcll(m0), c1 = (u32)__popcll(m1);
+      u32 i0 = c0, i1 = c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(kFull, i0, o), b = __shfl_up_sync(kFull, i1, o);
+        if (lane >= (u32)o) { i0 += a; i1 += b; }
+      }
+      const u32 tot0 = __shfl_sync(kFull, i0, 31);
+      const u32 base0 = i0 - c0, base1 = tot0 + i1 - c1;  // list position of the first pixel of rows lane, lane + 32
+      const bool multi = g.R < g.h8;
+      {
+        // row r of chunk r / R: entry = shared address of its pixel inside the chunk buffer
+        const u32 r0 = lane, r1 = lane + 32u;
+        const u32 rr0 = multi ? r0 % g.R : r0, rr1 = multi ? r1 % g.R : r1;
+        const u32 a0 = m0 ? (u32)__ffsll((long long)m0) - 1u : 0u, a1 = m1 ? (u32)__ffsll((long long)m1) - 1u : 0u;
+        const u64 run0 = m0 >> a0, run1 = m1 >> a1;
+        const bool single = ((run0 & (run0 + 1ull)) == 0ull) && ((run1 & (run1 + 1ull)) == 0ull);
+        if (__all_sync(kFull, single)) {
+          // one run per row (convex cells): the row's entries are consecutive addresses
+          u32 p = list_addr + 2u * base0, v = win_base + rr0 * g.pitchB + a0 * (u32)sizeof(PX);
+          const u32 e0 = p + 2u * c0;
+          const u32 it0 = __reduce_max_sync(kFull, c0);
+#pragma unroll 4
+          for (u32 it = 0; it < it0; ++it) {
+            if (p < e0) sts_u16(p, v);
+            p += 2u; v += (u32)sizeof(PX);
+          }
+          if (g.h > 32u) {
+            p = list_addr + 2u * base1; v = win_base + rr1 * g.pitchB + a1 * (u32)sizeof(PX);
+            const u32 e1 = p + 2u * c1;
+            const u32 it1 = __reduce_max_sync(kFull, c1);
+#pragma unroll 4
+            for (u32 it = 0; it < it1; ++it) {
+              if (p < e1) sts_u16(p, v);
+              p += 2u; v += (u32)sizeof(PX);
+            }
+          }
+        } else {
+          // any shape: bit by bit
+          u64 mm = m0;
+          u32 p = list_addr + 2u * base0;
+          const u32 row_a0 = win_base + rr0 * g.pitchB;
+          while (__any_sync(kFull, mm != 0ull)) {
+            if (mm) {
+              const u32 b = (u32)__ffsll((long long)mm) - 1u;
+              mm &= mm - 1ull;
+              sts_u16(p, row_a0 + b * (u32)sizeof(PX));
+              p += 2u;
+            }
+          }
+          mm = m1;
+          p = list_addr + 2u * base1;
+          const u32 row_a1 = win_base + rr1 * g.pitchB;
+          while (__any_sync(kFull, mm != 0ull)) {
+            if (mm) {
+              const u32 b = (u32)__ffsll((long long)mm) - 1u;
+              mm &= mm - 1ull;
+              sts_u16(p, row_a1 + b * (u32)sizeof(PX));
+              p += 2u;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      const u32 inv_pitch = 0xFFFFFFFFu / g.pitchB + 1u;
+      const u32 n_chunks = multi ? (g.h8 + g.R - 1u) / g.R : 1u;
+
+#pragma unroll 1
+      for (int q = q_lo; q < q_hi;) {
+        const abx_request rq = requests[q];
+        const int q_next = next_request(q + 1, q_hi);
+        Acc a;
+        a.sum = a.wh = a.vmax = a.m10 = a.m01 = 0; a.vmin = kFull; a.sq = a.q = 0;
+        const bool want_moi = (rq.features & ABX_F_MOI) != 0, want_wrap = (rq.features & ABX_F_WRAPSQ) != 0;
+        const bool want_ranks = (rq.features & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) != 0;
+        u32 vmin = 0, vmax = 0;
+        Ranked rk;
+        rk.med_lo = rk.med_hi = 0; rk.top2p5_sum = rk.top5_sum = 0;
+        bool wide = false, wide_done = false;
+        u64 sum64 = 0;
+#pragma unroll 1
+        for (u32 c = 0; c < n_chunks; ++c) {
+          // entries of this chunk: rows [c R, (c + 1) R)
+          u32 first = 0, cnt = g.n;
+          if (multi) {
+            const u32 ra = c * g.R, rb = min(ra + g.R, 64u);
+            const u32 fa = __shfl_sync(kFull, ra < 32u ? base0 : base1, ra & 31u);
+            const u32 fb = rb >= 64u ? g.n : __shfl_sync(kFull, rb < 32u ? base0 : base1, rb & 31u);
+            first = fa; cnt = fb - fa;
+          }
+          mbar_wait(bar, parity);
+          parity ^= 1u;
+          const u32 la = list_addr + 2u * first;
+          const u32 wb = win_base - c * g.R * g.pitchB;  // (wraps below zero for later chunks: only differences are used)
+          if (want_moi) {
+            if (want_wrap) sweep_chunk<PX, true, true>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
+            else sweep_chunk<PX, true, false>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
+          } else {
+            if (want_wrap) sweep_chunk<PX, false, true>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
+            else sweep_chunk<PX, false, false>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
+          }
+          __syncwarp();
+          const bool last_chunk = c + 1u == n_chunks;
+          if (last_chunk) {
+            vmin = __reduce_min_sync(kFull, a.vmin);
+            vmax = __reduce_max_sync(kFull, a.vmax);
+            wide = want_ranks && vmax - (vmin & ~3u) > 1023u;
+            if (wide && !multi) {  // the window is still here: refine now, before it is overwritten
+              sum64 = (u64)__reduce_add_sync(kFull, a.sum);
+              const u32 k2p5 = (u32)ceil((double)g.n * 0.025), k5 = min(g.n, 5u);
+              const u32 ranks[4] = {(g.n - 1) / 2, g.n / 2, g.n - k2p5, g.n - k5};
+              rk = wide_ranks<PX>(list_addr, g.n, vmin, vmax, sum64, rq.features, hist, t, ranks);
+              wide_done = true;
+            }
+          }
+          // ---- the next window: next chunk, next request, or the first request of the warp's next object ----
+          LoadDesc nx, pf;
+          nx.rows = pf.rows = 0;
+          if (!last_chunk) {
+            nx = make_load(g, q, c + 1u);
+            if (c + 2u < n_chunks) pf = make_load(g, q, c + 2u);
+            else if (q_next < q_hi) pf = make_load(g, q_next, 0);
+          } else if (q_next < q_hi) {
+            nx = make_load(g, q_next, 0);
+            const int q2 = next_request(q_next + 1, q_hi);
+            if (n_chunks > 1u) pf = make_load(g, q_next, 1u);
+            else if (q2 < q_hi) pf = make_load(g, q2, 0);
+            else if (have_next && nq_lo < nq_hi) pf = make_load(gn, nq_lo, 0);
+          } else if (have_next && nq_lo < nq_hi) {
+            nx = make_load(gn, nq_lo, 0);
+            const int q2 = next_request(nq_lo + 1, nq_hi);
+            if (gn.R < gn.h8) pf = make_load(gn, nq_lo, 1u);
+            else if (q2 < nq_hi) pf = make_load(gn, q2, 0);
+          }
+          issue(nx);
+          prefetch(pf);
+        }
+        // ---- reductions (under the copy that was just issued) ----
+        ChanStats cs;
+        cs.sum = wide_done ? sum64 : (u64)__reduce_add_sync(kFull, a.sum);  // n * 65535 < 2^32
+        cs.sumsq = warp_sum64(a.sq);
+        constexpr int kShift = (sizeof(PX) == 1) ? 12 : 8;
+        cs.wrapsq = want_wrap ? cs.sumsq - ((u64)__reduce_add_sync(kFull, a.wh) << (32 - 2 * kShift)) : 0;
+        cs.m10 = cs.m01 = cs.m20 = cs.m02 = 0;
+        if (want_moi) {
+          // coordinates relative to the TMA box (column s_px = bbox column 0): central moments are translation invariant
+          cs.m10 = warp_sum64((u64)a.m10);
+          cs.m01 = warp_sum64((u64)a.m01);
+          cs.m20 = warp_sum64(a.q);  // m20 + m02 as one sum (finalize.cu)
+        }
+        cs.vmin = vmin; cs.vmax = vmax;
+        cs.med_lo = rk.med_lo; cs.med_hi = rk.med_hi;
+        cs.top2p5_sum = rk.top2p5_sum; cs.top5_sum = rk.top5_sum;
+        if (want_ranks && !wide) {
+          const u32 vbase = vmin & ~3u;
+          const u32 nb = vmax - vbase + 1u;
+          const u32 k2p5 = (u32)ceil((double)g.n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
+          const u32 k5 = min(g.n, 5u);
+          const u32 ranks[4] = {(g.n - 1) / 2, g.n / 2, g.n - k2p5, g.n - k5};
+          find_ranks_rot(hist, vbase & 1023u, nb, ranks, t);
+          cs.med_lo = vbase + t[0]; cs.med_hi = vbase + t[1];
+          const u32 v2 = vbase + t[2], v3 = vbase + t[3];
+          // sum of the smallest values up to the rank = vbase * cnt + sum(count * bin) below + rank * value
+          const u64 below2 = (u64)vbase * t[10] + t[14] + (u64)t[6] * v2;
+          const u64 below3 = (u64)vbase * t[11] + t[15] + (u64)t[7] * v3;
+          cs.top2p5_sum = cs.sum - below2;
+          cs.top5_sum = cs.sum - below3;
+        }
+        if (lane == 0) {
+          chan[(i64)g.obj * n_requests + q] = cs;
+          if (wide && !wide_done) pair_list[atomicAdd(pair_count, 1u)] = g.obj * n_requests + q;  // multi-chunk and wide: rare
+        }
+        __syncwarp();
+        if (!wide_done) {  // (wide_ranks leaves the histogram clean)
+          // only the bins that can be non-zero: relative [0, nb) rounded to whole uint4s, at most all 1024
+          hist_zero(hist, 1024u);
+          __syncwarp();
+        }
+        q = q_next;
+      }
+    } else if (have_next && nq_lo < nq_hi) {
+      issue(make_load(gn, nq_lo, 0));  // this item had no request for this kernel: start the next object's first window
+    }
+    g = gn; q_lo = nq_lo; q_hi = nq_hi;
+    have = have_next;
+    item = nxt_item;
+    nxt_item = after_item;
+  }
+}
+
+// The tensor maps, or false when the pixel layout does not qualify for TMA (the caller then takes object_stats_warp).
+bool make_maps(const abx_extract_args* a, SweepMaps* m) {
+  EncodeFn encode = tensor_map_encoder();
+  if (!encode || a->Z != 1 || a->pixel_elems <= 0) return false;
+  const size_t es = a->pixel_dtype == ABX_U8 ? 1 : 2;
+  if ((reinterpret_cast<uintptr_t>(a->pixels) & 15u) || (a->row_stride * (i64)es) % 16 || a->row_stride * (i64)es < 128 ||
+      a->chan_stride % a->row_stride || a->chan_stride / a->row_stride > 0x7FFFFFFF / (a->C > 0 ? a->C : 1))
+    return false;
+  const i64 rows = a->pixel_elems / a->row_stride;  // whole rows inside the caller's buffer
+  if (rows < 8 || rows > 0x7FFFFFFF) return false;
+  const cuuint32_t estr[2] = {1u, 1u};
+  for (int i = 0; i < kMaxPitch; ++i) {
+    const cuuint32_t bw = (cuuint32_t)(16u * (i + 1) / es);
+    if (bw > (cuuint32_t)(64 * 2 / es) && es == 1) {}  // (u8: boxes above 64 columns are never used)
+    const cuuint64_t pdim[2] = {(cuuint64_t)a->row_stride, (cuuint64_t)rows};
+    const cuuint64_t pstr[1] = {(cuuint64_t)a->row_stride * es};
+    const cuuint32_t pbox[2] = {bw, 8u};
+    if (encode(&m->px[i], es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+               const_cast<void*>(a->pixels), pdim, pstr, pbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
+template <typename PX>
+int launch_sweep(const abx_extract_args* a, const Workspace& ws, const SweepMaps& maps, cudaStream_t st) {
+  static thread_local bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(object_sweep<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSlot);
+    if (e != cudaSuccess) return abx_check_cuda(e, "object_sweep smem attribute");
+    done[dev] = true;
+  }
+  const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
+  const int resident = 148 * kSwCtasPerSm;
+  // fewer objects than two rounds of resident warps: several work items per object, each with its share of the requests
+  int split_log2 = 0;
+  while (split_log2 < 3 && (n_total << split_log2) < 2 * resident && (2 << split_log2) <= a->n_requests) ++split_log2;
+  int grid = n_total << split_log2;
+  if (grid > resident) grid = resident;  // persistent: warps pull objects from a counter
+  object_sweep<PX><<<grid, 32, kSwSlot, st>>>(maps, ws.plan, ws.order_stats, ws.list_counts + kCntOrderBig,
+                                             n_total /* the plan kernel's capacity of the order array */,
+                                             ws.list_counts + kCntSweepWork, ws.bitmaps,
+                                             (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests, ws.chan,
+                                             ws.pair_list, ws.list_counts + kCntLeftover, split_log2);
+  return abx_check_cuda(cudaGetLastError(), "object_sweep");
+}
+
+}  // namespace
+
+// Whether abx_extract takes the sweep kernel for this call (layout and dtype qualify).
+bool abx_sweep_ok(const abx_extract_args* a) {
+  const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
+  if (n_total == 0 || a->n_requests == 0) return false;
+  if (a->pixel_dtype != ABX_U16 && a->pixel_dtype != ABX_U8) return false;
+  SweepMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  return make_maps(a, &maps);
+}
+
+// Routing of every object (statistics when `sweep`, shape always): runs after the label scan.
+int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool sweep) {
+  const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
+  if (n_total == 0 || (!sweep && !a->need_edt)) return ABX_OK;
+  PlanArgs p;
+  p.recs = ws.recs;
+  p.plane_base = a->plane_base;
+  p.plane_tile = a->plane_tile;
+  p.tile_offset = reinterpret_cast<const i64*>(a->tile_offset);
+  p.n_planes = a->n_planes;
+  p.n_objects = a->n_objects;
+  p.n_total = n_total;
+  p.row_stride = a->row_stride > 0 ? a->row_stride : 1;
+  p.align = a->pixel_dtype == ABX_U8 ? 16 : 8;
+  p.n_requests = a->n_requests;
+  p.sweep = sweep ? 1 : 0;
+  p.need_edt = a->need_edt ? 1 : 0;
+  p.chan = ws.chan;
+  p.shape = ws.shape;
+  p.plan = ws.plan;
+  p.order_stats = ws.order_stats;
+  p.order_edt = ws.order_edt;
+  p.stats_list = ws.stats_list;
+  p.pair_list = ws.pair_list;
+  p.edt_list = ws.edt_list;
+  p.counts = ws.list_counts;
+  plan_kernel<<<(n_total + 255) / 256, 256, 0, st>>>(p);
+  return abx_check_cuda(cudaGetLastError(), "plan");
+}
+
+int launch_object_sweep(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+  SweepMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (!make_maps(a, &maps)) return abx_set_error(ABX_ERR_INVALID, "object_sweep: layout does not qualify for TMA");
+  if (a->pixel_dtype == ABX_U16) return launch_sweep<uint16_t>(a, ws, maps, st);
+  return launch_sweep<uint8_t>(a, ws, maps, st);
+}

@@ -385,25 +385,27 @@ __global__ void __launch_bounds__(kStatsWarps * 32, 2)
 object_stats_warp(const Common cm, const PX* __restrict__ pixels, const i64* __restrict__ tile_offset, i64 chan_stride,
                   i64 z_stride, i64 px_row_stride, int Z, const abx_request* __restrict__ requests, int n_requests,
                   ChanStats* __restrict__ chan, int* __restrict__ stats_list, u32* __restrict__ stats_count,
-                  const u32* __restrict__ todo_count, int list_cap, const u32* __restrict__ gate, int bookkeeping) {
+                  const u32* __restrict__ todo_count, const int* __restrict__ pair_list, const u32* __restrict__ gate,
+                  int bookkeeping) {
   // gate: the launch has nothing to do when *gate == 0 (zreduce.cu: no request left to the stack).  bookkeeping = 0:
   // another kernel already zero-filled the absent labels and handed the large objects over.
   if (gate != nullptr && *gate == 0u) return;
   // Two modes.  todo_count == nullptr: every object of the launch, all its requests (the path for layouts TMA cannot
-  // address).  Otherwise: the objects object_stats_tma could not take (stored from the back of stats_list), one work
-  // item per (object, request) so that the few of them finish in the time of one request.
+  // address).  Otherwise: the (object, request) pairs the sweep kernel (object_sweep.cu) left over, one work item per
+  // pair so that the few of them finish in the time of one request.
   const u32 lane = lane_id();
   const u32 slot_off = (threadIdx.x >> 5) * kStatsSlot;
   const bool by_list = todo_count != nullptr;
-  const int n_items = by_list ? (int)(*todo_count) * n_requests : cm.n_total;
+  const int n_items = by_list ? (int)(*todo_count) : cm.n_total;
   Queue qu{cm.counters, n_items, 0};
   int item = qu.fetch();
   int nxt = item < n_items ? qu.fetch() : n_items;
   while (item < n_items) {
     int obj = item, q_lo = 0, q_hi = n_requests;
     if (by_list) {
-      obj = stats_list[list_cap - 1 - item / n_requests];
-      q_lo = item % n_requests;
+      const int pair = pair_list[item];
+      obj = pair / n_requests;
+      q_lo = pair - obj * n_requests;
       q_hi = q_lo + 1;
     }
     const abx_object_rec rec = cm.recs[obj];
@@ -492,8 +494,8 @@ int launch_stats(const abx_extract_args* a, const Workspace& ws, const Common& c
   if (todo) grid = 148;
   object_stats_warp<PX><<<grid, todo ? 32 : kStatsWarps * 32, todo ? (size_t)kStatsSlot : smem, st>>>(
       cm, static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride,
-      a->row_stride, a->Z, requests, a->n_requests, ws.chan, ws.stats_list, ws.list_counts,
-      todo ? ws.list_counts + 3 : nullptr, a->n_objects + a->n_planes, gate, bookkeeping);
+      a->row_stride, a->Z, requests, a->n_requests, ws.chan, ws.stats_list, ws.list_counts + kCntStatsList,
+      todo ? ws.list_counts + kCntLeftover : nullptr, ws.pair_list, gate, bookkeeping);
   return abx_check_cuda(cudaGetLastError(), "object_stats_warp");
 }
 
@@ -514,12 +516,12 @@ static Common make_common(const abx_extract_args* a, const Workspace& ws, int n_
   return cm;
 }
 
-// todo = false: every window-sized object; todo = true: the objects object_stats_tma left on its second list
+// todo = false: every window-sized object; todo = true: the (object, request) pairs the sweep kernel left over
 int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool todo) {
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0 || a->n_requests == 0) return ABX_OK;
   Common cm = make_common(a, ws, n_total);
-  cm.counters = ws.list_counts + (todo ? 6 : 2);
+  cm.counters = ws.list_counts + (todo ? kCntLeftoverWork : kCntGather);
   if (a->pixel_dtype == ABX_U16) return launch_stats<uint16_t>(a, ws, cm, st, todo, a->requests, nullptr, 1);
   if (a->pixel_dtype == ABX_U8) return launch_stats<uint8_t>(a, ws, cm, st, todo, a->requests, nullptr, 1);
   return ABX_OK;  // float pixels: every request belongs to object_float.cu
@@ -537,6 +539,6 @@ int launch_object_stats_rest(const abx_extract_args* a, const Workspace& ws, cud
   sums.row_stride = a->W;
   sums.Z = 1;
   Common cm = make_common(a, ws, n_total);
-  cm.counters = ws.list_counts + 8;
+  cm.counters = ws.list_counts + kCntRest;
   return launch_stats<uint32_t>(&sums, ws, cm, st, false, ws.req_rest, ws.zflags, 0);
 }

@@ -1,10 +1,11 @@
-// TMA (cp.async.bulk.tensor) and mbarrier plumbing shared by the kernels that stage windows in shared memory
-// (object_tma.cu, object_edt.cu).  Include inside the translation unit's anonymous namespace, after <cuda.h>,
-// common.cuh and warp_common.cuh.  One elected lane issues the boxes; the 32 lanes wait on the slot's mbarrier.
+// TMA (cp.async.bulk.tensor) and mbarrier plumbing shared by the kernels that stage tiles in shared memory
+// (label_scan.cu, object_sweep.cu).  Include inside the translation unit's anonymous namespace, after <cuda.h> and
+// common.cuh.  One elected lane issues the boxes; the 32 lanes wait on the slot's mbarrier.
 // Measured on B200 (tools/probes/tma_probe.cu): the innermost box coordinate times the element size must be a
 // multiple of 16 bytes, otherwise the copy faults with "illegal instruction"; rows may start anywhere.
 #pragma once
 
+__device__ __forceinline__ u32 smem_addr_of(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -26,6 +27,10 @@ __device__ __forceinline__ void tma_box_3d(u32 dst, const CUtensorMap* tmap, int
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+// L2 prefetch of one box (same tensor map and coordinates as the copy that follows later): fire and forget
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y) : "memory");
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -120,7 +120,11 @@ class ExtractArgs(C.Structure):
         ("stream", C.c_void_p),
         ("stage_events", C.POINTER(C.c_void_p)),
         ("pixel_elems", C.c_int64),
+        ("status", C.c_void_p),
     ]
+
+
+ABI_VERSION = 3  # include/aliby_b200.h ABX_VERSION
 
 
 class NativeError(RuntimeError):
@@ -162,6 +166,9 @@ def lib() -> C.CDLL:
     handle.abx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     for name in EXPORTS:
         getattr(handle, name)  # AttributeError if the header and the library drifted apart
+    if handle.abx_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI {handle.abx_version()}, this package needs {ABI_VERSION}: rebuild it "
+                          "(python -m aliby_b200.build --force)")
     _lib = handle
     return handle
 

@@ -225,6 +225,10 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   if ((rc = launch_shape_edt(args, ws, st))) return rc;
   mark(4);
   if ((rc = launch_finalize(args, ws, st))) return rc;
+  if (args->status) {
+    cudaError_t e = cudaMemcpyAsync(args->status, ws.err, sizeof(u32), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return abx_check_cuda(e, "status copy");
+  }
   mark(5);
   return ABX_OK;
 }

@@ -32,14 +32,7 @@ namespace {
 #include "warp_common.cuh"
 #include "tma.cuh"
 
-constexpr u32 kSwSlot = 16896;   // dynamic shared memory per single-warp CTA: 13 CTAs (+ 1 KB reserved each) per SM
-constexpr int kSwCtasPerSm = 13;
 constexpr u32 kBigFirst = 1536;  // objects above this many pixels are processed first
-constexpr int kMaxPitch = 8;     // tensor maps for box widths of 16, 32, ... 128 bytes
-
-struct SweepMaps {
-  CUtensorMap px[kMaxPitch];  // the pixel buffer as rows of row_stride elements, box (16 * (i + 1)) bytes x 8 rows
-};
 
 // ---- shared-memory accessors on 32-bit shared addresses (no generic-pointer arithmetic in the hot loops) ----
 __device__ __forceinline__ u32 lds_u16(u32 a) { u32 v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -167,11 +160,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
 struct Geo {  // one object's window as the kernel sees it (warp-uniform)
   int obj;
   int tma_x, tma_y;  // box coordinates of the window in channel 0
-  u32 n, h, w, s_px;
+  u32 n, h, w;
   u32 rot, row0;     // bitmap rotation (columns) and first bitmap row
-  u32 pitchB, pidx;  // window row pitch in bytes (a multiple of 16), tensor map index
-  u32 h8, R;         // rows rounded up to whole boxes; rows per chunk (a multiple of 8; == h8: one chunk)
-  u32 list_bytes;
+  u32 pitchB;        // window row pitch in bytes (a multiple of 16)
+  u32 h8, R;         // rows rounded up to whole boxes of 8; rows per chunk (a multiple of 8; == h8: one chunk)
 };
 
 template <typename PX>
@@ -183,14 +175,13 @@ __device__ __forceinline__ Geo make_geo(const ObjPlan& pl, int obj, u32 flex_byt
   g.h = (pl.geom & 63u) + 1u;
   g.w = ((pl.geom >> 6) & 63u) + 1u;
   g.row0 = (pl.geom >> 12) & 63u;
-  g.s_px = pl.geom >> 24;
-  g.rot = (((pl.geom >> 18) & 63u) - g.s_px) & 63u;
-  g.pitchB = ((g.w + g.s_px) * (u32)sizeof(PX) + 15u) & ~15u;
-  g.pidx = (g.pitchB >> 4) - 1u;
+  const u32 s_px = pl.geom >> 24;
+  g.rot = (((pl.geom >> 18) & 63u) - s_px) & 63u;
+  g.pitchB = ((g.w + s_px) * (u32)sizeof(PX) + 15u) & ~15u;
   g.h8 = (g.h + 7u) & ~7u;
-  g.list_bytes = ((g.n + 1u) & ~1u) * 2u;
+  const u32 list_bytes = ((g.n + 1u) & ~1u) * 2u;
   g.R = g.h8;
-  if (g.h8 * g.pitchB + g.list_bytes > flex_bytes) g.R = ((flex_bytes - g.list_bytes) / g.pitchB) & ~7u;
+  if (g.h8 * g.pitchB + list_bytes > flex_bytes) g.R = ((flex_bytes - list_bytes) / g.pitchB) & ~7u;
   return g;
 }
 
@@ -199,15 +190,13 @@ struct Acc {  // per-lane partial sums of one request
   u64 sq, q;
 };
 
-template <typename PX, bool kWrap>
+template <typename PX>
 __device__ __forceinline__ void accumulate(Acc& a, u32 v, u32 hbase) {
   constexpr int kShift = (sizeof(PX) == 1) ? 12 : 8;  // (x << kShift)^2 >> 32 == x^2 >> bits(PX)
   a.sum += v;
   a.sq += (u64)v * (u64)v;
-  if (kWrap) {
-    const u32 s = v << kShift;
-    a.wh += __umulhi(s, s);
-  }
+  const u32 s = v << kShift;
+  a.wh += __umulhi(s, s);
   a.vmin = min(a.vmin, v);
   a.vmax = max(a.vmax, v);
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hbase | ((v << 2) & 0xFFCu)) : "memory");
@@ -228,13 +217,13 @@ __device__ __forceinline__ void accumulate_moi(Acc& a, u32 v, u32 off, u32 inv_p
 // One pass over list entries [first, first + cnt) (shared addresses of the object's pixels inside the resident window
 // chunk): blocks of 128 entries unpredicated, the last partial block predicated.  win_base: the shared address window
 // row 0 WOULD have (rows of later chunks count on from the rows before them), for the moment-of-inertia coordinates.
-template <typename PX, bool kMoi, bool kWrap>
+template <typename PX, bool kMoi>
 __device__ __forceinline__ void sweep_chunk(Acc& a, u32 list_addr, u32 cnt, u32 hbase, u32 win_base, u32 inv_pitch, u32 pitchB) {
   const u32 lane = lane_id();
   u32 p = list_addr + 2u * lane;
   const u32 pend = list_addr + 2u * (cnt & ~127u);
   if (p < pend) {
-    // three-stage software pipeline: entries of block i + 1 and pixels of block i are loaded while block i - 1 is added up
+    // software pipeline: entries and pixels of block i + 1 are loaded while block i is added up
     u32 k[4], v[4], kn[4];
     k[0] = lds_u16_off<0>(p); k[1] = lds_u16_off<64>(p); k[2] = lds_u16_off<128>(p); k[3] = lds_u16_off<192>(p);
     p += 256u;
@@ -249,7 +238,7 @@ __device__ __forceinline__ void sweep_chunk(Acc& a, u32 list_addr, u32 cnt, u32 
       for (int u = 0; u < 4; ++u) vn[u] = lds_px<PX>(kn[u]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        accumulate<PX, kWrap>(a, v[u], hbase);
+        accumulate<PX>(a, v[u], hbase);
         if (kMoi) accumulate_moi<PX>(a, v[u], k[u] - win_base, inv_pitch, pitchB);
       }
 #pragma unroll
@@ -257,28 +246,36 @@ __device__ __forceinline__ void sweep_chunk(Acc& a, u32 list_addr, u32 cnt, u32 
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      accumulate<PX, kWrap>(a, v[u], hbase);
+      accumulate<PX>(a, v[u], hbase);
       if (kMoi) accumulate_moi<PX>(a, v[u], k[u] - win_base, inv_pitch, pitchB);
     }
   }
   // the last partial block
   const u32 rem = cnt & 127u;
-  if (rem) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (lane + 32u * u < rem) {
-        const u32 k = lds_u16(pend + 2u * (lane + 32u * u));
-        const u32 v = lds_px<PX>(k);
-        accumulate<PX, kWrap>(a, v, hbase);
-        if (kMoi) accumulate_moi<PX>(a, v, k - win_base, inv_pitch, pitchB);
-      }
+  for (int u = 0; u < 4; ++u) {
+    if (lane + 32u * u < rem) {
+      const u32 k = lds_u16(pend + 2u * (lane + 32u * u));
+      const u32 v = lds_px<PX>(k);
+      accumulate<PX>(a, v, hbase);
+      if (kMoi) accumulate_moi<PX>(a, v, k - win_base, inv_pitch, pitchB);
     }
   }
 }
 
+// Zero the relative bins [lane * per, (lane + 1) * per) of the circular histogram: together the 32 lanes clear every
+// bin a request with this `per` can have touched.
+__device__ __forceinline__ void zero_touched(u32* h, u32 rot, u32 per) {
+  const u32 b0 = lane_id() * per;
+#pragma unroll
+  for (u32 k = 0; k < 32u; k += 4u)
+    if (k < per) *reinterpret_cast<uint4*>(h + ((b0 + k + rot) & 1023u)) = make_uint4(0, 0, 0, 0);
+}
+
 // Locate four ranks in the circular histogram: relative bin j lives at h[(j + rot) & 1023], rot a multiple of 4, bins
-// [nb, 1024) relative are zero.  Same scheme and outputs as find_ranks32 (warp_common.cuh).
-__device__ __forceinline__ void find_ranks_rot(const u32* h, u32 rot, u32 nb, const u32 (&ranks)[4], u32* t) {
+// [nb, 1024) relative are zero.  Same scheme and outputs as find_ranks32 (warp_common.cuh); the touched bins are zeroed
+// on the way out.
+__device__ __forceinline__ void find_ranks_rot(u32* h, u32 rot, u32 nb, const u32 (&ranks)[4], u32* t) {
   const u32 lane = lane_id();
   const u32 per = bins_per_lane(nb);
   const u32 b0 = lane * per;
@@ -317,6 +314,8 @@ __device__ __forceinline__ void find_ranks_rot(const u32* h, u32 rot, u32 nb, co
     lc += c4[k];
     lq += c4[k] * (lb + k);
   }
+  __syncwarp();
+  zero_touched(h, rot, per);
   u32 ic = lc, iq = lq;
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {
@@ -415,34 +414,65 @@ __device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32
   return r;
 }
 
-// One TMA load = the rows [c * R, c * R + rows) of the window of request channel `chan`.
-struct LoadDesc {
-  int x, y;      // box coordinates of the first box
-  u32 rows;      // a multiple of 8; 0 = no load
-  u32 pitchB, pidx;
+
+// Three warps per CTA, four CTAs per SM: twelve objects in flight per SM, and every shared address of a CTA stays below
+// 2^16 (1 KB reserved + 56 KB), so that a list entry can be the 16-bit shared address of its pixel.
+constexpr int kSwWarps = 3, kSwCtasPerSm = 4;
+constexpr int kMaxRequests = 64;   // request table in shared memory
+constexpr u32 kSwSmem = 57344;     // 4 x (56 KB + 1 KB reserved) = the 228 KB of an SM
+constexpr u32 kSwHead = 1024 + kSwWarps * 128;  // request table | per warp: scratch u32[16], mbarrier
+
+struct SweepMaps {
+  // the pixel buffer as rows of row_stride elements; map [i][j]: box of 16 (i + 1) bytes x 8 (j + 1) rows, so that one
+  // copy brings a whole window (or window chunk)
+  CUtensorMap px[8][8];
+};
+
+struct ReqEntry {   // one request this kernel computes
+  int row_off;      // channel * rows per channel: added to the window's box row
+  u32 features;
+  int q;            // index into the caller's request list
+  int pad_;
 };
 
 template <typename PX>
-__global__ void __launch_bounds__(32, kSwCtasPerSm)
+__global__ void __launch_bounds__(kSwWarps * 32, kSwCtasPerSm)
 object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__ plan, const int* __restrict__ order,
-             const u32* __restrict__ order_counts /* [0] big, [1] small */, int n_total, u32* __restrict__ work_counter,
+             const u32* __restrict__ order_counts /* [0] big, [1] small */, int order_cap, u32* __restrict__ work_counter,
              const u64* __restrict__ bitmaps, int chan_rows, const abx_request* __restrict__ requests, int n_requests,
              ChanStats* __restrict__ chan, int* __restrict__ pair_list, u32* __restrict__ pair_count, int split_log2) {
   const u32 lane = lane_id();
+  const u32 warp = threadIdx.x >> 5;
   const u32 sbase = smem_addr_of(dyn);
-  // layout inside the slot (shared addresses): flex [sbase, hist) | hist 4 KB, 4 KB aligned | scratch, mbarrier
-  u32 hbase = (sbase + kSwSlot - 4096u) & ~4095u;
-  if (((sbase + kSwSlot) & 4095u) < 256u) hbase -= 4096u;
-  const u32 flex_bytes = hbase - sbase;
+  // ---- shared memory: head | histograms (4 KB each, 4 KB aligned in the shared window) | flex areas ----
+  ReqEntry* rtab = reinterpret_cast<ReqEntry*>(dyn);
+  int* n_valid_p = reinterpret_cast<int*>(dyn + kMaxRequests * sizeof(ReqEntry) - 16);  // (the table holds < 64 entries then)
+  const u32 hist0 = (sbase + kSwHead + 4095u) & ~4095u;
+  const u32 flex0 = hist0 + kSwWarps * 4096u;
+  const u32 flex_bytes = ((sbase + kSwSmem - flex0) / kSwWarps) & ~127u;
+  const u32 hbase = hist0 + warp * 4096u;
+  const u32 win_base = flex0 + warp * flex_bytes;
   u32* hist = reinterpret_cast<u32*>(dyn + (hbase - sbase));
-  u32* t = reinterpret_cast<u32*>(dyn + (hbase + 4096u - sbase));
-  const u32 bar = hbase + 4096u + 128u;
+  u32* t = reinterpret_cast<u32*>(dyn + 1024u + warp * 128u);
+  const u32 bar = sbase + 1024u + warp * 128u + 64u;
+  if (threadIdx.x == 0) {  // the requests this kernel computes (div requests belong to object_float.cu)
+    int nv = 0;
+    for (int q = 0; q < n_requests; ++q) {
+      const abx_request rq = requests[q];
+      if (rq.reduction == ABX_RED_DIV) continue;
+      ReqEntry e;
+      e.row_off = rq.channel * chan_rows; e.features = rq.features; e.q = q; e.pad_ = 0;
+      rtab[nv++] = e;
+    }
+    *n_valid_p = nv;
+  }
   if (lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   hist_zero(hist, 1024u);
-  __syncwarp();
+  __syncthreads();
+  const int n_valid = *n_valid_p;
   u32 parity = 0;
 
   const u32 n_big = order_counts[0], n_small = order_counts[1];
@@ -456,70 +486,54 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
   // work item -> object: the big objects from the front of the order array, then the others from its back
   auto object_of = [&](int item) {
     const u32 idx = (u32)(item >> split_log2);
-    return order[idx < n_big ? (int)idx : n_total - 1 - (int)(idx - n_big)];
+    return order[idx < n_big ? (int)idx : order_cap - 1 - (int)(idx - n_big)];
   };
-  // first / next request of a work item that this kernel computes (div requests belong to object_float.cu)
-  auto next_request = [&](int q, int q_hi) {
-    while (q < q_hi && requests[q].reduction == ABX_RED_DIV) ++q;
-    return q;
-  };
-  auto item_requests = [&](int item, int& q_lo, int& q_hi) {
+  auto item_requests = [&](int item, int& lo, int& hi) {  // this item's share of the request table
     const int part = item & (split - 1);
-    q_lo = (part * n_requests) >> split_log2;
-    q_hi = ((part + 1) * n_requests) >> split_log2;
+    lo = (part * n_valid) >> split_log2;
+    hi = ((part + 1) * n_valid) >> split_log2;
   };
-  auto make_load = [&](const Geo& g, int q, u32 c) {
-    LoadDesc d;
-    d.x = g.tma_x;
-    d.y = g.tma_y + requests[q].channel * chan_rows + (int)(c * g.R);
-    d.rows = min(g.R, g.h8 - c * g.R);
-    d.pitchB = g.pitchB; d.pidx = g.pidx;
-    return d;
-  };
-  auto issue = [&](const LoadDesc& d) {  // by lane 0, after every lane is done with the window
-    if (lane == 0 && d.rows) {
+  // One copy = rows [c R, c R + rows) of the window of one request: a single box.
+  auto issue = [&](const Geo& g, int row_off, u32 c) {  // every lane is done with the window (syncwarp by the caller)
+    if (lane == 0) {
+      const u32 rows = min(g.R, g.h8 - c * g.R);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, d.rows * d.pitchB);
-      const u32 box = 8u * d.pitchB;
-      u32 dst = sbase;
-      for (u32 j = 0; j < d.rows; j += 8, dst += box) tma_box_2d(dst, &maps.px[d.pidx], d.x, d.y + (int)j, bar);
+      mbar_expect_tx(bar, rows * g.pitchB);
+      tma_box_2d(win_base, &maps.px[(g.pitchB >> 4) - 1u][(rows >> 3) - 1u], g.tma_x, g.tma_y + row_off + (int)(c * g.R), bar);
     }
   };
-  auto prefetch = [&](const LoadDesc& d) {
+  auto prefetch = [&](const Geo& g, int row_off) {  // first chunk of a window, into L2
 #ifndef ABX_NO_PREFETCH
-    if (lane == 0 && d.rows)
-      for (u32 j = 0; j < d.rows; j += 8) tma_prefetch_2d(&maps.px[d.pidx], d.x, d.y + (int)j);
+    if (lane == 0)
+      tma_prefetch_2d(&maps.px[(g.pitchB >> 4) - 1u][(g.R >> 3) - 1u], g.tma_x, g.tma_y + row_off);
 #endif
   };
 
   int item = fetch();
   int nxt_item = item < n_items ? fetch() : n_items;
   Geo g, gn;
-  int q_lo = 0, q_hi = 0, nq_lo = 0, nq_hi = 0;
-  bool have = false;
-  if (item < n_items) {
+  int i_lo = 0, i_hi = 0, ni_lo = 0, ni_hi = 0;
+  bool have = item < n_items;
+  if (have) {
     const int obj = object_of(item);
     g = make_geo<PX>(plan[obj], obj, flex_bytes);
-    item_requests(item, q_lo, q_hi);
-    q_lo = next_request(q_lo, q_hi);
-    have = true;
-    if (q_lo < q_hi) issue(make_load(g, q_lo, 0));
+    item_requests(item, i_lo, i_hi);
+    if (i_lo < i_hi) issue(g, rtab[i_lo].row_off, 0);
   }
   while (have) {
-    // the warp's next object (its first load is issued by this object's last sweep)
-    bool have_next = nxt_item < n_items;
+    // the warp's next object (its first window is requested by this object's last sweep)
+    const bool have_next = nxt_item < n_items;
     if (have_next) {
       const int nobj = object_of(nxt_item);
       gn = make_geo<PX>(plan[nobj], nobj, flex_bytes);
-      item_requests(nxt_item, nq_lo, nq_hi);
-      nq_lo = next_request(nq_lo, nq_hi);
+      item_requests(nxt_item, ni_lo, ni_hi);
     }
+    const bool next_has = have_next && ni_lo < ni_hi;
     const int after_item = have_next ? fetch() : n_items;
 
-    if (q_lo < q_hi) {
+    if (i_lo < i_hi) {
       // ---- pixel list from the torus bitmap (while the first window is in flight) ----
-      const u32 win_base = sbase;
-      const u32 list_addr = sbase + g.R * g.pitchB;
+      const u32 list_addr = win_base + g.R * g.pitchB;
       const u64* bm = bitmaps + (size_t)g.obj * 64u;
       u64 m0 = bm[(g.row0 + lane) & 63u], m1 = bm[(g.row0 + lane + 32u) & 63u];
       m0 = (m0 >> g.rot) | (g.rot ? (m0 << (64u - g.rot)) : 0ull);
@@ -536,8 +550,7 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
       const bool multi = g.R < g.h8;
       {
         // row r of chunk r / R: entry = shared address of its pixel inside the chunk buffer
-        const u32 r0 = lane, r1 = lane + 32u;
-        const u32 rr0 = multi ? r0 % g.R : r0, rr1 = multi ? r1 % g.R : r1;
+        const u32 rr0 = multi ? lane % g.R : lane, rr1 = multi ? (lane + 32u) % g.R : lane + 32u;
         const u32 a0 = m0 ? (u32)__ffsll((long long)m0) - 1u : 0u, a1 = m1 ? (u32)__ffsll((long long)m1) - 1u : 0u;
         const u64 run0 = m0 >> a0, run1 = m1 >> a1;
         const bool single = ((run0 & (run0 + 1ull)) == 0ull) && ((run1 & (run1 + 1ull)) == 0ull);
@@ -563,26 +576,18 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
           }
         } else {
           // any shape: bit by bit
-          u64 mm = m0;
-          u32 p = list_addr + 2u * base0;
-          const u32 row_a0 = win_base + rr0 * g.pitchB;
-          while (__any_sync(kFull, mm != 0ull)) {
-            if (mm) {
-              const u32 b = (u32)__ffsll((long long)mm) - 1u;
-              mm &= mm - 1ull;
-              sts_u16(p, row_a0 + b * (u32)sizeof(PX));
-              p += 2u;
-            }
-          }
-          mm = m1;
-          p = list_addr + 2u * base1;
-          const u32 row_a1 = win_base + rr1 * g.pitchB;
-          while (__any_sync(kFull, mm != 0ull)) {
-            if (mm) {
-              const u32 b = (u32)__ffsll((long long)mm) - 1u;
-              mm &= mm - 1ull;
-              sts_u16(p, row_a1 + b * (u32)sizeof(PX));
-              p += 2u;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            u64 mm = half ? m1 : m0;
+            u32 p = list_addr + 2u * (half ? base1 : base0);
+            const u32 row_a = win_base + (half ? rr1 : rr0) * g.pitchB;
+            while (__any_sync(kFull, mm != 0ull)) {
+              if (mm) {
+                const u32 b = (u32)__ffsll((long long)mm) - 1u;
+                mm &= mm - 1ull;
+                sts_u16(p, row_a + b * (u32)sizeof(PX));
+                p += 2u;
+              }
             }
           }
         }
@@ -590,14 +595,15 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
       __syncwarp();
       const u32 inv_pitch = 0xFFFFFFFFu / g.pitchB + 1u;
       const u32 n_chunks = multi ? (g.h8 + g.R - 1u) / g.R : 1u;
+      const u32 k2p5 = (u32)ceil((double)g.n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
+      const u32 ranks[4] = {(g.n - 1) / 2, g.n / 2, g.n - k2p5, g.n - min(g.n, 5u)};
 
 #pragma unroll 1
-      for (int q = q_lo; q < q_hi;) {
-        const abx_request rq = requests[q];
-        const int q_next = next_request(q + 1, q_hi);
+      for (int i = i_lo; i < i_hi; ++i) {
+        const ReqEntry rq = rtab[i];
         Acc a;
         a.sum = a.wh = a.vmax = a.m10 = a.m01 = 0; a.vmin = kFull; a.sq = a.q = 0;
-        const bool want_moi = (rq.features & ABX_F_MOI) != 0, want_wrap = (rq.features & ABX_F_WRAPSQ) != 0;
+        const bool want_moi = (rq.features & ABX_F_MOI) != 0;
         const bool want_ranks = (rq.features & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) != 0;
         u32 vmin = 0, vmax = 0;
         Ranked rk;
@@ -618,13 +624,8 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
           parity ^= 1u;
           const u32 la = list_addr + 2u * first;
           const u32 wb = win_base - c * g.R * g.pitchB;  // (wraps below zero for later chunks: only differences are used)
-          if (want_moi) {
-            if (want_wrap) sweep_chunk<PX, true, true>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
-            else sweep_chunk<PX, true, false>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
-          } else {
-            if (want_wrap) sweep_chunk<PX, false, true>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
-            else sweep_chunk<PX, false, false>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
-          }
+          if (want_moi) sweep_chunk<PX, true>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
+          else sweep_chunk<PX, false>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
           __syncwarp();
           const bool last_chunk = c + 1u == n_chunks;
           if (last_chunk) {
@@ -633,40 +634,29 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
             wide = want_ranks && vmax - (vmin & ~3u) > 1023u;
             if (wide && !multi) {  // the window is still here: refine now, before it is overwritten
               sum64 = (u64)__reduce_add_sync(kFull, a.sum);
-              const u32 k2p5 = (u32)ceil((double)g.n * 0.025), k5 = min(g.n, 5u);
-              const u32 ranks[4] = {(g.n - 1) / 2, g.n / 2, g.n - k2p5, g.n - k5};
               rk = wide_ranks<PX>(list_addr, g.n, vmin, vmax, sum64, rq.features, hist, t, ranks);
               wide_done = true;
             }
           }
-          // ---- the next window: next chunk, next request, or the first request of the warp's next object ----
-          LoadDesc nx, pf;
-          nx.rows = pf.rows = 0;
+          // ---- the next window: next chunk, next request, or the first request of the warp's next object; the
+          // window after that one goes to L2 ----
           if (!last_chunk) {
-            nx = make_load(g, q, c + 1u);
-            if (c + 2u < n_chunks) pf = make_load(g, q, c + 2u);
-            else if (q_next < q_hi) pf = make_load(g, q_next, 0);
-          } else if (q_next < q_hi) {
-            nx = make_load(g, q_next, 0);
-            const int q2 = next_request(q_next + 1, q_hi);
-            if (n_chunks > 1u) pf = make_load(g, q_next, 1u);
-            else if (q2 < q_hi) pf = make_load(g, q2, 0);
-            else if (have_next && nq_lo < nq_hi) pf = make_load(gn, nq_lo, 0);
-          } else if (have_next && nq_lo < nq_hi) {
-            nx = make_load(gn, nq_lo, 0);
-            const int q2 = next_request(nq_lo + 1, nq_hi);
-            if (gn.R < gn.h8) pf = make_load(gn, nq_lo, 1u);
-            else if (q2 < nq_hi) pf = make_load(gn, q2, 0);
+            issue(g, rq.row_off, c + 1u);
+          } else if (i + 1 < i_hi) {
+            issue(g, rtab[i + 1].row_off, 0);
+            if (i + 2 < i_hi) prefetch(g, rtab[i + 2].row_off);
+            else if (next_has) prefetch(gn, rtab[ni_lo].row_off);
+          } else if (next_has) {
+            issue(gn, rtab[ni_lo].row_off, 0);
+            if (ni_lo + 1 < ni_hi) prefetch(gn, rtab[ni_lo + 1].row_off);
           }
-          issue(nx);
-          prefetch(pf);
         }
         // ---- reductions (under the copy that was just issued) ----
         ChanStats cs;
         cs.sum = wide_done ? sum64 : (u64)__reduce_add_sync(kFull, a.sum);  // n * 65535 < 2^32
         cs.sumsq = warp_sum64(a.sq);
         constexpr int kShift = (sizeof(PX) == 1) ? 12 : 8;
-        cs.wrapsq = want_wrap ? cs.sumsq - ((u64)__reduce_add_sync(kFull, a.wh) << (32 - 2 * kShift)) : 0;
+        cs.wrapsq = cs.sumsq - ((u64)__reduce_add_sync(kFull, a.wh) << (32 - 2 * kShift));
         cs.m10 = cs.m01 = cs.m20 = cs.m02 = 0;
         if (want_moi) {
           // coordinates relative to the TMA box (column s_px = bbox column 0): central moments are translation invariant
@@ -677,37 +667,32 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         cs.vmin = vmin; cs.vmax = vmax;
         cs.med_lo = rk.med_lo; cs.med_hi = rk.med_hi;
         cs.top2p5_sum = rk.top2p5_sum; cs.top5_sum = rk.top5_sum;
-        if (want_ranks && !wide) {
+        if (!wide_done) {
           const u32 vbase = vmin & ~3u;
-          const u32 nb = vmax - vbase + 1u;
-          const u32 k2p5 = (u32)ceil((double)g.n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
-          const u32 k5 = min(g.n, 5u);
-          const u32 ranks[4] = {(g.n - 1) / 2, g.n / 2, g.n - k2p5, g.n - k5};
-          find_ranks_rot(hist, vbase & 1023u, nb, ranks, t);
-          cs.med_lo = vbase + t[0]; cs.med_hi = vbase + t[1];
-          const u32 v2 = vbase + t[2], v3 = vbase + t[3];
-          // sum of the smallest values up to the rank = vbase * cnt + sum(count * bin) below + rank * value
-          const u64 below2 = (u64)vbase * t[10] + t[14] + (u64)t[6] * v2;
-          const u64 below3 = (u64)vbase * t[11] + t[15] + (u64)t[7] * v3;
-          cs.top2p5_sum = cs.sum - below2;
-          cs.top5_sum = cs.sum - below3;
+          if (want_ranks && !wide) {
+            find_ranks_rot(hist, vbase & 1023u, vmax - vbase + 1u, ranks, t);
+            cs.med_lo = vbase + t[0]; cs.med_hi = vbase + t[1];
+            const u32 v2 = vbase + t[2], v3 = vbase + t[3];
+            // sum of the smallest values up to the rank = vbase * cnt + sum(count * bin) below + rank * value
+            const u64 below2 = (u64)vbase * t[10] + t[14] + (u64)t[6] * v2;
+            const u64 below3 = (u64)vbase * t[11] + t[15] + (u64)t[7] * v3;
+            cs.top2p5_sum = cs.sum - below2;
+            cs.top5_sum = cs.sum - below3;
+          } else {  // no order statistics wanted (or a wide range in a chunked window): just clean up
+            const u32 span = vmax - vbase;
+            zero_touched(hist, vbase & 1023u, span > 1023u ? 32u : bins_per_lane(span + 1u));
+          }
         }
         if (lane == 0) {
-          chan[(i64)g.obj * n_requests + q] = cs;
-          if (wide && !wide_done) pair_list[atomicAdd(pair_count, 1u)] = g.obj * n_requests + q;  // multi-chunk and wide: rare
+          chan[(i64)g.obj * n_requests + rq.q] = cs;
+          if (wide && !wide_done) pair_list[atomicAdd(pair_count, 1u)] = g.obj * n_requests + rq.q;  // chunked and wide: rare
         }
         __syncwarp();
-        if (!wide_done) {  // (wide_ranks leaves the histogram clean)
-          // only the bins that can be non-zero: relative [0, nb) rounded to whole uint4s, at most all 1024
-          hist_zero(hist, 1024u);
-          __syncwarp();
-        }
-        q = q_next;
       }
-    } else if (have_next && nq_lo < nq_hi) {
-      issue(make_load(gn, nq_lo, 0));  // this item had no request for this kernel: start the next object's first window
+    } else if (next_has) {
+      issue(gn, rtab[ni_lo].row_off, 0);  // this item had no request for this kernel: start the next object's first window
     }
-    g = gn; q_lo = nq_lo; q_hi = nq_hi;
+    g = gn; i_lo = ni_lo; i_hi = ni_hi;
     have = have_next;
     item = nxt_item;
     nxt_item = after_item;
@@ -717,25 +702,34 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
 // The tensor maps, or false when the pixel layout does not qualify for TMA (the caller then takes object_stats_warp).
 bool make_maps(const abx_extract_args* a, SweepMaps* m) {
   EncodeFn encode = tensor_map_encoder();
-  if (!encode || a->Z != 1 || a->pixel_elems <= 0) return false;
+  if (!encode || a->Z != 1 || a->pixel_elems <= 0 || a->n_requests > kMaxRequests - 2) return false;
   const size_t es = a->pixel_dtype == ABX_U8 ? 1 : 2;
   if ((reinterpret_cast<uintptr_t>(a->pixels) & 15u) || (a->row_stride * (i64)es) % 16 || a->row_stride * (i64)es < 128 ||
       a->chan_stride % a->row_stride || a->chan_stride / a->row_stride > 0x7FFFFFFF / (a->C > 0 ? a->C : 1))
     return false;
   const i64 rows = a->pixel_elems / a->row_stride;  // whole rows inside the caller's buffer
-  if (rows < 8 || rows > 0x7FFFFFFF) return false;
-  const cuuint32_t estr[2] = {1u, 1u};
-  for (int i = 0; i < kMaxPitch; ++i) {
-    const cuuint32_t bw = (cuuint32_t)(16u * (i + 1) / es);
-    if (bw > (cuuint32_t)(64 * 2 / es) && es == 1) {}  // (u8: boxes above 64 columns are never used)
-    const cuuint64_t pdim[2] = {(cuuint64_t)a->row_stride, (cuuint64_t)rows};
-    const cuuint64_t pstr[1] = {(cuuint64_t)a->row_stride * es};
-    const cuuint32_t pbox[2] = {bw, 8u};
-    if (encode(&m->px[i], es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
-               const_cast<void*>(a->pixels), pdim, pstr, pbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return false;
+  if (rows < 64 || rows > 0x7FFFFFFF) return false;
+  // the 64 encodings are cached per host thread: a pipeline calls with the same buffer at every time point
+  struct Key { const void* px; i64 rs, rows; int dtype; };
+  static thread_local Key ckey = {nullptr, 0, 0, -1};
+  static thread_local SweepMaps cmaps;
+  if (ckey.px == a->pixels && ckey.rs == a->row_stride && ckey.rows == rows && ckey.dtype == a->pixel_dtype) {
+    memcpy(m, &cmaps, sizeof(SweepMaps));
+    return true;
   }
+  const cuuint32_t estr[2] = {1u, 1u};
+  const cuuint64_t pdim[2] = {(cuuint64_t)a->row_stride, (cuuint64_t)rows};
+  const cuuint64_t pstr[1] = {(cuuint64_t)a->row_stride * es};
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j < 8; ++j) {
+      const cuuint32_t pbox[2] = {(cuuint32_t)(16u * (i + 1) / es), (cuuint32_t)(8 * (j + 1))};
+      if (encode(&m->px[i][j], es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                 const_cast<void*>(a->pixels), pdim, pstr, pbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    }
+  memcpy(&cmaps, m, sizeof(SweepMaps));
+  ckey = Key{a->pixels, a->row_stride, rows, a->pixel_dtype};
   return true;
 }
 
@@ -745,22 +739,22 @@ int launch_sweep(const abx_extract_args* a, const Workspace& ws, const SweepMaps
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(object_sweep<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSlot);
+    cudaError_t e = cudaFuncSetAttribute(object_sweep<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem);
     if (e != cudaSuccess) return abx_check_cuda(e, "object_sweep smem attribute");
     done[dev] = true;
   }
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
-  const int resident = 148 * kSwCtasPerSm;
+  const int resident = 148 * kSwCtasPerSm * kSwWarps;
   // fewer objects than two rounds of resident warps: several work items per object, each with its share of the requests
   int split_log2 = 0;
   while (split_log2 < 3 && (n_total << split_log2) < 2 * resident && (2 << split_log2) <= a->n_requests) ++split_log2;
-  int grid = n_total << split_log2;
-  if (grid > resident) grid = resident;  // persistent: warps pull objects from a counter
-  object_sweep<PX><<<grid, 32, kSwSlot, st>>>(maps, ws.plan, ws.order_stats, ws.list_counts + kCntOrderBig,
-                                             n_total /* the plan kernel's capacity of the order array */,
-                                             ws.list_counts + kCntSweepWork, ws.bitmaps,
-                                             (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests, ws.chan,
-                                             ws.pair_list, ws.list_counts + kCntLeftover, split_log2);
+  int grid = ((n_total << split_log2) + kSwWarps - 1) / kSwWarps;
+  if (grid > 148 * kSwCtasPerSm) grid = 148 * kSwCtasPerSm;  // persistent: warps pull objects from a counter
+  object_sweep<PX><<<grid, kSwWarps * 32, kSwSmem, st>>>(maps, ws.plan, ws.order_stats, ws.list_counts + kCntOrderBig,
+                                                        n_total /* the plan kernel's capacity of the order array */,
+                                                        ws.list_counts + kCntSweepWork, ws.bitmaps,
+                                                        (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests,
+                                                        ws.chan, ws.pair_list, ws.list_counts + kCntLeftover, split_log2);
   return abx_check_cuda(cudaGetLastError(), "object_sweep");
 }
 

@@ -177,18 +177,29 @@ def compile_instructions(instructions: list) -> Plan:
 
 _DTYPES = {"uint8": nat.U8, "uint16": nat.U16, "float32": nat.F32, "float64": nat.F64}
 PIXEL_DTYPES = tuple(_DTYPES)  # numpy / torch dtype names with a kernel
-_workspaces: dict = {}
 
 
-def _workspace(device, nbytes: int):
+def alloc_table(n_objects: int, n_cols: int, device, n_status: int = 1):
+    """Device table plus status words in ONE buffer, so that a single device-to-host copy returns both.
+
+    Returns ``(buf, table, status)``: ``buf`` float64 ``[n_objects * n_cols + n_status]``, ``table`` its first part as
+    ``(n_objects, n_cols)``, ``status`` an int32 view of the last ``n_status`` slots (two int32 per slot; the library
+    writes the first)."""
     import torch
 
-    key = str(device)
-    buf = _workspaces.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
-    return buf
+    buf = torch.empty(n_objects * n_cols + n_status, dtype=torch.float64, device=device)
+    status = buf[n_objects * n_cols :].view(torch.int32)
+    status.zero_()
+    return buf, buf[: n_objects * n_cols].view(n_objects, n_cols), status
+
+
+def raise_on_status(word: int) -> None:
+    """Error flags of a finished call (``abx_extract_args.status``)."""
+    if int(word) & 1:
+        raise IndexError(
+            "a label id exceeds the number of labels given for its plane (n_labels / plane_base): the masks changed "
+            "after their maximum was taken, or n_labels is stale — the table would be missing those pixels"
+        )
 
 
 _meta_cache: dict = {}
@@ -242,8 +253,13 @@ def run_planes(
     n_z: int,
     out=None,
     stage_events=None,
+    status=None,
 ):
-    """Launch the hot path on the current stream; returns the dense fp64 table (device)."""
+    """Launch the hot path on the current stream; returns the dense fp64 table (device).
+
+    ``status``: optional int32 device tensor whose first element receives the call's error flags (stream-ordered;
+    check it with :func:`raise_on_status` once it is on the host).  Re-entrant: the scratch memory of a call comes from
+    the caching allocator on the current stream, nothing is shared between calls in flight."""
     import torch
 
     if plan.error is not None and int(np.sum(n_labels)) > 0:
@@ -261,9 +277,24 @@ def run_planes(
         return out
     if plan.requests and plan.max_channel >= n_channels:
         raise IndexError(f"index {plan.max_channel} is out of bounds for axis 1 with size {n_channels}")
+    plane_tile = np.asarray(plane_tile, dtype=np.int32)
+    tile_offset = np.ascontiguousarray(tile_offset, dtype=np.int64)
+    if plan.requests:
+        # every label plane must lie inside the pixel window of its tile (the reference indexes pixels[tile][mask] and
+        # raises IndexError when the shapes differ; the kernels would read neighbouring tiles)
+        if len(plane_tile) and (plane_tile.min() < 0 or plane_tile.max() >= len(tile_offset)):
+            raise IndexError(f"tile index {int(plane_tile.max())} is out of bounds for {len(tile_offset)} pixel tiles")
+        elems = (pixels.untyped_storage().nbytes() // pixels.element_size()) - pixels.storage_offset()
+        last = int(tile_offset.max()) + (max(1, n_channels) - 1) * int(chan_stride) + (max(1, n_z) - 1) * int(z_stride) \
+            + (H - 1) * int(row_stride) + W
+        if int(tile_offset.min()) < 0 or last > elems or W > int(row_stride):
+            raise IndexError(
+                f"label planes of {H} x {W} do not fit the pixel tiles (row stride {int(row_stride)}, last element "
+                f"{last} of {elems}): masks and pixels must have the same (Y, X)"
+            )
     base = np.zeros(P + 1, dtype=np.int32)
     np.cumsum(n_labels, out=base[1:])
-    meta = _device_meta(device, np.asarray(plane_tile, dtype=np.int32), base, np.ascontiguousarray(tile_offset, dtype=np.int64))
+    meta = _device_meta(device, plane_tile, base, tile_offset)
     req_t, col_t = plan.device_arrays(device)
 
     a = nat.ExtractArgs()
@@ -297,10 +328,15 @@ def run_planes(
         a.stage_events = C.cast(ev, C.POINTER(C.c_void_p))
     need = C.c_size_t(0)
     nat.check(lib.abx_extract_workspace_bytes(C.byref(a), C.byref(need)), "abx_extract_workspace_bytes")
-    ws = _workspace(device, need.value)
-    a.workspace = ws.data_ptr()
-    a.workspace_bytes = ws.numel()
+    # scratch of this call: from the caching allocator, on the current stream (a block freed here is handed out again
+    # only to later work of the same stream, so nothing in flight can be overwritten)
     with torch.cuda.device(device):
+        ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=device)
+        a.workspace = ws.data_ptr()
+        a.workspace_bytes = ws.numel()
+        if status is not None:
+            assert status.dtype == torch.int32 and status.device == device
+            a.status = status.data_ptr()
         nat.check(lib.abx_extract(C.byref(a)), "abx_extract")
     # meta must outlive the launch: it is kept alive by the per-device cache
     return out

@@ -39,7 +39,13 @@ class ExtractionResults(list):
     items: tuple | None = None
 
 
-_last_items = {"items": None, "objects": None, "plan": None}
+class ItemTuple(tuple):
+    """The ``tileid_instructions`` tuple of :func:`process_tree_masks`, carrying what it was built from (the compiled
+    plan and the object list) so that :func:`extract_tree` need not re-derive them from |objects| x |instructions|
+    items.  A plain tuple to every consumer; nothing is kept in module state, so concurrent callers do not interfere."""
+
+    plan: "engine.Plan | None" = None
+    objects: "list | None" = None
 
 
 def _as_mask_list(masks):
@@ -92,8 +98,11 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
         T, C_, Z_, Y, X = pixels.shape
         offs = np.arange(T, dtype=np.int64) * (C_ * Z_ * Y * X)
         cs, zs, rs = Z_ * Y * X, Y * X, X
-    table = engine.run_planes(plan, labels_dev, plane_tile, n_labels, px_dev, offs, cs, zs, rs, C_, Z_)
-    return table.cpu().numpy()
+    buf, table, status = engine.alloc_table(n_objects, plan.n_columns, device)
+    engine.run_planes(plan, labels_dev, plane_tile, n_labels, px_dev, offs, cs, zs, rs, C_, Z_, out=table, status=status)
+    host = buf.cpu()  # one copy: the table and the call's error flags
+    engine.raise_on_status(host[n_objects * plan.n_columns :].view(torch.int32)[0])
+    return host[: n_objects * plan.n_columns].view(n_objects, plan.n_columns).numpy()
 
 
 class ExtractionTable:
@@ -218,19 +227,22 @@ def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
     done.synchronize()  # the row count has to reach the host; the pixel uploads keep running meanwhile
     n_labels = nmax_host.numpy().astype(np.int64)
     rows = np.concatenate([[0], np.cumsum(n_labels)])
-    table = torch.empty((int(rows[-1]), plan.n_columns), dtype=torch.float64, device=device)
+    n_rows, n_cols = int(rows[-1]), plan.n_columns
+    buf, table, status = engine.alloc_table(n_rows, n_cols, device, n_status=len(staged))
     p0 = 0
-    for tiles, px, ev in staged:
+    for k, (tiles, px, ev) in enumerate(staged):
         cur.wait_event(ev)
         p1 = p0 + len(tiles)
         offs = np.arange(len(tiles), dtype=np.int64) * (C_ * Z_ * Y * X)
         engine.run_planes(plan, lab[p0:p1], np.arange(len(tiles), dtype=np.int32), n_labels[p0:p1], px, offs,
-                          Z_ * Y * X, Y * X, X, C_, Z_, out=table[int(rows[p0]) : int(rows[p1])])
+                          Z_ * Y * X, Y * X, X, C_, Z_, out=table[int(rows[p0]) : int(rows[p1])], status=status[2 * k :])
         p0 = p1
-    host = torch.empty(table.shape, dtype=torch.float64, pin_memory=True)
-    host.copy_(table, non_blocking=True)
+    host = torch.empty(buf.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(buf, non_blocking=True)  # one copy: the table and every chunk's error flags
     cur.synchronize()
-    return host.numpy(), n_labels
+    for word in host[n_rows * n_cols :].view(torch.int32)[::2]:
+        engine.raise_on_status(word)
+    return host[: n_rows * n_cols].view(n_rows, n_cols).numpy(), n_labels
 
 
 def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | None = None,
@@ -278,8 +290,13 @@ def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | No
             offs = np.arange(T, dtype=np.int64) * (C_ * Z_ * Y * X)
             cs, zs, rs = Z_ * Y * X, Y * X, X
         n_labels = nmax.cpu().numpy().astype(np.int64)  # small D2H: the row count has to reach the host
-        table = engine.run_planes(plan, labels_dev, np.asarray(keep, dtype=np.int32), n_labels, px_dev, offs, cs, zs, rs, C_, Z_)
-        values = table.cpu().numpy()
+        n_rows = int(n_labels.sum())
+        buf, table, status = engine.alloc_table(n_rows, plan.n_columns, device)
+        engine.run_planes(plan, labels_dev, np.asarray(keep, dtype=np.int32), n_labels, px_dev, offs, cs, zs, rs, C_, Z_,
+                          out=table, status=status)
+        host = buf.cpu()
+        engine.raise_on_status(host[n_rows * plan.n_columns :].view(torch.int32)[0])
+        values = host[: n_rows * plan.n_columns].view(n_rows, plan.n_columns).numpy()
     cols = np.fromiter((c[0] for c in plan.inst_cols), dtype=np.int64, count=len(plan.inst_cols))
     objects = np.stack(
         [np.repeat(np.asarray(keep, dtype=np.int64), n_labels), np.concatenate([np.arange(1, k + 1) for k in n_labels])],
@@ -324,8 +341,8 @@ def process_tree_masks(
         if len(masks_in_tile):
             for mask_i in range(1, int(masks_in_tile.max()) + 1):
                 ind_masks.append((tile_i, mask_i))
-    tileid_instructions = tuple(product(ind_masks, instructions))
-    _last_items.update(items=tileid_instructions, objects=ind_masks, plan=engine.compile_instructions(instructions))
+    tileid_instructions = ItemTuple(product(ind_masks, instructions))
+    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions), ind_masks
     extra = {}
     if cp_measure_kwargs is not None:
         extra["cp_measure_kwargs"] = cp_measure_kwargs
@@ -365,8 +382,8 @@ def process_tree_masks_overlap(
             ids = ids[ids > 0]
             inverse_mappings[(tile_i, stack_i)] = np.concatenate([[0], ids]).astype(np.int64)
             tile_stack_mask.extend((tile_i, stack_i, mask_i) for mask_i in range(1, len(ids) + 1))
-    tileid_instructions = tuple(product(tile_stack_mask, instructions))
-    _last_items.update(items=tileid_instructions, objects=tile_stack_mask, plan=engine.compile_instructions(instructions))
+    tileid_instructions = ItemTuple(product(tile_stack_mask, instructions))
+    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions), tile_stack_mask
     extra = {}
     if cp_measure_kwargs is not None:
         extra["cp_measure_kwargs"] = cp_measure_kwargs
@@ -396,8 +413,8 @@ def extract_tree(
     if not len(tileid_instructions):
         return results
     masks = _as_mask_list(masks)
-    if tileid_instructions is _last_items["items"]:
-        plan, objects = _last_items["plan"], _last_items["objects"]
+    if isinstance(tileid_instructions, ItemTuple) and tileid_instructions.plan is not None:
+        plan, objects = tileid_instructions.plan, tileid_instructions.objects
         n_inst = len(plan.instructions)
         row_of_item = inst_of_item = None  # object-major product: implicit
     else:

@@ -30,7 +30,9 @@
  * every buffer (device memory unless stated otherwise); nothing is allocated on the
  * hot call — size the scratch with abx_extract_workspace_bytes().  All strides and
  * offsets are in ELEMENTS of the addressed array.  Calls are re-entrant across
- * streams and devices; the only global state is the thread-local error string.
+ * streams and devices as long as every call in flight has its own workspace.  State the library keeps: the
+ * thread-local error string, and per (host thread, device) one helper stream with two events (created on first use,
+ * kept for the life of the thread) and the cached encodings of the last call's TMA descriptors.
  */
 #ifndef ALIBY_B200_H
 #define ALIBY_B200_H
@@ -42,7 +44,7 @@
 extern "C" {
 #endif
 
-#define ABX_VERSION 2
+#define ABX_VERSION 3
 
 typedef enum abx_status {
   ABX_OK = 0,
@@ -162,6 +164,11 @@ typedef struct abx_extract_args {
    * to the TMA unit (whole rows of row_stride elements, out-of-buffer parts of a box zero-filled); without it, or for
    * layouts TMA cannot address (unaligned base / strides, Z stacks), the statistics kernel gathers with plain loads. */
   int64_t pixel_elems;
+  /* optional (ABI 3): device uint32 that receives the call's error flags when the kernels have run, stream-ordered like
+   * the table (copy it back together with the table).  Bit 0: a label above its plane's n_labels
+   * (plane_base[p + 1] - plane_base[p]) was met — those pixels belong to no row of the table and the background
+   * statistics of that plane are not meaningful; the caller passed a stale or wrong plane_base. */
+  uint32_t* status;
 } abx_extract_args;
 
 int abx_version(void);

@@ -40,6 +40,9 @@ def _axes_from_window(win: np.ndarray, r0: int, c0: int):
     return minor, major, from_edge
 
 
+BBOX_METRICS = ("bbox_rmin", "bbox_rmax", "bbox_cmin", "bbox_cmax")
+
+
 class PlaneIndex:
     """Sort-by-label index of one label plane."""
 
@@ -79,6 +82,8 @@ def shape_metric(index: PlaneIndex, lab: int, metric: str):
         return (4 * np.pi * radius**3) / 3
     if metric == "bbox":
         return index.bbox(lab) if n else None
+    if metric in BBOX_METRICS:  # extension (AreaShape_BoundingBox* territory): inclusive bbox, NaN for absent ids
+        return np.float64(index.bbox(lab)[BBOX_METRICS.index(metric)]) if n else np.float64(np.nan)
     # EDT family
     if n == 0:
         return {
@@ -153,7 +158,7 @@ def intensity_metric(index: PlaneIndex, lab: int, img: np.ndarray, metric: str):
     raise KeyError(metric)
 
 
-SHAPE_METRICS = set(port.MASK_ONLY) | {"bbox"}
+SHAPE_METRICS = set(port.MASK_ONLY) | {"bbox"} | set(BBOX_METRICS)
 BACKGROUND_METRICS = {"imBackground", "background_max5"}
 
 
@@ -173,7 +178,7 @@ def run_tree(tree: dict, masks, pixels: np.ndarray):
         index = PlaneIndex(np.asarray(lab_plane))
         projected: dict = {}
         for j, (ch, red, metric) in enumerate(instructions):
-            if metric not in port.CELL_METRICS and metric not in {"max", "min"} | BACKGROUND_METRICS:
+            if metric not in port.CELL_METRICS and metric not in {"max", "min"} | BACKGROUND_METRICS | set(BBOX_METRICS):
                 raise KeyError(metric)
             img = None
             if ch != "None":

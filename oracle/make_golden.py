@@ -281,6 +281,59 @@ def main():
     )
     print("overlap", len(items))
 
+    # ---- 8. profile assembly: get_profiles_from_state exec'd out of pipe_core.py (the module needs numcodecs/dask/nahual) ----
+    # state of a 3-time-point run with two extract steps of one prefix (concatenated) and one extractmulti step
+    # (joined on the metadata keys), one time point without objects; results are what the reference's own
+    # process_tree_masks returns, cast to float like a pipeline does before format_extraction accepts them.
+    import pyarrow
+    import pyarrow.parquet
+
+    src = open("/root/reference/src/aliby/pipe_core.py").read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_profiles_from_state")
+    ns = {"numpy": np, "np": np, "pyarrow": pyarrow, "pa": pyarrow, "format_extraction": ref_extract.format_extraction}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "pipe_core.py", "exec"), ns)
+    # (steps of one prefix must share their columns: pyarrow.concat_tables, pipe_core.py:501, rejects differing schemas —
+    # the stock builder gives every object the same tree, pipe_builder.py:115-134)
+    tree_a = {"None": {"None": ["area", "centroid_x"]}, 0: {"max": ["mean", "median"]}, 1: {"max": ["max5px_median", "total"]}}
+    state = {"data": {"extract_nuclei": [], "extract_cell": [], "extractmulti_nuclei": []}}
+    inputs = {}
+    for tp in range(3):
+        p, l = synth.make_field(seed=60 + tp, shape=(48, 64), n_channels=2, n_objects=4, n_z=1, semi_axes=(3, 7))
+        if tp == 1:
+            l = np.zeros_like(l)  # a time point without objects: its tables are skipped (pipe_core.py:486)
+        _, l2 = synth.make_field(seed=80 + tp, shape=(48, 64), n_channels=2, n_objects=3, n_z=1, semi_axes=(4, 9))
+        inputs[f"pixels{tp}"], inputs[f"labels{tp}"], inputs[f"labels_cell{tp}"] = p, l, l2
+        for step, lab_img in (("extract_nuclei", l), ("extract_cell", l2)):
+            items, res = ref_extract.process_tree_masks(tree_a, lab_img, p, ref_extract.extract_tree)
+            state["data"][step].append((items, [float(r) for r in res]))
+        # colocalisation-shaped results: dict-valued metrics keyed by ((ch0, ch1), red_ch, red_z, metric) instructions
+        n_obj = int(l.max())
+        multi_items = tuple(((0, lab), ((0, 1), "None", "max", "pearson")) for lab in range(1, n_obj + 1))
+        multi_res = [{"Correlation_Pearson": np.array([0.25 * lab + tp])} for lab in range(1, n_obj + 1)]
+        state["data"]["extractmulti_nuclei"].append((multi_items, multi_res))
+    pipeline = {"steps": {"tile": {}, "segment_nuclei": {}, "extract_nuclei": {}, "extract_cell": {}, "extractmulti_nuclei": {}}}
+    profiles = ns["get_profiles_from_state"](state, pipeline)
+    pq_path = os.path.join(tempfile.mkdtemp(prefix="aliby_pq_"), "profiles.parquet")
+    pyarrow.parquet.write_table(profiles, pq_path, compression="zstd")  # pipe_core.py:411-413
+    back = pyarrow.parquet.read_table(pq_path)
+    cols = profiles.column_names
+    np.savez_compressed(
+        f"{OUT}/profiles.npz",
+        tree_a=json.dumps({str(k): v for k, v in tree_a.items()}),
+        columns=json.dumps(cols),
+        types=json.dumps([str(t) for t in profiles.schema.types]),
+        parquet_types=json.dumps([str(t) for t in back.schema.types]),
+        n_rows=profiles.num_rows,
+        **{f"col{j}": (np.array([x or "" for x in profiles.column(c).to_pylist()], dtype=str)
+                       if str(profiles.schema.types[j]) == "string" else np.asarray(profiles.column(c).to_pylist(), dtype=float))
+           for j, c in enumerate(cols)},
+        **{f"null{j}": np.asarray(profiles.column(c).is_null().to_pylist()) for j, c in enumerate(cols)},
+        **{f"state_{step}_{tp}_values": np.array([r if isinstance(r, float) else float(r["Correlation_Pearson"][0]) for r in out[1]])
+           for step, outs in state["data"].items() for tp, out in enumerate(outs)},
+        **inputs,
+    )
+    print("profiles", profiles.num_rows, "rows x", profiles.num_columns, "columns")
+
     with open(f"{OUT}/META.json", "w") as f:
         json.dump(meta, f)
 

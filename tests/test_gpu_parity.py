@@ -21,6 +21,7 @@ RTOL_LOOSE = 1e-9
 
 SHAPE = ["area", "centroid", "centroid_x", "centroid_y", "conical_volume", "eccentricity",
          "min_maj_approximation", "spherical_volume", "volume"]
+BBOX = ["bbox_rmin", "bbox_rmax", "bbox_cmin", "bbox_cmax"]  # extensions: inclusive bounding box, NaN for absent ids
 INTENSITY = ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median",
              "moment_of_inertia", "ratio"]
 
@@ -148,11 +149,11 @@ def test_config_c1(ab):
     from aliby_b200 import synth
 
     pixels, labels = synth.make_field(synth.CONFIG_SEEDS["C1"], (1080, 1080), 2, 300)
-    tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume"]},
+    tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume"] + BBOX},
             0: {"max": ["mean", "std", "median", "total", "max2p5pc", "max5px_median", "max", "min"]},
             1: {"max": ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median", "moment_of_inertia"]}}
     items, got = against_oracle(ab, tree, labels, pixels)
-    assert len(items) == int(labels.max()) * 22
+    assert len(items) == int(labels.max()) * 26
 
 
 def test_config_c2_full_size(ab):
@@ -160,7 +161,7 @@ def test_config_c2_full_size(ab):
     from aliby_b200 import synth
 
     pixels, labels = synth.make_field(synth.CONFIG_SEEDS["C2"], (2160, 2160), 5, 2000)
-    tree = {"None": {"None": SHAPE}}
+    tree = {"None": {"None": SHAPE + BBOX}}
     for ch in range(5):
         tree[ch] = {"max": INTENSITY + ["max", "min"]}
     items, got = against_oracle(ab, tree, labels, pixels)
@@ -463,7 +464,7 @@ def test_fuzz_random_label_planes(ab, seed):
         masks.append(lab)
     pixels = rng.integers(0, np.iinfo(dtype).max + 1, size=(n_tiles, 2, Z, H, W)).astype(dtype)
     tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume",
-                              "min_maj_approximation"]},
+                              "min_maj_approximation"] + BBOX},
             0: {"max": INTENSITY + ["max", "min", "imBackground", "background_max5"]},
             1: {"add": ["mean", "median", "total", "total_squared", "max2p5pc", "max5px_median", "std"]}}
     against_oracle(ab, tree, masks if n_tiles > 1 else masks[0], pixels)
@@ -502,7 +503,7 @@ def test_fuzz_tma_staged_windows(ab, seed):
     else:
         pixels = rng.integers(0, top + 1, size=(n_tiles, 3, Z, H, W)).astype(dtype)
     tree = {"None": {"None": ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume",
-                              "min_maj_approximation"]},
+                              "min_maj_approximation"] + BBOX},
             0: {"max": INTENSITY + ["max", "min"]},
             1: {"max": ["median", "mean"], "add": ["total", "median"]},
             2: {"add": ["mean", "median", "total", "total_squared", "max2p5pc", "max5px_median", "std", "moment_of_inertia"]}}
@@ -622,3 +623,66 @@ def test_background_of_a_whole_field_streaming_path(ab):
         col = tab.values[:, tab.names.index(name)]
         assert (col == want).all(), (name, col[:3], want)
     assert dt < 5.0
+
+
+def test_stale_label_count_is_reported(ab):
+    """A label above the plane's n_labels (a caller's stale plane_base) must not produce a silently wrong table: the
+    device error flag travels back with the table (abx_extract_args.status) and raises."""
+    import torch
+
+    from aliby_b200 import engine, synth
+
+    pixels, labels = synth.make_field(77, (96, 128), 1, 6, semi_axes=(4, 9))
+    plan = engine.compile_tree({"None": {"None": ["area"]}, 0: {"max": ["mean"]}})
+    dev = torch.device("cuda", 0)
+    lab = torch.from_numpy(labels[None].astype(np.uint16)).to(dev)
+    px = torch.from_numpy(pixels).to(dev)
+    n_true = int(labels.max())
+    for n_given, bad in ((n_true, False), (n_true - 2, True)):
+        buf, table, status = engine.alloc_table(n_given, plan.n_columns, dev)
+        engine.run_planes(plan, lab, np.zeros(1, np.int32), np.array([n_given]), px, np.zeros(1, np.int64),
+                          96 * 128, 96 * 128, 128, 1, 1, out=table, status=status)
+        word = int(status.cpu()[0])
+        assert bool(word & 1) == bad
+        if bad:
+            with pytest.raises(IndexError, match="label id exceeds"):
+                engine.raise_on_status(word)
+    # and through the public API: masks whose shape differs from the pixels' (the reference raises IndexError too)
+    with pytest.raises(IndexError):
+        ab.process_tree_masks({0: {"max": ["mean"]}}, np.pad(labels, ((0, 8), (0, 0))), pixels, ab.extract_tree)
+
+
+def test_concurrent_calls_two_threads_two_streams(ab):
+    """The host engine is re-entrant: two threads, each on its own stream of one device, extract different fields at
+    the same time and both get the oracle's numbers (per-call scratch, no shared item state)."""
+    import threading
+
+    import torch
+
+    from aliby_b200 import synth
+    from oracle import fast
+
+    tree = {"None": {"None": ["area", "eccentricity"]}, 0: {"max": ["mean", "median", "max2p5pc", "std"]},
+            1: {"max": ["total", "max5px_median"]}}
+    fields = [synth.make_field(300 + k, (256, 320), 2, 40, semi_axes=(5, 20)) for k in range(2)]
+    want = []
+    for px, lab in fields:
+        _, w = fast.run_tree(tree, lab, px)
+        want.append(as_float_pairs(w)[0])
+    errors, results = [], [None, None]
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(20):
+                    items, got = ab.process_tree_masks(tree, fields[k][1], fields[k][0], ab.extract_tree)
+                    results[k] = (items, got)
+                    check_items(items, got, want[k])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors

@@ -1,6 +1,7 @@
 """CPU-only checks: C-ABI exports, plan compiler, host-side table logic, sharding (gloo, world 2)."""
 
 import ctypes
+import json
 import os
 import re
 import subprocess
@@ -24,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(nat.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert nat.lib().abx_version() == 2
+    assert nat.lib().abx_version() == 3
     # struct mirrors: sizes must agree with the C side (48-byte records, 16-byte requests)
     assert ctypes.sizeof(nat.ObjectRec) == 48 and ctypes.sizeof(nat.Request) == 16 and ctypes.sizeof(nat.Column) == 8
 
@@ -285,3 +286,102 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
     assert int(out["sizeof_rec"]) == ctypes.sizeof(nat.ObjectRec)
     assert out["enums"].split() == [str(v) for v in (nat.F64, nat.RED_DIV, nat.METRIC["background_max5"], nat.METRIC["mean"],
                                                      nat.F_MOI, -2)]
+
+
+def _golden_profile_state():
+    """(state, pipeline, golden) of tests/golden/profiles.npz: the (instructions, results) pairs the reference produced."""
+    from itertools import product
+
+    from conftest import load_golden
+
+    g = load_golden("profiles.npz")
+    tree = {(int(k) if k.lstrip("-").isdigit() else k): v for k, v in json.loads(str(g["tree_a"])).items()}
+    insts = [(ch, red, m) for ch, reds in tree.items() for red, ms in reds.items() for m in ms]
+    state = {"data": {"extract_nuclei": [], "extract_cell": [], "extractmulti_nuclei": []}}
+    for tp in range(3):
+        for step, key in (("extract_nuclei", f"labels{tp}"), ("extract_cell", f"labels_cell{tp}")):
+            n_obj = int(g[key].max())
+            items = tuple(product([(0, lab) for lab in range(1, n_obj + 1)], insts))
+            state["data"][step].append((items, [float(v) for v in g[f"state_{step}_{tp}_values"]]))
+        n_obj = int(g[f"labels{tp}"].max())
+        multi_items = tuple(((0, lab), ((0, 1), "None", "max", "pearson")) for lab in range(1, n_obj + 1))
+        multi_res = [{"Correlation_Pearson": np.array([v])} for v in g[f"state_extractmulti_nuclei_{tp}_values"]]
+        state["data"]["extractmulti_nuclei"].append((multi_items, multi_res))
+    pipeline = {"steps": {"tile": {}, "segment_nuclei": {}, "extract_nuclei": {}, "extract_cell": {}, "extractmulti_nuclei": {}}}
+    return state, pipeline, g, tree
+
+
+def _assert_table_equals_golden(table, g):
+    """Names, order and types of the columns exactly; rows as a set keyed by (tp, tile, object, label): the reference's
+    pyarrow join (pipe_core.py:506-510) does not define a row order."""
+    cols = json.loads(str(g["columns"]))
+    types = json.loads(str(g["types"]))
+    assert table.column_names == cols
+    assert [str(t) for t in table.schema.types] == types
+    keys = [cols.index(f"metadata_{k}") for k in ("tp", "tile", "object", "label")]
+
+    def rows_of(columns, nulls):
+        n = len(columns[0])
+        rows = {}
+        for i in range(n):
+            vals = tuple(None if nulls[j][i] else (columns[j][i].item() if hasattr(columns[j][i], "item") else columns[j][i])
+                         for j in range(len(cols)))
+            rows[tuple(vals[k] for k in keys)] = vals
+        assert len(rows) == n  # keys are unique
+        return rows
+
+    got_cols = [table.column(c).to_pylist() for c in cols]
+    got = rows_of(got_cols, [[v is None for v in col] for col in got_cols])
+    want = rows_of([g[f"col{j}"] for j in range(len(cols))], [g[f"null{j}"] for j in range(len(cols))])
+    assert got.keys() == want.keys()
+    for k, w in want.items():
+        for c, a, b in zip(cols, got[k], w):
+            assert (a == b) or (a is None and b is None) or (a != a and b != b), (k, c, a, b)
+
+
+def test_profiles_match_the_reference_table(tmp_path):
+    """pipe.get_profiles_from_state and write_profiles against the table the REFERENCE's get_profiles_from_state
+    (pipe_core.py:453-512, exec'd from source by oracle/make_golden.py) built from the same state: names, order,
+    types, values, nulls of the extract/extractmulti join, and the zstd Parquet schema (pipe_core.py:411-413)."""
+    import pyarrow.parquet as pq
+
+    from aliby_b200 import pipe
+
+    state, pipeline, g, _ = _golden_profile_state()
+    table = pipe.get_profiles_from_state(state, pipeline)
+    assert table.num_rows == int(g["n_rows"])
+    _assert_table_equals_golden(table, g)
+    path = pipe.write_profiles(table, tmp_path, "pos001")
+    back = pq.read_table(path)
+    assert back.column_names == json.loads(str(g["columns"]))
+    assert [str(t) for t in back.schema.types] == json.loads(str(g["parquet_types"]))
+    assert pq.ParquetFile(path).metadata.row_group(0).column(0).compression == "ZSTD"
+
+
+def test_dense_profile_path_matches_the_reference_table():
+    """profiles_from_tables (dense ExtractionTable per time point, no per-item lists) reproduces the reference's rows of
+    one extract step: same columns, types and values as the golden profile table restricted to that object."""
+    from aliby_b200 import pipe
+    from aliby_b200.extract import ExtractionTable
+
+    state, pipeline, g, tree = _golden_profile_state()
+    insts = [(ch, red, m) for ch, reds in tree.items() for red, ms in reds.items() for m in ms]
+    names = ["/".join(str(x) for x in i) + f"/{i[-1]}" for i in insts]
+    tables = []
+    for tp in range(3):
+        items, res = state["data"]["extract_nuclei"][tp]
+        n_obj = len(items) // len(insts)
+        objs = np.array([(0, lab) for lab in range(1, n_obj + 1)], dtype=np.int64).reshape(n_obj, 2)
+        tables.append(ExtractionTable(objs, names, np.asarray(res, dtype=float).reshape(n_obj, len(insts))) if n_obj else None)
+    got = pipe.profiles_from_tables(tables, "nuclei")
+    # the golden rows of this object, in the golden's order
+    cols = json.loads(str(g["columns"]))
+    obj_col = g[f"col{cols.index('metadata_object')}"]
+    sel = np.flatnonzero(obj_col == "nuclei")
+    assert got.num_rows == len(sel)
+    for c in got.column_names:
+        j = cols.index(c)
+        want = g[f"col{j}"][sel]
+        for a, b in zip(got.column(c).to_pylist(), want):
+            assert (a == b) or (a != a and b != b), (c, a, b)
+        assert str(got.schema.field(c).type) == json.loads(str(g["types"]))[j], c

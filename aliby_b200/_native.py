@@ -43,11 +43,37 @@ METRIC = {
     "min": 26,
     "imBackground": 27,
     "background_max5": 28,
+    # cp_measure `intensity` / `sizeshape` building blocks (ABX_M_CP_*)
+    "cp_lower_quartile": 32,
+    "cp_median": 33,
+    "cp_upper_quartile": 34,
+    "cp_mad": 35,
+    "cp_mass_displacement": 36,
+    "cp_center_mass_x": 37,
+    "cp_center_mass_y": 38,
+    "cp_max_pos_x": 39,
+    "cp_max_pos_y": 40,
+    "cp_zero": 41,
+    "cp_center_mass_z": 42,
+    "cp_bbox_area": 48,
+    "cp_bbox_max_x": 49,
+    "cp_bbox_max_y": 50,
+    "cp_center_x": 51,
+    "cp_center_y": 52,
+    "cp_equivalent_diameter": 53,
+    "cp_extent": 54,
+    "cp_maximum_radius": 55,
+    "cp_mean_radius": 56,
+    "cp_eccentricity": 57,
+    "cp_major_axis_length": 58,
+    "cp_minor_axis_length": 59,
 }
-EDT_METRICS = {4, 5, 6, 7, 8}
+EDT_METRICS = {4, 5, 6, 7, 8, 55}       # need_edt bit 0 (three chained EDTs; 55: the maximum of the first)
+CONICAL_METRICS = {6, 56}               # need_edt bit 1 (sum of the first EDT)
+MOMENT_METRICS = {57, 58, 59}           # need_edt bit 2 (second coordinate moments)
 CONICAL_METRIC = 6
 
-F_MEDIAN, F_TOP2P5, F_TOP5, F_WRAPSQ, F_MOI = 1, 2, 4, 8, 16
+F_MEDIAN, F_TOP2P5, F_TOP5, F_WRAPSQ, F_MOI, F_CPQ, F_CPMAD = 1, 2, 4, 8, 16, 32, 64
 F_HAS_DIV = 0x40000000
 
 EXPORTS = (

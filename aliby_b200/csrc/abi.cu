@@ -63,6 +63,8 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   // torus bitmaps of the label scan (+ one dummy for out-of-range labels), routing of the plan kernel
   ws->bitmaps = reinterpret_cast<u64*>(b + off);
   off = align_up(off + ((size_t)a->n_objects + 1) * 512);
+  ws->mom = reinterpret_cast<MaskMoments*>(b + off);
+  off = align_up(off + ((a->need_edt & 4) ? (size_t)a->n_objects * sizeof(MaskMoments) : 0));
   ws->plan = reinterpret_cast<ObjPlan*>(b + off);
   off = align_up(off + n_rec * sizeof(ObjPlan));
   ws->order_stats = reinterpret_cast<int*>(b + off);
@@ -207,7 +209,7 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   // The few (object, request) pairs the sweep kernel left over (windows too wide at their alignment, wide value ranges
   // of chunked windows) go through the gather kernel on a helper stream, one warp per CTA, next to the shape kernel:
   // their cost is one warp's latency, which hides behind the EDT launch.
-  const bool edt = args->need_edt && args->n_objects > 0;
+  const bool edt = (args->need_edt & 3) && args->n_objects > 0;
   Helper* hp = (sweep && edt) ? helper_stream() : nullptr;
   if (sweep && !hp && (rc = launch_object_stats_warp(&red, ws, st, true))) return rc;
   if (hp) cudaEventRecord(hp->fork, st);

@@ -21,7 +21,15 @@ struct ChanStats {
   u64 top5_sum;    // sum of the min(5, n) largest values
   u32 vmin, vmax;
   u32 med_lo, med_hi;  // the two middle order statistics (equal for odd n)
+  // cp_measure `intensity` (object_sweep.cu only): order statistics i = floor(n f) and i + 1 for f = 1/4, 1/2, 3/4;
+  // the same pair for floor(|2 v - 2 median| / 2) with f = 1/2 (MAD; bit 31 of mad_hi: the deviations are half-integers);
+  // position of the first maximum, (row << 16) | column relative to the bounding box
+  u32 q[6];
+  u32 mad_lo, mad_hi;
+  u32 maxpos;
+  u32 pad_;
 };
+static_assert(sizeof(ChanStats) == 128, "ChanStats layout");
 
 // The same 96-byte slot for a request whose values are floating point (float pixels or the `div` reducer).
 struct FloatStats {
@@ -63,8 +71,15 @@ constexpr int kCounterWords = 32;  // err[0] + list_counts[31], zeroed by the la
 constexpr int kCntStatsList = 0, kCntEdtList = 1, kCntGather = 2, kCntLeftover = 3, kCntEdtWork = 4, kCntLeftoverWork = 6,
               kCntRest = 8, kCntOrderBig = 12, kCntOrderSmall = 13, kCntSweepWork = 14, kCntEdtBig = 15, kCntEdtSmall = 16;
 
+// Raw second moments of an object's pixel coordinates relative to its bounding box origin (plan kernel, from the bitmap)
+struct MaskMoments {
+  u64 s_rr, s_cc, s_rc;  // sum r^2, sum c^2, sum r c
+  u64 pad_;
+};
+
 struct Workspace {
   abx_object_rec* recs;  // [n_objects + n_planes]
+  MaskMoments* mom;      // [n_objects] when need_edt bit 2
   u64* bitmaps;          // [n_objects + 1][64] torus bitmaps written by the label scan (label_scan.cu)
   ObjPlan* plan;         // [n_objects + n_planes]
   int* order_stats;      // [n_objects + n_planes] work order of the statistics kernel: big objects from the front, others from the back

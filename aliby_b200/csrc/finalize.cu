@@ -61,8 +61,17 @@ __device__ double float_metric(const FloatStats& f, int metric, u32 n_px, int pi
   }
 }
 
+// CellProfiler's order-statistic rule (MeasureObjectIntensity): q = n f, i = floor(q); v[i] (1 - frac) + v[i + 1] frac when
+// i < n - 1, else v[i].  k = 4 f in {1, 2, 3}; (lo, hi) = v[i], v[min(i + 1, n - 1)]; half: the values are lo + 1/2, hi + 1/2.
+__device__ __forceinline__ double cp_quantile(u32 n, u32 k, double lo, double hi) {
+  const u32 i = (n * k) >> 2;
+  const double frac = (double)((n * k) & 3u) * 0.25;
+  return i < n - 1u ? lo * (1.0 - frac) + hi * frac : lo;
+}
+
 __device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const abx_object_rec* __restrict__ recs,
                                 const ChanStats* __restrict__ chan, const ShapeStats* __restrict__ shape,
+                                const MaskMoments* __restrict__ mom,
                                 const int32_t* __restrict__ plane_base, int n_planes, int n_objects,
                                 const abx_request* __restrict__ requests, int n_requests,
                                 const abx_column* __restrict__ columns, int pixel_dtype) {
@@ -70,7 +79,36 @@ __device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const
   const double n = (double)r.n;
   const double kNaN = nan("");
   double v = kNaN;
-  if (cd.metric < 16) {
+  if (cd.metric >= ABX_M_CP_BBOX_AREA) {
+    // ---- cp_measure `sizeshape` subset (label plane only) ----
+    if (r.n) {
+      const double hh = (double)(r.rmax - r.rmin + 1u), ww = (double)(r.cmax - r.cmin + 1u);
+      switch (cd.metric) {
+        case ABX_M_CP_BBOX_AREA: v = hh * ww; break;
+        case ABX_M_CP_BBOX_MAX_X: v = (double)r.cmax + 1.0; break;  // exclusive, like skimage's bbox
+        case ABX_M_CP_BBOX_MAX_Y: v = (double)r.rmax + 1.0; break;
+        case ABX_M_CP_CENTER_X: v = (double)(r.sum_col - r.n) / n; break;  // 0-based centroid
+        case ABX_M_CP_CENTER_Y: v = (double)(r.sum_row - r.n) / n; break;
+        case ABX_M_CP_EQUIVALENT_DIAMETER: v = sqrt(4.0 * n / 3.141592653589793); break;
+        case ABX_M_CP_EXTENT: v = n / (hh * ww); break;
+        case ABX_M_CP_MAXIMUM_RADIUS: v = sqrt((double)shape[obj].max_nn2); break;
+        case ABX_M_CP_MEAN_RADIUS: v = shape[obj].sum_nn / n; break;
+        default: {
+          // second central moments of the coordinates from the raw sums relative to the bbox origin
+          const MaskMoments m = mom[obj];
+          const double sr = (double)(r.sum_row - (u64)r.n * (r.rmin + 1u)), sc = (double)(r.sum_col - (u64)r.n * (r.cmin + 1u));
+          const double mu_rr = ((double)m.s_rr - sr * sr / n) / n, mu_cc = ((double)m.s_cc - sc * sc / n) / n;
+          const double mu_rc = ((double)m.s_rc - sr * sc / n) / n;
+          const double half_tr = (mu_rr + mu_cc) / 2.0, dd = (mu_rr - mu_cc) / 2.0;
+          const double root = sqrt(dd * dd + mu_rc * mu_rc);
+          const double l1 = half_tr + root, l2 = fmax(half_tr - root, 0.0);
+          if (cd.metric == ABX_M_CP_MAJOR_AXIS_LENGTH) v = 4.0 * sqrt(l1);
+          else if (cd.metric == ABX_M_CP_MINOR_AXIS_LENGTH) v = 4.0 * sqrt(l2);
+          else v = l1 > 0.0 ? sqrt(1.0 - l2 / l1) : 0.0;  // ABX_M_CP_ECCENTRICITY
+        } break;
+      }
+    }
+  } else if (cd.metric < 16) {
     double minor = 0, major = 0;
     if (cd.metric == ABX_M_ECCENTRICITY || cd.metric == ABX_M_VOLUME || cd.metric == ABX_M_MINOR_AXIS ||
         cd.metric == ABX_M_MAJOR_AXIS) {
@@ -136,6 +174,29 @@ __device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const
       case ABX_M_MOMENT_OF_INERTIA: if (r.n) v = moment_of_inertia(c); break;
       case ABX_M_MAX: if (r.n) v = (double)c.vmax; break;
       case ABX_M_MIN: if (r.n) v = (double)c.vmin; break;
+      // ---- cp_measure `intensity` (object_sweep.cu fills q / mad / maxpos) ----
+      case ABX_M_CP_LOWER_QUARTILE: if (r.n) v = cp_quantile(r.n, 1u, (double)c.q[0], (double)c.q[1]); break;
+      case ABX_M_CP_MEDIAN: if (r.n) v = cp_quantile(r.n, 2u, (double)c.q[2], (double)c.q[3]); break;
+      case ABX_M_CP_UPPER_QUARTILE: if (r.n) v = cp_quantile(r.n, 3u, (double)c.q[4], (double)c.q[5]); break;
+      case ABX_M_CP_MAD:
+        if (r.n) {
+          const double half = (c.mad_hi >> 31) ? 0.5 : 0.0;
+          v = cp_quantile(r.n, 2u, (double)c.mad_lo + half, (double)(c.mad_hi & 0x7FFFFFFFu) + half);
+        }
+        break;
+      case ABX_M_CP_CENTER_MASS_X: if (r.n && c.sum) v = (double)r.cmin + (double)c.m10 / (double)c.sum; break;
+      case ABX_M_CP_CENTER_MASS_Y: if (r.n && c.sum) v = (double)r.rmin + (double)c.m01 / (double)c.sum; break;
+      case ABX_M_CP_MASS_DISPLACEMENT:
+        if (r.n && c.sum) {
+          const double dx = (double)r.cmin + (double)c.m10 / (double)c.sum - (double)(r.sum_col - r.n) / n;
+          const double dy = (double)r.rmin + (double)c.m01 / (double)c.sum - (double)(r.sum_row - r.n) / n;
+          v = sqrt(dx * dx + dy * dy);
+        }
+        break;
+      case ABX_M_CP_MAX_POS_X: if (r.n) v = (double)(r.cmin + (c.maxpos & 0xFFFFu)); break;
+      case ABX_M_CP_MAX_POS_Y: if (r.n) v = (double)(r.rmin + (c.maxpos >> 16)); break;
+      case ABX_M_CP_ZERO: if (r.n) v = 0.0; break;
+      case ABX_M_CP_CENTER_MASS_Z: if (r.n && c.sum) v = 0.0; break;
       case ABX_M_RATIO: default: break;  // cell.py:268-279: NaN for any 2-D image
     }
   }
@@ -149,7 +210,8 @@ constexpr int kFinObjects = 32, kFinWarps = 8, kFinColChunk = 64;
 
 __global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __restrict__ chan,
-                                const ShapeStats* __restrict__ shape, const int32_t* __restrict__ plane_base,
+                                const ShapeStats* __restrict__ shape, const MaskMoments* __restrict__ mom,
+                                const int32_t* __restrict__ plane_base,
                                 int n_planes, int n_objects, const abx_request* __restrict__ requests,
                                 int n_requests, const abx_column* __restrict__ columns, int n_columns,
                                 int pixel_dtype, double* __restrict__ table) {
@@ -163,7 +225,7 @@ finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __rest
     const int ncol = min(kFinColChunk, n_columns - cbase);
     for (int cl = warp; cl < ncol; cl += kFinWarps) {
       const int col = cbase + cl;
-      tile[lane][cl] = live ? finalize_cell(r, obj, col, recs, chan, shape, plane_base, n_planes, n_objects, requests,
+      tile[lane][cl] = live ? finalize_cell(r, obj, col, recs, chan, shape, mom, plane_base, n_planes, n_objects, requests,
                                             n_requests, columns, pixel_dtype)
                             : 0.0;
     }
@@ -183,7 +245,7 @@ int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t
   const i64 cells = (i64)a->n_objects * a->n_columns;
   if (cells == 0) return ABX_OK;
   const unsigned blocks = (unsigned)((a->n_objects + kFinObjects - 1) / kFinObjects);
-  finalize_kernel<<<blocks, kFinWarps * 32, 0, st>>>(ws.recs, ws.chan, ws.shape, a->plane_base, a->n_planes,
+  finalize_kernel<<<blocks, kFinWarps * 32, 0, st>>>(ws.recs, ws.chan, ws.shape, ws.mom, a->plane_base, a->n_planes,
                                                    a->n_objects, a->requests, a->n_requests, a->columns,
                                                    a->n_columns, a->pixel_dtype, a->table);
   return abx_check_cuda(cudaGetLastError(), "finalize");

@@ -77,7 +77,7 @@ __global__ void sqrt_table_kernel(double* tab, int n) {
 int abx_sqrt_table_entries() { return (kSide / 2) * (kSide / 2) + 1; }  // row distances are <= 32
 
 int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
-  if (!a->need_edt || a->n_objects == 0) return ABX_OK;
+  if (!(a->need_edt & 3) || a->n_objects == 0) return ABX_OK;
   constexpr size_t smem = (size_t)kGridWarps * kGridSlot;
   static thread_local bool done[64] = {false};
   int dev = 0;

@@ -87,7 +87,17 @@ struct PlanArgs {
   int* pair_list;   // (object, request) pairs for object_stats_warp
   int* edt_list;    // hand-over to the CTA-per-object shape kernel
   u32* counts;      // Workspace::list_counts
+  // cp_measure features
+  int cp_requests;        // some request wants ABX_F_CPQ / ABX_F_CPMAD: only the sweep kernel computes those
+  int want_moments;       // need_edt bit 2: second coordinate moments of every object, from its bitmap
+  const u64* bitmaps;
+  MaskMoments* mom;
+  u32* err;
 };
+
+// sum of k and of k^2 over [a, b]
+__device__ __forceinline__ u64 sum1(u64 a, u64 b) { return (a + b) * (b - a + 1) / 2; }
+__device__ __forceinline__ u64 sum2(u64 a, u64 b) { return (b * (b + 1) * (2 * b + 1) - (a ? (a - 1) * a * (2 * a - 1) : 0)) / 6; }
 
 __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,6 +148,33 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
       const u32 b = atomicAdd(a.counts + kCntLeftover, (u32)a.n_requests);  // rare: no aggregation
       for (int q = 0; q < a.n_requests; ++q) a.pair_list[b + q] = i * a.n_requests + q;
     }
+    if (a.cp_requests && ((hand && !is_bg) || too_wide)) atomicOr(a.err, 2u);  // status bit 1: cp statistics not served
+  }
+  // ---- second moments of the pixel coordinates (cp_measure sizeshape), relative to the bounding box origin ----
+  if (a.want_moments && live && !is_bg) {
+    MaskMoments mm;
+    mm.s_rr = mm.s_cc = mm.s_rc = mm.pad_ = 0;
+    if (rec.n > 0 && h <= kSide && w <= kSide) {
+      const u64* bm = a.bitmaps + (size_t)i * 64u;
+      const u32 rot = rec.cmin & 63u;
+      for (int r = 0; r < h; ++r) {
+        u64 m = bm[(rec.rmin + (u32)r) & 63u];
+        m = (m >> rot) | (rot ? (m << (64u - rot)) : 0ull);
+        while (m) {  // run by run: closed forms for sum c and sum c^2
+          const u32 c0 = (u32)__ffsll((long long)m) - 1u;
+          const u64 run = m >> c0;
+          const u32 len = (~run) ? (u32)__ffsll((long long)~run) - 1u : 64u - c0;
+          const u64 s1 = sum1(c0, c0 + len - 1u);
+          mm.s_cc += sum2(c0, c0 + len - 1u);
+          mm.s_rc += (u64)r * s1;
+          mm.s_rr += (u64)r * (u64)r * len;
+          m = (len + c0 >= 64u) ? 0ull : (m & (~0ull << (c0 + len)));
+        }
+      }
+    } else if (rec.n > 0) {
+      atomicOr(a.err, 2u);  // a cell above 64 x 64 has no bitmap
+    }
+    a.mom[i] = mm;
   }
   // ---- shape ----
   if (a.need_edt) {
@@ -160,7 +197,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
 struct Geo {  // one object's window as the kernel sees it (warp-uniform)
   int obj;
   int tma_x, tma_y;  // box coordinates of the window in channel 0
-  u32 n, h, w;
+  u32 n, h, w, s_px;
   u32 rot, row0;     // bitmap rotation (columns) and first bitmap row
   u32 pitchB;        // window row pitch in bytes (a multiple of 16)
   u32 h8, R;         // rows rounded up to whole boxes of 8; rows per chunk (a multiple of 8; == h8: one chunk)
@@ -175,9 +212,9 @@ __device__ __forceinline__ Geo make_geo(const ObjPlan& pl, int obj, u32 flex_byt
   g.h = (pl.geom & 63u) + 1u;
   g.w = ((pl.geom >> 6) & 63u) + 1u;
   g.row0 = (pl.geom >> 12) & 63u;
-  const u32 s_px = pl.geom >> 24;
-  g.rot = (((pl.geom >> 18) & 63u) - s_px) & 63u;
-  g.pitchB = ((g.w + s_px) * (u32)sizeof(PX) + 15u) & ~15u;
+  g.s_px = pl.geom >> 24;
+  g.rot = (((pl.geom >> 18) & 63u) - g.s_px) & 63u;
+  g.pitchB = ((g.w + g.s_px) * (u32)sizeof(PX) + 15u) & ~15u;
   g.h8 = (g.h + 7u) & ~7u;
   const u32 list_bytes = ((g.n + 1u) & ~1u) * 2u;
   g.R = g.h8;
@@ -273,8 +310,9 @@ __device__ __forceinline__ void zero_touched(u32* h, u32 rot, u32 per) {
 }
 
 // Locate four ranks in the circular histogram: relative bin j lives at h[(j + rot) & 1023], rot a multiple of 4, bins
-// [nb, 1024) relative are zero.  Same scheme and outputs as find_ranks32 (warp_common.cuh); the touched bins are zeroed
-// on the way out.
+// [nb, 1024) relative are zero.  Same scheme and outputs as find_ranks32 (warp_common.cuh); kZero: the touched bins are
+// zeroed on the way out.
+template <bool kZero>
 __device__ __forceinline__ void find_ranks_rot(u32* h, u32 rot, u32 nb, const u32 (&ranks)[4], u32* t) {
   const u32 lane = lane_id();
   const u32 per = bins_per_lane(nb);
@@ -315,7 +353,7 @@ __device__ __forceinline__ void find_ranks_rot(u32* h, u32 rot, u32 nb, const u3
     lq += c4[k] * (lb + k);
   }
   __syncwarp();
-  zero_touched(h, rot, per);
+  if (kZero) zero_touched(h, rot, per);
   u32 ic = lc, iq = lq;
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {
@@ -345,13 +383,26 @@ struct Ranked {
   u64 top2p5_sum, top5_sum;
 };
 
-// Order statistics of a request whose values span more than the circular histogram resolves: coarse histogram of
-// (v - vmin) >> s0, then 7 more bits per sweep inside the four target bins (the window is still resident).
-template <typename PX>
-__device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32 vmax, u64 sum, u32 feats, u32* hist, u32* t,
-                                             const u32 (&ranks)[4]) {
+// Exact order statistics by radix selection on the resident window, for value ranges the 1024-bin histogram does not
+// resolve: coarse histogram of (x - lo) >> s0, then 7 more bits per sweep inside the four target bins.  x = xf(v): the
+// pixel value itself, or floor(|2 v - med2| / 2) for the MAD.  key[j] = the order statistic of rank ranks[j], minus lo.
+// Leaves the histogram clean.
+struct XfIdentity {
+  __device__ __forceinline__ u32 operator()(u32 v) const { return v; }
+};
+struct XfAbsDev {
+  u32 med2;
+  __device__ __forceinline__ u32 operator()(u32 v) const {
+    const int d = (int)(2u * v) - (int)med2;
+    return (u32)(d < 0 ? -d : d) >> 1;
+  }
+};
+
+template <typename PX, typename Xf>
+__device__ __forceinline__ void wide_select(u32 list_addr, u32 n, u32 lo, u32 hi, const Xf& xf, const u32 (&ranks)[4], u32* hist,
+                                            u32* t, u32 (&key)[4]) {
   const u32 lane = lane_id();
-  const u32 range = vmax - vmin;
+  const u32 range = hi - lo;
   int s0 = 0;
   while ((range >> s0) >= 1024u) ++s0;
   const u32 nb = (range >> s0) + 1;
@@ -359,11 +410,10 @@ __device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32
   hist_zero(hist, 1024u);
   __syncwarp();
 #pragma unroll 1
-  for (u32 i = lane; i < n; i += 32) hist_add(hist, (lds_px<PX>(lds_u16(list_addr + 2u * i)) - vmin) >> s0);
+  for (u32 i = lane; i < n; i += 32) hist_add(hist, (xf(lds_px<PX>(lds_u16(list_addr + 2u * i))) - lo) >> s0);
   __syncwarp();
   find_ranks32(hist, nb, ranks, t);
   int cur = s0;
-  u32 key[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) key[j] = t[j];
 #pragma unroll 1
@@ -375,12 +425,12 @@ __device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32
     __syncwarp();
 #pragma unroll 1
     for (u32 i = lane; i < n; i += 32) {
-      const u32 d = lds_px<PX>(lds_u16(list_addr + 2u * i)) - vmin;
-      const u32 hi = d >> cur;
+      const u32 d = xf(lds_px<PX>(lds_u16(list_addr + 2u * i))) - lo;
+      const u32 hi_bits = d >> cur;
       const u32 sb = (d >> nxt) & (nsub - 1u);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (hi == key[j]) hist_add(hist, 128u * j + sb);
+        if (hi_bits == key[j]) hist_add(hist, 128u * j + sb);
     }
     __syncwarp();
     find_ranks32_x4(hist, t);
@@ -388,6 +438,18 @@ __device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32
     for (int j = 0; j < 4; ++j) key[j] = (key[j] << (cur - nxt)) | t[j];
     cur = nxt;
   }
+  __syncwarp();
+  hist_zero(hist, 1024u);
+  __syncwarp();
+}
+
+// The four ranks of the cell functions (two medians, top 2.5 %, top 5) of a wide-range request.
+template <typename PX>
+__device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32 vmax, u64 sum, u32 feats, u32* hist, u32* t,
+                                             const u32 (&ranks)[4]) {
+  const u32 lane = lane_id();
+  u32 key[4];
+  wide_select<PX>(list_addr, n, vmin, vmax, XfIdentity(), ranks, hist, t, key);
   Ranked r;
   r.med_lo = vmin + key[0]; r.med_hi = vmin + key[1];
   const u32 v2 = vmin + key[2], v3 = vmin + key[3];
@@ -408,8 +470,6 @@ __device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32
   }
   r.top2p5_sum = sum - below2;
   r.top5_sum = sum - below3;
-  __syncwarp();
-  hist_zero(hist, 1024u);  // the next sweep expects a clean circular histogram
   __syncwarp();
   return r;
 }
@@ -440,7 +500,8 @@ __global__ void __launch_bounds__(kSwWarps * 32, kSwCtasPerSm)
 object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__ plan, const int* __restrict__ order,
              const u32* __restrict__ order_counts /* [0] big, [1] small */, int order_cap, u32* __restrict__ work_counter,
              const u64* __restrict__ bitmaps, int chan_rows, const abx_request* __restrict__ requests, int n_requests,
-             ChanStats* __restrict__ chan, int* __restrict__ pair_list, u32* __restrict__ pair_count, int split_log2) {
+             ChanStats* __restrict__ chan, int* __restrict__ pair_list, u32* __restrict__ pair_count, int split_log2,
+             u32* __restrict__ err) {
   const u32 lane = lane_id();
   const u32 warp = threadIdx.x >> 5;
   const u32 sbase = smem_addr_of(dyn);
@@ -605,10 +666,12 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         a.sum = a.wh = a.vmax = a.m10 = a.m01 = 0; a.vmin = kFull; a.sq = a.q = 0;
         const bool want_moi = (rq.features & ABX_F_MOI) != 0;
         const bool want_ranks = (rq.features & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) != 0;
+        const bool want_cp = (rq.features & (ABX_F_CPQ | ABX_F_CPMAD)) != 0;  // cp_measure `intensity` order statistics
         u32 vmin = 0, vmax = 0;
         Ranked rk;
         rk.med_lo = rk.med_hi = 0; rk.top2p5_sum = rk.top5_sum = 0;
-        bool wide = false, wide_done = false;
+        u32 cpq[6] = {0, 0, 0, 0, 0, 0}, mad_lo = 0, mad_hi = 0, maxpos = 0;
+        bool wide = false, wide_done = false;  // wide_done: order statistics found and histogram cleaned before the next copy
         u64 sum64 = 0;
 #pragma unroll 1
         for (u32 c = 0; c < n_chunks; ++c) {
@@ -631,8 +694,70 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
           if (last_chunk) {
             vmin = __reduce_min_sync(kFull, a.vmin);
             vmax = __reduce_max_sync(kFull, a.vmax);
-            wide = want_ranks && vmax - (vmin & ~3u) > 1023u;
-            if (wide && !multi) {  // the window is still here: refine now, before it is overwritten
+            wide = (want_ranks || want_cp) && vmax - (vmin & ~3u) > 1023u;
+            if (want_cp && multi) {
+              if (lane == 0) atomicOr(err, 2u);  // cp_measure statistics of a chunked window: not served (status bit 1)
+            } else if (want_cp) {
+              // ---- cp_measure `intensity`: every order statistic now, while the window is resident (the MAD needs
+              // a second pass over it) ----
+              sum64 = (u64)__reduce_add_sync(kFull, a.sum);
+              const u32 n = g.n, last = n - 1u;
+              const u32 i1 = n >> 2, i2 = n >> 1, i3 = (3u * n) >> 2;  // floor(n f): CellProfiler's rank rule
+              const u32 rb1[4] = {i1, min(i1 + 1u, last), i2, min(i2 + 1u, last)};
+              const u32 rb2[4] = {i3, min(i3 + 1u, last), i3, min(i3 + 1u, last)};
+              const u32 vbase = vmin & ~3u, rot = vbase & 1023u, nb = vmax - vbase + 1u;
+              if (!wide) {
+                if (want_ranks) {
+                  find_ranks_rot<false>(hist, rot, nb, ranks, t);
+                  rk.med_lo = vbase + t[0]; rk.med_hi = vbase + t[1];
+                  const u32 v2 = vbase + t[2], v3 = vbase + t[3];
+                  rk.top2p5_sum = sum64 - ((u64)vbase * t[10] + t[14] + (u64)t[6] * v2);
+                  rk.top5_sum = sum64 - ((u64)vbase * t[11] + t[15] + (u64)t[7] * v3);
+                }
+                find_ranks_rot<false>(hist, rot, nb, rb1, t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cpq[j] = vbase + t[j];
+                find_ranks_rot<true>(hist, rot, nb, rb2, t);
+                cpq[4] = vbase + t[0]; cpq[5] = vbase + t[1];
+              } else {
+                if (want_ranks) rk = wide_ranks<PX>(list_addr, n, vmin, vmax, sum64, rq.features, hist, t, ranks);
+                u32 key[4];
+                wide_select<PX>(list_addr, n, vmin, vmax, XfIdentity(), rb1, hist, t, key);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cpq[j] = vmin + key[j];
+                wide_select<PX>(list_addr, n, vmin, vmax, XfIdentity(), rb2, hist, t, key);
+                cpq[4] = vmin + key[0]; cpq[5] = vmin + key[1];
+              }
+              if (rq.features & ABX_F_CPMAD) {
+                // twice the median (an integer): f = 1/2 exactly when n is odd
+                const u32 med2 = ((n & 1u) && i2 < last) ? cpq[2] + cpq[3] : 2u * cpq[2];
+                const XfAbsDev xf{med2};
+                const u32 rmad[4] = {i2, min(i2 + 1u, last), i2, min(i2 + 1u, last)};
+                u32 first = kFull;  // list index of the first maximum (row-major order)
+                __syncwarp();
+#pragma unroll 1
+                for (u32 k = lane; k < n; k += 32) {
+                  const u32 v = lds_px<PX>(lds_u16(list_addr + 2u * k));
+                  if (v == vmax) first = min(first, k);
+                  if (!wide) hist_add(hist, xf(v));  // deviations fit the histogram: <= max - min <= 1023
+                }
+                __syncwarp();
+                u32 key[4];
+                if (!wide) {
+                  find_ranks_rot<true>(hist, 0u, vmax - vmin + 1u, rmad, t);
+                  key[0] = t[0]; key[1] = t[1];
+                } else {
+                  wide_select<PX>(list_addr, n, 0u, vmax - vmin, xf, rmad, hist, t, key);
+                }
+                mad_lo = key[0];
+                mad_hi = key[1] | ((med2 & 1u) << 31);
+                first = __reduce_min_sync(kFull, first);
+                const u32 off = lds_u16(list_addr + 2u * first) - win_base;
+                const u32 r = __umulhi(off, inv_pitch);
+                maxpos = (r << 16) | (((off - r * g.pitchB) >> (sizeof(PX) == 1 ? 0 : 1)) - g.s_px);
+              }
+              wide_done = true;
+            } else if (wide && !multi) {  // the window is still here: refine now, before it is overwritten
               sum64 = (u64)__reduce_add_sync(kFull, a.sum);
               rk = wide_ranks<PX>(list_addr, g.n, vmin, vmax, sum64, rq.features, hist, t, ranks);
               wide_done = true;
@@ -659,18 +784,22 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         cs.wrapsq = cs.sumsq - ((u64)__reduce_add_sync(kFull, a.wh) << (32 - 2 * kShift));
         cs.m10 = cs.m01 = cs.m20 = cs.m02 = 0;
         if (want_moi) {
-          // coordinates relative to the TMA box (column s_px = bbox column 0): central moments are translation invariant
-          cs.m10 = warp_sum64((u64)a.m10);
+          // the sweep counted columns from the TMA box (bbox column 0 = box column s_px): back to the bbox origin
+          const u64 m10w = warp_sum64((u64)a.m10), s = (u64)g.s_px;
+          cs.m10 = m10w - s * cs.sum;
           cs.m01 = warp_sum64((u64)a.m01);
-          cs.m20 = warp_sum64(a.q);  // m20 + m02 as one sum (finalize.cu)
+          cs.m20 = warp_sum64(a.q) - 2ull * s * m10w + s * s * cs.sum;  // m20 + m02 as one sum (finalize.cu)
         }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) cs.q[j] = cpq[j];
+        cs.mad_lo = mad_lo; cs.mad_hi = mad_hi; cs.maxpos = maxpos; cs.pad_ = 0;
         cs.vmin = vmin; cs.vmax = vmax;
         cs.med_lo = rk.med_lo; cs.med_hi = rk.med_hi;
         cs.top2p5_sum = rk.top2p5_sum; cs.top5_sum = rk.top5_sum;
         if (!wide_done) {
           const u32 vbase = vmin & ~3u;
           if (want_ranks && !wide) {
-            find_ranks_rot(hist, vbase & 1023u, vmax - vbase + 1u, ranks, t);
+            find_ranks_rot<true>(hist, vbase & 1023u, vmax - vbase + 1u, ranks, t);
             cs.med_lo = vbase + t[0]; cs.med_hi = vbase + t[1];
             const u32 v2 = vbase + t[2], v3 = vbase + t[3];
             // sum of the smallest values up to the rank = vbase * cnt + sum(count * bin) below + rank * value
@@ -685,7 +814,8 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         }
         if (lane == 0) {
           chan[(i64)g.obj * n_requests + rq.q] = cs;
-          if (wide && !wide_done) pair_list[atomicAdd(pair_count, 1u)] = g.obj * n_requests + rq.q;  // chunked and wide: rare
+          if (wide && !wide_done && want_ranks)
+            pair_list[atomicAdd(pair_count, 1u)] = g.obj * n_requests + rq.q;  // chunked and wide (rare): the gather kernel
         }
         __syncwarp();
       }
@@ -754,7 +884,7 @@ int launch_sweep(const abx_extract_args* a, const Workspace& ws, const SweepMaps
                                                         n_total /* the plan kernel's capacity of the order array */,
                                                         ws.list_counts + kCntSweepWork, ws.bitmaps,
                                                         (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests,
-                                                        ws.chan, ws.pair_list, ws.list_counts + kCntLeftover, split_log2);
+                                                        ws.chan, ws.pair_list, ws.list_counts + kCntLeftover, split_log2, ws.err);
   return abx_check_cuda(cudaGetLastError(), "object_sweep");
 }
 
@@ -774,6 +904,10 @@ bool abx_sweep_ok(const abx_extract_args* a) {
 int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool sweep) {
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0 || (!sweep && !a->need_edt)) return ABX_OK;
+  if (!sweep && (a->request_feature_union & (int)(ABX_F_CPQ | ABX_F_CPMAD)))
+    return abx_set_error(ABX_ERR_UNSUPPORTED,
+                         "cp_measure intensity statistics need uint8/uint16 pixels in a TMA-addressable layout (16-byte aligned rows, Z = 1 or a max "
+                         "reduction); there is no CPU fallback");
   PlanArgs p;
   p.recs = ws.recs;
   p.plane_base = a->plane_base;
@@ -786,7 +920,7 @@ int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st,
   p.align = a->pixel_dtype == ABX_U8 ? 16 : 8;
   p.n_requests = a->n_requests;
   p.sweep = sweep ? 1 : 0;
-  p.need_edt = a->need_edt ? 1 : 0;
+  p.need_edt = (a->need_edt & 3) ? 1 : 0;
   p.chan = ws.chan;
   p.shape = ws.shape;
   p.plan = ws.plan;
@@ -796,6 +930,11 @@ int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st,
   p.pair_list = ws.pair_list;
   p.edt_list = ws.edt_list;
   p.counts = ws.list_counts;
+  p.cp_requests = (a->request_feature_union & (int)(ABX_F_CPQ | ABX_F_CPMAD)) != 0;
+  p.want_moments = (a->need_edt & 4) != 0;
+  p.bitmaps = ws.bitmaps;
+  p.mom = ws.mom;
+  p.err = ws.err;
   plan_kernel<<<(n_total + 255) / 256, 256, 0, st>>>(p);
   return abx_check_cuda(cudaGetLastError(), "plan");
 }

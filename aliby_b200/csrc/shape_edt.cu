@@ -199,7 +199,7 @@ shape_edt_kernel(const uint16_t* __restrict__ labels, i64 plane_stride, i64 row_
 }  // namespace
 
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
-  if (!a->need_edt || a->n_objects == 0) return ABX_OK;
+  if (!(a->need_edt & 3) || a->n_objects == 0) return ABX_OK;
   const size_t smem = (size_t)kEdtSmemWindow * kEdtBytesPerPixel;
   static thread_local bool attr_done[64] = {false};
   int dev = 0;

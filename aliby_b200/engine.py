@@ -54,6 +54,48 @@ INTENSITY_METRICS = {
 }
 BACKGROUND_METRICS = {"imBackground": nat.F_MEDIAN, "background_max5": nat.F_TOP5}
 
+# cp_measure features with a kernel (loaders.py:71-77,135-150): dict-valued metrics, one table column per key.
+# `intensity` = CellProfiler MeasureObjectIntensity WITHOUT the edge features (the caller has to switch those off with
+# cp_measure_kwargs={"intensity": {"edge_measurements": False}}, pipe_builder.py:84-91); `sizeshape` = the subset of
+# MeasureObjectSizeShape that the label scan, the first EDT and the coordinate moments give.  Parity is self-defined
+# against oracle/cpm.py (cp_measure's source is not available: SURVEY.md 8c).
+CP_INTENSITY = (  # (key, building block, request features)
+    ("Intensity_IntegratedIntensity", "total", 0),
+    ("Intensity_MeanIntensity", "mean", 0),
+    ("Intensity_StdIntensity", "std", 0),
+    ("Intensity_MinIntensity", "min", 0),
+    ("Intensity_MaxIntensity", "max", 0),
+    ("Intensity_MassDisplacement", "cp_mass_displacement", nat.F_MOI),
+    ("Intensity_LowerQuartileIntensity", "cp_lower_quartile", nat.F_CPQ),
+    ("Intensity_MedianIntensity", "cp_median", nat.F_CPQ),
+    ("Intensity_MADIntensity", "cp_mad", nat.F_CPQ | nat.F_CPMAD),
+    ("Intensity_UpperQuartileIntensity", "cp_upper_quartile", nat.F_CPQ),
+    ("Location_CenterMassIntensity_X", "cp_center_mass_x", nat.F_MOI),
+    ("Location_CenterMassIntensity_Y", "cp_center_mass_y", nat.F_MOI),
+    ("Location_CenterMassIntensity_Z", "cp_center_mass_z", 0),
+    ("Location_MaxIntensity_X", "cp_max_pos_x", nat.F_CPQ | nat.F_CPMAD),
+    ("Location_MaxIntensity_Y", "cp_max_pos_y", nat.F_CPQ | nat.F_CPMAD),
+    ("Location_MaxIntensity_Z", "cp_zero", 0),
+)
+CP_SIZESHAPE = (  # (key, building block)
+    ("AreaShape_Area", "area"),
+    ("AreaShape_BoundingBoxArea", "cp_bbox_area"),
+    ("AreaShape_BoundingBoxMaximum_X", "cp_bbox_max_x"),
+    ("AreaShape_BoundingBoxMaximum_Y", "cp_bbox_max_y"),
+    ("AreaShape_BoundingBoxMinimum_X", "bbox_cmin"),
+    ("AreaShape_BoundingBoxMinimum_Y", "bbox_rmin"),
+    ("AreaShape_Center_X", "cp_center_x"),
+    ("AreaShape_Center_Y", "cp_center_y"),
+    ("AreaShape_Eccentricity", "cp_eccentricity"),
+    ("AreaShape_EquivalentDiameter", "cp_equivalent_diameter"),
+    ("AreaShape_Extent", "cp_extent"),
+    ("AreaShape_MajorAxisLength", "cp_major_axis_length"),
+    ("AreaShape_MaximumRadius", "cp_maximum_radius"),
+    ("AreaShape_MeanRadius", "cp_mean_radius"),
+    ("AreaShape_MinorAxisLength", "cp_minor_axis_length"),
+)
+CP_FEATURE_NAMES = ("intensity", "sizeshape")
+
 CELL_FUN_NAMES = tuple(
     sorted(
         [
@@ -89,6 +131,7 @@ class Plan:
     requests: list = field(default_factory=list)  # [(channel, red_enum, features, bg_features)]
     columns: list = field(default_factory=list)  # [(request_idx, metric_enum)]
     inst_cols: list = field(default_factory=list)  # per instruction: tuple of dense column indices
+    inst_keys: list = field(default_factory=list)  # per instruction: None, or the dict keys of a dict-valued metric
     need_edt: int = 0  # bit 0: axes (eccentricity/volume/min/maj), bit 1: conical_volume
     with_background: bool = False
     error: Exception | None = None  # raised only when there is at least one object, like the reference
@@ -118,12 +161,13 @@ class Plan:
         return self._dev[key]
 
 
-def compile_tree(tree: dict) -> Plan:
-    return compile_instructions(kv(flatten(tree)))
+def compile_tree(tree: dict, cp_measure_kwargs=None) -> Plan:
+    return compile_instructions(kv(flatten(tree)), cp_measure_kwargs)
 
 
-def compile_instructions(instructions: list) -> Plan:
+def compile_instructions(instructions: list, cp_measure_kwargs=None) -> Plan:
     plan = Plan(instructions=list(instructions))
+    cp_kw = dict(cp_measure_kwargs or {})
     req_index: dict = {}
     col_index: dict = {}
 
@@ -140,7 +184,11 @@ def compile_instructions(instructions: list) -> Plan:
             col_index[key] = len(plan.columns)
             plan.columns.append(key)
             if key[1] in nat.EDT_METRICS:
-                plan.need_edt |= 2 if key[1] == nat.CONICAL_METRIC else 1
+                plan.need_edt |= 1
+            if key[1] in nat.CONICAL_METRICS:
+                plan.need_edt |= 2
+            if key[1] in nat.MOMENT_METRICS:
+                plan.need_edt |= 4
         return col_index[key]
 
     for inst in instructions:
@@ -148,14 +196,32 @@ def compile_instructions(instructions: list) -> Plan:
             ch, red, metric = inst
             if red not in REDUCERS:
                 raise KeyError(red)  # REDUCTION_FUNS[red_z], extract.py:151
-            known = metric in SHAPE_METRICS or metric in INTENSITY_METRICS or metric in BACKGROUND_METRICS
+            known = (metric in SHAPE_METRICS or metric in INTENSITY_METRICS or metric in BACKGROUND_METRICS
+                     or metric in CP_FEATURE_NAMES)
             if not known:
                 raise KeyError(metric)  # CELL_FUNS[metric], extract.py:152
             has_pixels = not (isinstance(ch, str) and ch == "None")
             if has_pixels:
                 if REDUCERS[red] != "ufunc":
                     raise Exception(f"{REDUCERS[red]} is an invalid reducer.")  # distributors.py:24
-            if metric in SHAPE_METRICS:
+            keys = None
+            if metric == "sizeshape":
+                cols = tuple(column(-1, block) for _, block in CP_SIZESHAPE)
+                keys = [k for k, _ in CP_SIZESHAPE]
+            elif metric == "intensity":
+                if not has_pixels:
+                    raise TypeError("metric 'intensity' needs pixels but the channel is 'None'")
+                if cp_kw.get("intensity", {}).get("edge_measurements", True):
+                    raise NotImplementedError(
+                        "cp_measure 'intensity' with edge_measurements=True (the *Edge features need the object's outline) has no "
+                        "CUDA kernel: pass cp_measure_kwargs={'intensity': {'edge_measurements': False}}"
+                    )
+                r = request(ch, red)
+                for _, _, feats in CP_INTENSITY:
+                    plan.requests[r][2] |= feats
+                cols = tuple(column(r, block) for _, block, _ in CP_INTENSITY)
+                keys = [k for k, _, _ in CP_INTENSITY]
+            elif metric in SHAPE_METRICS:
                 cols = tuple(column(-1, m) for m in SHAPE_METRICS[metric])
             else:
                 if not has_pixels:
@@ -168,10 +234,12 @@ def compile_instructions(instructions: list) -> Plan:
                     plan.requests[r][2] |= INTENSITY_METRICS[metric]
                 cols = (column(r, metric),)
             plan.inst_cols.append(cols)
+            plan.inst_keys.append(keys)
         except Exception as e:  # noqa: BLE001 - deferred, see Plan.error
             if plan.error is None:
                 plan.error = e
             plan.inst_cols.append(())
+            plan.inst_keys.append(None)
     return plan
 
 
@@ -216,7 +284,10 @@ def _device_meta(device, plane_tile: np.ndarray, plane_base: np.ndarray, tile_of
     key = (str(device), blob)
     hit = _meta_cache.get(key)
     if hit is not None:
-        torch.cuda.current_stream(device).wait_event(hit._abx_ready)  # no-op on the uploading stream
+        # (inside a graph capture neither a query nor a wait on an outside event is legal; GraphedExtract has
+        # synchronised with the upload before it captures)
+        if not torch.cuda.is_current_stream_capturing() and not hit._abx_ready.query():
+            torch.cuda.current_stream(device).wait_event(hit._abx_ready)  # no-op on the uploading stream
         return hit
     if len(_meta_cache) >= 64:
         _meta_cache.pop(next(iter(_meta_cache)))
@@ -319,6 +390,10 @@ def run_planes(
     a.n_columns = n_cols
     a.need_edt = int(plan.need_edt)
     a.request_feature_union = nat.F_HAS_DIV if any(r[1] == nat.RED_DIV for r in plan.requests) else 0
+    for r in plan.requests:
+        a.request_feature_union |= int(r[2]) | int(r[3])
+    if a.request_feature_union & (nat.F_CPQ | nat.F_CPMAD) and a.pixel_dtype not in (nat.U8, nat.U16):
+        raise NotImplementedError("cp_measure 'intensity' has a CUDA kernel for uint8/uint16 pixels only; there is no CPU fallback")
     if plan.requests:  # extent of the pixel buffer behind data_ptr(), for the TMA description of it
         a.pixel_elems = (pixels.untyped_storage().nbytes() // pixels.element_size()) - pixels.storage_offset()
     a.table = out.data_ptr()
@@ -340,3 +415,68 @@ def run_planes(
         nat.check(lib.abx_extract(C.byref(a)), "abx_extract")
     # meta must outlive the launch: it is kept alive by the per-device cache
     return out
+
+
+import threading as _threading
+
+_capture_lock = _threading.Lock()  # torch's capture context synchronises the device: one capture at a time per process
+
+
+class GraphedExtract:
+    """One extract call of FIXED shapes captured in a CUDA graph and replayed: the regime of a time-lapse pipeline,
+    which calls the extract step once per time point with a few hundred objects — a dozen launches whose latencies,
+    not their work, set the time of the call (0.11 ms per C3 time point eagerly).
+
+    Static device buffers hold the inputs (labels ``(P, H, W)`` uint16; pixels in the caller's layout) and the table;
+    every plane owns ``cap`` table rows (``plane_base[p] = p * cap``), so that nothing the graph bakes in depends on the
+    label counts of a time point.  :meth:`run` copies the new inputs in, replays the graph and returns the table (still
+    on the device, rows of absent labels NaN); a label above ``cap`` sets the status word — the caller then builds a
+    larger instance.  One instance belongs to one stream of one device."""
+
+    def __init__(self, plan: Plan, n_planes: int, H: int, W: int, plane_tile, pixel_shape, pixel_dtype, tile_offset,
+                 chan_stride: int, z_stride: int, row_stride: int, n_channels: int, n_z: int, cap: int, device):
+        import torch
+
+        self.plan, self.cap, self.P = plan, int(cap), int(n_planes)
+        self.device = device
+        self.labels = torch.zeros((n_planes, H, W), dtype=torch.uint16, device=device)
+        self.pixels = torch.zeros(pixel_shape, dtype=pixel_dtype, device=device)
+        self.n_labels = np.full(n_planes, self.cap, dtype=np.int64)
+        self.buf, self.table, self.status = alloc_table(n_planes * self.cap, plan.n_columns, device)
+        self._args = (np.asarray(plane_tile, dtype=np.int32), self.n_labels, self.pixels,
+                      np.ascontiguousarray(tile_offset, dtype=np.int64), int(chan_stride), int(z_stride), int(row_stride),
+                      int(n_channels), int(n_z))
+        self.stream = torch.cuda.Stream(device=device)
+        self.stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(self.stream):
+            for _ in range(2):  # first calls set kernel attributes, encode tensor maps, upload the plan: not capturable
+                self._launch()
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        # thread-local capture mode: other host threads keep making (synchronising) CUDA calls while this one captures
+        with _capture_lock:
+            with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+                self._launch()
+        torch.cuda.current_stream(device).wait_stream(self.stream)
+
+    def _launch(self):
+        pt, nl, px, off, cs, zs, rs, C_, Z_ = self._args
+        run_planes(self.plan, self.labels, pt, nl, px, off, cs, zs, rs, C_, Z_, out=self.table, status=self.status)
+
+    def run(self, labels=None, pixels=None):
+        """Copy new inputs into the static buffers (tensors or arrays of the captured shapes; ``None`` = unchanged), replay."""
+        import torch
+
+        if labels is not None:
+            self.labels.copy_(labels if isinstance(labels, torch.Tensor) else torch.from_numpy(labels), non_blocking=True)
+        if pixels is not None:
+            self.pixels.copy_(pixels if isinstance(pixels, torch.Tensor) else torch.from_numpy(pixels), non_blocking=True)
+        self.graph.replay()
+        return self.table
+
+    def rows(self, n_labels) -> np.ndarray:
+        """Row indices of the objects ``1..n_labels[p]`` of every plane inside the capacity-padded table."""
+        n_labels = np.asarray(n_labels, dtype=np.int64)
+        if n_labels.max(initial=0) > self.cap:
+            raise IndexError(f"{int(n_labels.max())} labels in a plane exceed the captured capacity {self.cap}")
+        return np.concatenate([p * self.cap + np.arange(k) for p, k in enumerate(n_labels)]) if len(n_labels) else np.zeros(0, np.int64)

@@ -54,16 +54,52 @@ def _as_mask_list(masks):
     return masks
 
 
-def _to_device_labels(planes: list[np.ndarray], device):
-    """Stack equally-shaped 2-D label planes into one uint16 device tensor."""
-    import torch
-
+def _host_label_stack(planes: list[np.ndarray]) -> np.ndarray:
+    """Equally-shaped 2-D label planes as one contiguous uint16 array."""
     stack = np.stack(planes)
     if stack.dtype != np.uint16:
         if stack.size and (stack.min() < 0 or stack.max() > 65535):
             raise OverflowError("label ids must fit uint16 (segment/dispatch.py:14-19 enforces the same)")
         stack = stack.astype(np.uint16)
-    return torch.from_numpy(np.ascontiguousarray(stack)).to(device, non_blocking=True)
+    return np.ascontiguousarray(stack)
+
+
+def _to_device_labels(planes: list[np.ndarray], device):
+    """Stack equally-shaped 2-D label planes into one uint16 device tensor."""
+    import torch
+
+    return torch.from_numpy(_host_label_stack(planes)).to(device, non_blocking=True)
+
+
+# ---- CUDA graphs for the small-call regime (one call per time point with a few hundred objects) ----
+_GRAPH_MAX_OBJECTS = 8192   # above this the launches are no longer what the call costs
+_GRAPH_AFTER_CALLS = 2      # eager calls with the same shapes before a graph is captured
+_graph_seen: dict = {}
+_graph_cache: dict = {}
+
+
+def _graphs_enabled() -> bool:
+    import os
+
+    return os.environ.get("ALIBY_B200_GRAPHS", "1") != "0"
+
+
+def _graphed(key, build):
+    """Per (thread, key) instance of engine.GraphedExtract, built after the key has been seen a few times."""
+    import threading
+
+    key = (threading.get_ident(), *key)
+    g = _graph_cache.get(key)
+    if g is not None:
+        return g
+    seen = _graph_seen.get(key, 0) + 1
+    _graph_seen[key] = seen
+    if seen <= _GRAPH_AFTER_CALLS:
+        return None
+    while len(_graph_cache) >= 8:
+        _graph_cache.pop(next(iter(_graph_cache)))
+    g = _graph_cache[key] = build()
+    return g
 
 
 def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
@@ -72,14 +108,47 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
 
     from .tile import TileView
 
-    if device is None:
-        device = torch.device("cuda", torch.cuda.current_device())
     n_objects = int(np.sum(n_labels))
     if n_objects == 0:
         return np.zeros((0, plan.n_columns))
-    if plan.error is not None:
+    if plan.error is not None:  # (before anything touches CUDA: an unknown metric is a host-side error)
         raise plan.error
-    labels_dev = _to_device_labels(planes, device)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    host_labels = _host_label_stack(planes)
+    # ---- small calls of repeating shapes: replay a captured graph (engine.GraphedExtract) ----
+    if (_graphs_enabled() and n_objects <= _GRAPH_MAX_OBJECTS and plan.n_columns and plan.requests
+            and isinstance(pixels, (np.ndarray, TileView)) and str(pixels.dtype) in ("uint8", "uint16")
+            and not (isinstance(pixels, TileView) and pixels.out_of_frame.any())):
+        n_labels = np.asarray(n_labels, dtype=np.int64)
+        cap = max(16, int(-(-2 * int(n_labels.max()) // 8) * 8))
+        P, H, W = host_labels.shape
+        if isinstance(pixels, TileView):
+            frame = np.ascontiguousarray(pixels.frame)
+            C_, Z_, FH, FW = frame.shape
+            offs = (pixels.origins[:, 0] * FW + pixels.origins[:, 1]).astype(np.int64)
+            layout = (frame.shape, str(frame.dtype), offs.tobytes(), Z_ * FH * FW, FH * FW, FW, C_, Z_)
+            src = frame
+        else:
+            T, C_, Z_, Y, X = pixels.shape
+            offs = np.arange(T, dtype=np.int64) * (C_ * Z_ * Y * X)
+            layout = (pixels.shape, str(pixels.dtype), offs.tobytes(), Z_ * Y * X, Y * X, X, C_, Z_)
+            src = np.ascontiguousarray(pixels)
+        key = (str(device), tuple(plan.instructions), (P, H, W), tuple(np.asarray(plane_tile).tolist()), layout)
+        cur = _graph_cache.get((__import__("threading").get_ident(), *key))
+        if cur is not None and cur.cap < int(n_labels.max()):  # more labels than captured: a larger instance
+            _graph_cache.pop((__import__("threading").get_ident(), *key))
+            cur = None
+        g = cur or _graphed(key, lambda: engine.GraphedExtract(
+            plan, P, H, W, plane_tile, layout[0], getattr(torch, layout[1]), offs, layout[3], layout[4], layout[5],
+            layout[6], layout[7], cap, device))
+        if g is not None:
+            g.run(host_labels, src)
+            host = g.buf.cpu()
+            n_cells = g.P * g.cap * plan.n_columns
+            engine.raise_on_status(host[n_cells:].view(torch.int32)[0])
+            return host[:n_cells].view(g.P * g.cap, plan.n_columns).numpy()[g.rows(n_labels)]
+    labels_dev = torch.from_numpy(host_labels).to(device, non_blocking=True)
     if isinstance(pixels, TileView):
         px_dev, offs, cs, zs, rs, C_, Z_ = pixels.addressing(device)
     else:
@@ -246,7 +315,7 @@ def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
 
 
 def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | None = None,
-                  chunk_bytes: int = 160 << 20) -> ExtractionTable:
+                  chunk_bytes: int = 160 << 20, cp_measure_kwargs=None) -> ExtractionTable:
     """Fast public entry point: tree + host (or device) arrays in, dense per-object table out.
 
     Does what ``process_tree_masks`` + ``extract_tree`` + the pivot of ``format_extraction`` do
@@ -260,13 +329,18 @@ def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | No
     from .tile import TileView
 
     masks = _as_mask_list(masks)
-    plan = plan or engine.compile_tree(tree)
-    if any(len(c) != 1 for c in plan.inst_cols if c):
+    plan = plan or engine.compile_tree(tree, cp_measure_kwargs)
+    if any(len(c) != 1 and k is None for c, k in zip(plan.inst_cols, plan.inst_keys) if c):
         raise Exception("tuple-valued metrics (centroid, min_maj_approximation) cannot be table columns")
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     keep = [i for i, m in enumerate(masks) if len(m)]
-    names = ["/".join(str(x) for x in inst) + f"/{inst[-1]}" for inst in plan.instructions]
+    names, name_cols = [], []  # reference column names; a dict-valued metric contributes one column per key
+    for inst, cols_, keys_ in zip(plan.instructions, plan.inst_cols, plan.inst_keys):
+        branch = "/".join(str(x) for x in inst)
+        for k, j in zip(keys_ if keys_ is not None else [inst[-1]], cols_):
+            names.append(f"{branch}/{k}")
+            name_cols.append(j)
     if not keep:
         return ExtractionTable(np.zeros((0, 2), np.int64), names, np.zeros((0, len(names))))
     host_inputs = isinstance(pixels, np.ndarray) and not isinstance(masks[keep[0]], torch.Tensor)
@@ -297,7 +371,7 @@ def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | No
         host = buf.cpu()
         engine.raise_on_status(host[n_rows * plan.n_columns :].view(torch.int32)[0])
         values = host[: n_rows * plan.n_columns].view(n_rows, plan.n_columns).numpy()
-    cols = np.fromiter((c[0] for c in plan.inst_cols), dtype=np.int64, count=len(plan.inst_cols))
+    cols = np.asarray(name_cols, dtype=np.int64)
     objects = np.stack(
         [np.repeat(np.asarray(keep, dtype=np.int64), n_labels), np.concatenate([np.arange(1, k + 1) for k in n_labels])],
         axis=1,
@@ -310,15 +384,19 @@ def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | No
 
 
 def _results_from_dense(plan, dense, row_of_item, inst_of_item):
-    """Flat python list in item order; tuple-valued metrics become tuples."""
-    single = all(len(c) == 1 for c in plan.inst_cols)
+    """Flat python list in item order; tuple-valued metrics become tuples, cp_measure features dicts of
+    ``{key: ndarray of length 1}`` (what ``wrap_cp_measure_features`` returns, loaders.py:135-150)."""
+    single = all(len(c) == 1 and k is None for c, k in zip(plan.inst_cols, plan.inst_keys))
     if single and len(row_of_item):
         cols = np.fromiter((c[0] for c in plan.inst_cols), dtype=np.int64)
         return dense[row_of_item, cols[inst_of_item]].tolist()
     out = []
     for r, i in zip(row_of_item, inst_of_item):
-        c = plan.inst_cols[i]
-        out.append(float(dense[r, c[0]]) if len(c) == 1 else tuple(float(dense[r, k]) for k in c))
+        c, keys = plan.inst_cols[i], plan.inst_keys[i]
+        if keys is not None:
+            out.append({k: dense[r, j : j + 1].copy() for k, j in zip(keys, c)})
+        else:
+            out.append(float(dense[r, c[0]]) if len(c) == 1 else tuple(float(dense[r, k]) for k in c))
     return out
 
 
@@ -342,7 +420,7 @@ def process_tree_masks(
             for mask_i in range(1, int(masks_in_tile.max()) + 1):
                 ind_masks.append((tile_i, mask_i))
     tileid_instructions = ItemTuple(product(ind_masks, instructions))
-    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions), ind_masks
+    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions, cp_measure_kwargs), ind_masks
     extra = {}
     if cp_measure_kwargs is not None:
         extra["cp_measure_kwargs"] = cp_measure_kwargs
@@ -383,7 +461,7 @@ def process_tree_masks_overlap(
             inverse_mappings[(tile_i, stack_i)] = np.concatenate([[0], ids]).astype(np.int64)
             tile_stack_mask.extend((tile_i, stack_i, mask_i) for mask_i in range(1, len(ids) + 1))
     tileid_instructions = ItemTuple(product(tile_stack_mask, instructions))
-    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions), tile_stack_mask
+    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions, cp_measure_kwargs), tile_stack_mask
     extra = {}
     if cp_measure_kwargs is not None:
         extra["cp_measure_kwargs"] = cp_measure_kwargs
@@ -425,7 +503,7 @@ def extract_tree(
         for k, (obj, inst) in enumerate(tileid_instructions):
             row_of_item[k] = obj_index.setdefault(tuple(obj), len(obj_index))
             inst_of_item[k] = inst_index.setdefault(tuple(inst), len(inst_index))
-        plan = engine.compile_instructions(list(inst_index))
+        plan = engine.compile_instructions(list(inst_index), cp_measure_kwargs)
         objects = list(obj_index)
         n_inst = len(inst_index)
 
@@ -567,7 +645,7 @@ def format_extraction_overlap(instructions_result):
 def _format_dense(results: ExtractionResults, pa):
     """Arrow table straight from the dense block (no per-value Python work)."""
     plan = results.plan
-    if any(len(c) != 1 for c in plan.inst_cols):
+    if any(len(c) != 1 and k is None for c, k in zip(plan.inst_cols, plan.inst_keys)):
         return None  # tuple-valued metric: let the generic path raise like the reference
     objs = results.objects
     keys = objs[:, [0, -1]]
@@ -576,8 +654,13 @@ def _format_dense(results: ExtractionResults, pa):
     if len(first) != len(keys):
         return None
     names = {}
-    for inst, cols in zip(plan.instructions, plan.inst_cols):
-        names["/".join(str(x) for x in inst) + f"/{inst[-1]}"] = cols[0]
+    for inst, cols, dict_keys in zip(plan.instructions, plan.inst_cols, plan.inst_keys):
+        branch = "/".join(str(x) for x in inst)
+        if dict_keys is None:
+            names[f"{branch}/{inst[-1]}"] = cols[0]
+        else:  # dict-valued metric: one column per key (extract.py:553-562)
+            for k, j in zip(dict_keys, cols):
+                names[f"{branch}/{k}"] = j
     data = {"tile": pa.array(keys[:, 0], pa.int64()), "label": pa.array(keys[:, 1], pa.int64())}
     block = results.dense[results.obj_rows]
     for name in sorted(names):

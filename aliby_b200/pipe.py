@@ -1,5 +1,4 @@
-"""Pipeline seam: serve ``extract_*`` (and pre-located ``tile``) steps of an ALIBY pipeline
-from the CUDA hot path.
+"""Pipeline seam: serve the ``extract_*`` and ``tile*`` steps of an ALIBY pipeline from the CUDA hot path.
 
 The reference has no plugin registry; a step is chosen by the prefix of its name inside
 ``init_step`` (``src/aliby/pipe.py:47-72``) and the sanctioned seam is the ``init_step_fn``
@@ -7,8 +6,9 @@ argument of ``_run_pipeline_and_post_impl`` (``src/aliby/pipe_core.py:381-389``)
 provides exactly that:
 
 * :func:`init_step` — returns our extractor for ``extract_*`` steps (same ``partial`` shape as
-  ``pipe_core._init_extract``, ``pipe_core.py:68-81``) and defers every other step to the
-  reference's own ``aliby.pipe.init_step`` when ALIBY is importable;
+  ``pipe_core._init_extract``, ``pipe_core.py:68-81``), our fused tiler for ``tile*`` steps (the crop of
+  ``tiler.py:309-366`` becomes a view that the extraction kernels read in place) and defers every other step —
+  ``extractmulti_*`` included — to the reference's own ``aliby.pipe.init_step`` when ALIBY is importable;
 * :func:`run_pipeline_and_post` — ``partial(_run_pipeline_and_post_impl, init_step_fn=init_step)``
   (what ``aliby/pipe.py:75-77`` does with its own ``init_step``), available when ALIBY is importable;
 * :func:`get_profiles_from_state` — table assembly of ``pipe_core.py:453-512`` (rename
@@ -37,22 +37,58 @@ def _init_extract(step_name: str, parameters: dict, *, overlap: bool = False):
     return partial(process, measure_fn=measure_fn, tree=parameters["tree"], **parameters.get("kwargs", {}))
 
 
-def init_step(step_name: str, parameters: dict, other_steps: dict | None = None, *, overlap: bool = False):
-    """Drop-in ``init_step_fn``: ours for ``extract_*``, the reference's for everything else."""
-    if step_name.startswith("extract_"):
-        return _init_extract(step_name, parameters, overlap=overlap)
-    if step_name.startswith("extractmulti_"):
-        raise NotImplementedError(
-            "extractmulti_* (cp_measure colocalisation) has no CUDA kernel in aliby_b200; "
-            "route this step through aliby.pipe.init_step"
-        )
+def _reference_init_step(step_name: str, parameters: dict, other_steps: dict | None, why: str):
+    """Hand a step to the reference's own ``aliby.pipe.init_step`` (pipe.py:47-72)."""
     try:
         from aliby.pipe import init_step as reference_init_step
     except ImportError as e:  # ALIBY itself is not installed next to us
-        raise ImportError(
-            f"step '{step_name}' is not an extract step and the reference (aliby.pipe.init_step) is not importable"
-        ) from e
+        raise ImportError(f"step '{step_name}' {why} and the reference (aliby.pipe.init_step) is not importable") from e
     return reference_init_step(step_name, parameters, other_steps)
+
+
+def _init_tile(step_name: str, parameters: dict, other_steps: dict | None):
+    """``tile*`` steps (pipe.py:56-57, pipe_core.py:54-65) with the crop fused into the extraction.
+
+    * Pre-located tiles — ``{"pixels": <(T, C, Z, Y, X) array>, "tile_centres": [(row, col), ...], "tile_size": n}``
+      (what a position looks like after the reference's trap detection at time point 0, tiler.py:407-417) — are served
+      by :class:`aliby_b200.tile.FusedTiler` alone.
+    * Anything else is initialised by the reference (image readers, trap detection, drift: out of scope here) and its
+      crop method is swapped for the fused view (:func:`aliby_b200.tile.fuse_reference_tiler`): ``run_tp`` then returns
+      ``{"drift": ..., "pixels": TileView}`` and the extract step reads the tile windows in place.
+    """
+    from .tile import FusedTiler, fuse_reference_tiler
+
+    if "tile_centres" in parameters:
+        if "pixels" not in parameters or "tile_size" not in parameters:
+            raise ValueError(f"Step '{step_name}' with 'tile_centres' also needs 'pixels' and 'tile_size'.")
+        return FusedTiler(parameters["pixels"], parameters["tile_centres"], parameters["tile_size"])
+    return fuse_reference_tiler(_reference_init_step(step_name, parameters, other_steps, "needs the reference's image readers"))
+
+
+def init_step(step_name: str, parameters: dict, other_steps: dict | None = None, *, overlap: bool = False):
+    """Drop-in ``init_step_fn``: ours for ``extract_*`` and ``tile*``, the reference's for everything else.
+
+    An ``extract_*`` step whose tree names a metric without a CUDA kernel (cp_measure features beyond ``intensity`` /
+    ``sizeshape``, decided here with the plan compiler) and every ``extractmulti_*`` step (cp_measure colocalisation)
+    go to the reference's own implementation when ALIBY is importable; otherwise the error names the metric — there
+    is no CPU fallback inside this package."""
+    if step_name.startswith("extract_"):
+        if "tree" in parameters:
+            from . import engine
+
+            err = engine.compile_tree(parameters["tree"], parameters.get("kwargs", {}).get("cp_measure_kwargs")).error
+            if isinstance(err, KeyError):
+                try:
+                    return _reference_init_step(step_name, parameters, other_steps, f"asks for {err} which has no CUDA kernel")
+                except ImportError:
+                    pass  # the step then raises KeyError(metric) at its first call with objects, like the reference would
+        return _init_extract(step_name, parameters, overlap=overlap)
+    if step_name.startswith("extractmulti_"):
+        return _reference_init_step(step_name, parameters, other_steps,
+                                    "(cp_measure colocalisation, extract.py:200-237) has no CUDA kernel in aliby_b200")
+    if step_name.startswith("tile"):
+        return _init_tile(step_name, parameters, other_steps)
+    return _reference_init_step(step_name, parameters, other_steps, "is not an extract or tile step")
 
 
 def run_pipeline_and_post(*args, **kwargs):

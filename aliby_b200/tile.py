@@ -147,3 +147,29 @@ class FusedTiler:
             frame = frame.compute(scheduler="synchronous")
         view = TileView(np.asarray(frame), tile_origins(self.centres, self.tile_size), self.tile_size)
         return {"drift": [0.0, 0.0], "pixels": view}
+
+
+def fuse_reference_tiler(tiler):
+    """Swap the crop of a reference ``Tiler`` (tiler.py:309-366 ``get_fczyx``) for the fused :class:`TileView`.
+
+    Everything else of the step stays the reference's: image reading, trap detection at time point 0
+    (``set_areas_of_interest``), drift bookkeeping and the returned ``{"drift", "pixels"}`` dict (tiler.py:393-448).
+    Only what ``pixels`` IS changes — a view that the extraction kernels address through tile offsets; a consumer that
+    wants the dense ``(tiles, C, Z, h, w)`` array (a segmenter receiving ``tile.get_fczyx`` as passed method,
+    pipe_builder.py:155-157) gets it from ``np.asarray(view)``, cropped on the device with the reference's padding
+    rules."""
+
+    def get_fczyx(tp: int):
+        frame = tiler.pixels[tp]
+        if hasattr(frame, "compute"):  # dask: fetch the frame once (the reference fetches it once per channel)
+            frame = frame.compute(scheduler="synchronous")
+        locs = tiler.tile_locs
+        size = locs.tile_size if hasattr(locs, "tile_size") else tiler.tile_size
+        origins = []
+        for tile in locs.tiles:  # tiles.py:109-166: as_range(tp) = the two slices of the window at this time point
+            rows, cols = tile.as_range(tp)
+            origins.append((rows.start, cols.start))
+        return TileView(np.asarray(frame), np.asarray(origins, dtype=np.int64).reshape(-1, 2), size)
+
+    tiler.get_fczyx = get_fczyx  # instance attribute: shadows the method for run_tp and for passed methods
+    return tiler

@@ -10,9 +10,17 @@ collective on the data path: weak scaling).  The batch (``--fields`` x 65 MB of 
 larger than the 126 MB L2, so every step re-reads its inputs from HBM.
 
 Printed JSON line (rank 0):
-  value      object-features/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  value      object-features/s, inputs resident in HBM, CUDA-event timed, max over ranks; every step finds its own
+             per-field label maxima on the device (abx_label_max, what masks.max() is to the reference,
+             extract.py:279) and reads them back inside the timed region
   e2e        same metric through the public API ``aliby_b200.extract.extract_table`` with
-             pinned HOST inputs: H2D of labels+pixels and D2H of the table inside the timed region
+             pinned HOST inputs: H2D of labels+pixels and D2H of the table inside the timed region;
+             ``h2d_only_ms`` = the same bytes copied with no kernel at all (the PCIe / host-memory floor of the box,
+             all ranks copying at once)
+  e2e_dropin one C2 field per call through process_tree_masks + extract_tree + format_extraction with pageable
+             NumPy inputs — the calls pipe_core.py:217 makes
+  configs    device-timed and end-to-end numbers of C1, C2 (one field per call), C3 (per time point and batched,
+             fused crop, background metrics) and C4 (tools/bench_configs.py)
   roofline   dominant kernel (per-stage CUDA events recorded inside the timed steps) against
              the measured HBM copy peak of MEASURED_PEAKS.json
   cpu_baseline  the reference's CPU algorithm (oracle.port, faithful restatement) on a bounded
@@ -38,12 +46,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # stages of abx_extract bracketed by its stage events, and the kernels each one launches
-# object_stats: object_stats_tma (TMA-staged windows; object_stats_warp when the layout does not qualify);
-# object_edt: object_edt_grid, with the statistics of the few objects the TMA kernel left over on a helper stream next to it
+# object_stats: plan kernel + object_sweep (TMA-staged windows; object_stats_warp when the layout does not qualify);
+# object_edt: object_edt_grid, with the few (object, request) pairs the sweep kernel left over on a helper stream next to it
 STAGES = ["label_scan", "object_stats", "object_edt", "large_objects", "finalize"]
 N_STAGES = len(STAGES)
-LAUNCHES_PER_STEP = 10  # init_records, label_scan, object_stats_tma, sqrt_table, object_edt_grid, object_stats_warp (left-overs),
-# object_stats, shape_edt x2, finalize
+LAUNCHES_PER_STEP = 12  # label_max, init_records, label_scan, plan, object_sweep, sqrt_table, object_edt_grid,
+# object_stats_warp (left-over pairs), object_stats, shape_edt x2, finalize
 FIELD = (2160, 2160)
 N_CHANNELS = 5
 N_OBJECTS = 2000
@@ -234,6 +242,9 @@ def reference_arm(args):
                 n_feat += len(res)
     total = sum(times)
     value = n_feat / total
+    from tools import bench_configs
+
+    ref_configs = bench_configs.reference_configs(cores)
     line = {
         "impl": "reference",
         "metric": "object_features_per_s",
@@ -257,6 +268,7 @@ def reference_arm(args):
         },
         "e2e": {"value": value, "unit": "object-features/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "configs": ref_configs,  # C1 and one C3 time point in full, same algorithm, all cores
     }
     print(json.dumps(line))
     return 0
@@ -293,6 +305,13 @@ def ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one slice of the host's cores per rank, chosen BEFORE the pinned buffers are allocated (first touch): the ranks'
+        # copy threads and staging memory then do not share cores (all eight GPUs of the box hang off one NUMA node)
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // world)
+        mine = cpus[local_rank * per:(local_rank + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
 
     from aliby_b200 import _native as nat
     from aliby_b200 import engine, extract
@@ -320,11 +339,28 @@ def ours(args):
     lab_dev = lab_pin.to(device)
     offs = np.arange(F, dtype=np.int64) * (N_CHANNELS * H * W)
     plane_tile = np.arange(F, dtype=np.int32)
-    out = torch.empty((n_objects, plan.n_columns), dtype=torch.float64, device=device)
+    out_buf, out, status = engine.alloc_table(n_objects, plan.n_columns, device)
+
+    # The per-field label maxima (masks.max() of extract.py:279) are part of every step: abx_label_max on a side stream,
+    # read back through pinned memory; the maxima of step k + 1 are found while the kernels of step k run, so the
+    # launch stream never waits for the host.
+    side = torch.cuda.Stream(device=device)
+    nmax_host = torch.zeros(F, dtype=torch.int32).pin_memory()
+    nmax_ready = torch.cuda.Event()
+
+    def launch_label_max():
+        with torch.cuda.stream(side):
+            nmax_host.copy_(extract._label_max(lab_dev, device), non_blocking=True)
+            nmax_ready.record(side)
+
+    launch_label_max()
 
     def step(events=None):
-        engine.run_planes(plan, lab_dev, plane_tile, n_labels, px_dev, offs, H * W, H * W, W, N_CHANNELS, 1,
-                          out=out, stage_events=events)
+        nmax_ready.synchronize()
+        n_lab = nmax_host.numpy().astype(np.int64)
+        launch_label_max()
+        engine.run_planes(plan, lab_dev, plane_tile, n_lab, px_dev, offs, H * W, H * W, W, N_CHANNELS, 1,
+                          out=out, stage_events=events, status=status)
 
     def barrier():
         if dist is not None:
@@ -366,6 +402,8 @@ def ours(args):
         for h in evs:
             lib.abx_event_destroy(h)
     stage_ms /= args.steps
+    engine.raise_on_status(int(status.cpu()[0]))
+    assert np.array_equal(nmax_host.numpy().astype(np.int64), n_labels)
 
     # ---- e2e leg: public API, pinned host inputs, H2D + D2H inside the timed region ----
     masks_host = [lab_pin[i].numpy() for i in range(F)]
@@ -387,6 +425,17 @@ def ours(args):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
 
+    # ---- the copy floor: the same host-to-device bytes with no kernel, every rank at once ----
+    h2d_ms = float("nan")
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lab_dev.copy_(lab_pin, non_blocking=True)
+            px_dev.copy_(px_pin, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_ms = 1e3 * (time.perf_counter() - t0) / 3
+
     clocks = sampler.stop()
     clocks["window"] = "warm-up + timed steps + e2e leg"
 
@@ -397,12 +446,12 @@ def ours(args):
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = [[round(float(x[0]), 4), round(float(x[1]), 4)] for x in allr]
-    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=device)
+    t = torch.tensor([ms_total, e2e_s, h2d_ms], dtype=torch.float64, device=device)
     units = torch.tensor([float(n_objects * n_feat_cols), float(algo_bytes)], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(units, op=dist.ReduceOp.SUM)
-    ms_total, e2e_s = t.tolist()
+    ms_total, e2e_s, h2d_ms = t.tolist()
     feat_per_step, bytes_per_step = units.tolist()
 
     if rank == 0:
@@ -411,6 +460,7 @@ def ours(args):
         dom = int(np.argmax(stage_ms))
         achieved = (algo_bytes / 1e9) / (stage_ms[dom] / 1e3)
         prof = profiled_traffic() or {}
+        step_traffic = sum(v for k, v in prof.items() if k in STAGES and isinstance(v, (int, float)))
         line = {
             "metric": "object_features_per_s",
             "value": feat_per_step * args.steps / (ms_total / 1e3),
@@ -439,6 +489,8 @@ def ours(args):
                 "frac": achieved / peak,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "traffic": prof.get(names[dom]),
+                # all hot kernels of one step (ncu dram bytes, profiles/traffic.json) over the step's algorithmic bytes
+                "step_traffic_over_algorithmic": (step_traffic / algo_bytes) if step_traffic else None,
             },
             "e2e": {
                 "value": feat_per_step * e2e_steps / e2e_s,
@@ -446,6 +498,8 @@ def ours(args):
                 "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": table_bytes + 4 * F,
                 "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "h2d_only_ms": h2d_ms,  # max over ranks, all ranks copying at once: what the box's PCIe / host memory allows
+                "frac_of_copy_floor": h2d_ms / (1e3 * e2e_s / e2e_steps) if e2e_s == e2e_s else None,
                 "api": "aliby_b200.extract.extract_table(tree, masks, pixels) with pinned host arrays",
             },
             "gpu_launches": args.steps * LAUNCHES_PER_STEP,
@@ -454,6 +508,13 @@ def ours(args):
             "host_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count(),
             "clocks": clocks,
         }
+        if world == 1 and not args.no_configs:
+            from tools import bench_configs
+
+            del px_dev, lab_dev, out_buf
+            torch.cuda.empty_cache()
+            line["e2e_dropin"] = bench_configs.dropin_call_ms(device)
+            line["configs"] = bench_configs.measure_configs(device, peak)
         if world == 1 and not args.no_cpu:
             v, n_items, dt, _ = cpu_port_sample()
             line["cpu_baseline"] = {
@@ -483,6 +544,7 @@ def main():
     ap.add_argument("--fields", type=int, default=32, help="C2 fields per step per GPU (1.8 GB of inputs; 8 -> 1.59e9, 32 -> 1.92e9 object-features/s: launch latencies and kernel tails amortise)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration section (C1, C2 single field, C3, C4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -60,7 +60,7 @@ typedef enum abx_dtype { ABX_U8 = 0, ABX_U16 = 1, ABX_U32 = 2, ABX_F32 = 3, ABX_
  * left fold of true divisions whose result is float64 whatever the pixel dtype (distributors.py:19-21). */
 typedef enum abx_reduction { ABX_RED_MAX = 0, ABX_RED_ADD = 1, ABX_RED_DIV = 2 } abx_reduction;
 
-/* Dense-table column kinds. 0-15 need only the label plane, 16+ a pixel request. */
+/* Dense-table column kinds. 0-15 and 48-63 need only the label plane, 16-47 a pixel request. */
 typedef enum abx_metric {
   ABX_M_AREA = 0,
   ABX_M_CENTROID_X = 1,
@@ -87,7 +87,38 @@ typedef enum abx_metric {
   ABX_M_MAX = 25,
   ABX_M_MIN = 26,
   ABX_M_IMBACKGROUND = 27,
-  ABX_M_BACKGROUND_MAX5 = 28
+  ABX_M_BACKGROUND_MAX5 = 28,
+  /* cp_measure `intensity` (loaders.py:71-73,135-150; CellProfiler MeasureObjectIntensity without the edge features).
+   * Integrated / Mean / Std / Min / Max are ABX_M_TOTAL / MEAN / STD / MIN / MAX.  Quartiles, median and MAD follow
+   * CellProfiler's rank rule (i = floor(n f), linear interpolation to i + 1), not np.median.  Positions are 0-based
+   * plane coordinates.  Needs a pixel request; computed by the sweep kernel only (window <= 64 x 64, TMA-addressable
+   * layout): anything else sets status bit 1. */
+  ABX_M_CP_LOWER_QUARTILE = 32,
+  ABX_M_CP_MEDIAN = 33,
+  ABX_M_CP_UPPER_QUARTILE = 34,
+  ABX_M_CP_MAD = 35,
+  ABX_M_CP_MASS_DISPLACEMENT = 36,
+  ABX_M_CP_CENTER_MASS_X = 37,
+  ABX_M_CP_CENTER_MASS_Y = 38,
+  ABX_M_CP_MAX_POS_X = 39,
+  ABX_M_CP_MAX_POS_Y = 40,
+  ABX_M_CP_ZERO = 41, /* Location_MaxIntensity_Z of a 2-D image: 0 (NaN for an absent label) */
+  ABX_M_CP_CENTER_MASS_Z = 42, /* 0, NaN when the intensities sum to 0 (0 / 0 in CellProfiler) */
+  /* cp_measure `sizeshape` subset (label plane only, like 0-15): bounding box with exclusive maxima, 0-based centroid,
+   * equivalent diameter, extent, maximum / mean radius (distance to the background: need_edt bits 0 / 1), and
+   * eccentricity / axis lengths from the second central moments of the coordinates (need_edt bit 2) */
+  ABX_M_CP_BBOX_AREA = 48,
+  ABX_M_CP_BBOX_MAX_X = 49,
+  ABX_M_CP_BBOX_MAX_Y = 50,
+  ABX_M_CP_CENTER_X = 51,
+  ABX_M_CP_CENTER_Y = 52,
+  ABX_M_CP_EQUIVALENT_DIAMETER = 53,
+  ABX_M_CP_EXTENT = 54,
+  ABX_M_CP_MAXIMUM_RADIUS = 55,
+  ABX_M_CP_MEAN_RADIUS = 56,
+  ABX_M_CP_ECCENTRICITY = 57,
+  ABX_M_CP_MAJOR_AXIS_LENGTH = 58,
+  ABX_M_CP_MINOR_AXIS_LENGTH = 59
 } abx_metric;
 
 /* What a pixel request has to compute (bit mask). Sums/min/max are always produced. */
@@ -96,6 +127,8 @@ typedef enum abx_metric {
 #define ABX_F_TOP5 4u
 #define ABX_F_WRAPSQ 8u   /* total_squared with the square wrapped in the pixel dtype */
 #define ABX_F_MOI 16u
+#define ABX_F_CPQ 32u     /* CellProfiler quartiles + median (six order statistics) */
+#define ABX_F_CPMAD 64u   /* CellProfiler MAD and the position of the maximum (a second pass over the window) */
 /* abx_extract_args.request_feature_union only: some request uses ABX_RED_DIV (the float kernel must run
  * even though the pixels are integers) */
 #define ABX_F_HAS_DIV 0x40000000u
@@ -149,7 +182,8 @@ typedef struct abx_extract_args {
   int32_t n_requests;
   const abx_column* columns;   /* device, [n_columns] */
   int32_t n_columns;
-  int32_t need_edt;            /* bit 0: ECCENTRICITY/VOLUME/MINOR/MAJOR requested, bit 1: CONICAL_VOLUME */
+  int32_t need_edt;            /* bit 0: ECCENTRICITY/VOLUME/MINOR/MAJOR/CP_MAXIMUM_RADIUS requested, bit 1: CONICAL_VOLUME /
+                                * CP_MEAN_RADIUS, bit 2: second coordinate moments (CP_ECCENTRICITY / CP_*_AXIS_LENGTH) */
   int32_t request_feature_union; /* OR of features|bg_features over requests (host copy), | ABX_F_HAS_DIV */
   /* output: [n_objects][n_columns] float64, row-major */
   double* table;
@@ -167,7 +201,9 @@ typedef struct abx_extract_args {
   /* optional (ABI 3): device uint32 that receives the call's error flags when the kernels have run, stream-ordered like
    * the table (copy it back together with the table).  Bit 0: a label above its plane's n_labels
    * (plane_base[p + 1] - plane_base[p]) was met — those pixels belong to no row of the table and the background
-   * statistics of that plane are not meaningful; the caller passed a stale or wrong plane_base. */
+   * statistics of that plane are not meaningful; the caller passed a stale or wrong plane_base.  Bit 1: an
+   * ABX_M_CP_* intensity column was requested for an object that the sweep kernel does not serve (window above
+   * 64 x 64, or a chunked window with a wide value range): that cell of the table is not meaningful. */
   uint32_t* status;
 } abx_extract_args;
 

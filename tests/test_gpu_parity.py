@@ -679,10 +679,125 @@ def test_concurrent_calls_two_threads_two_streams(ab):
                     items, got = ab.process_tree_masks(tree, fields[k][1], fields[k][0], ab.extract_tree)
                     results[k] = (items, got)
                     check_items(items, got, want[k])
-        except Exception as e:  # noqa: BLE001
-            errors.append(e)
+        except Exception:  # noqa: BLE001
+            import traceback
+
+            errors.append(traceback.format_exc())
 
     threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
     [t.start() for t in threads]
     [t.join() for t in threads]
-    assert not errors, errors
+    assert not errors, "\n".join(errors)
+
+
+def test_graph_replay_of_repeated_small_calls(ab):
+    """The small-call regime of a time-lapse (same shapes at every time point): after two eager calls the extract step
+    replays a captured CUDA graph (engine.GraphedExtract).  Different data and different label counts at every call —
+    including more labels than the captured per-plane capacity, which rebuilds the graph — must give the oracle's
+    numbers, for a dense (tiles, C, Z, Y, X) array and for the fused tile view."""
+    from aliby_b200 import extract as ex
+    from aliby_b200 import synth
+    from aliby_b200.tile import TileView
+    from oracle import fast, port
+
+    tree = {"None": {"None": ["area", "eccentricity", "centroid_x"]},
+            0: {"max": ["mean", "median", "max2p5pc", "std", "imBackground"]}, 1: {"max": ["total", "max5px_median", "max"]}}
+    ex._graph_cache.clear(); ex._graph_seen.clear()
+    counts = [6, 9, 4, 7, 40, 5, 12]  # 40 > 2 x 9: above the first graph's capacity
+    for k, n in enumerate(counts):
+        tiles = [synth.make_field(900 + 10 * k + t, (96, 128), 2, n if t == 0 else 3, semi_axes=(3, 7)) for t in range(3)]
+        px = np.concatenate([t[0] for t in tiles])
+        masks = [t[1] for t in tiles]
+        against_oracle(ab, tree, masks, px)
+    assert any(isinstance(g, object) for g in ex._graph_cache.values()) and len(ex._graph_cache) >= 1
+    # fused tile crop: frames of one position, tile table fixed
+    frames, centres, labels = synth.make_trap_position(77, n_tp=5, n_channels=2, frame=(400, 480), n_tiles=6, tile_size=64)
+    org = centres - 32
+    ex._graph_cache.clear(); ex._graph_seen.clear()
+    for t in range(5):
+        view = TileView(frames[t], org, 64)
+        masks = [labels[t, i] for i in range(6)]
+        items, got = ab.process_tree_masks(tree, masks, view, ab.extract_tree)
+        _, want = fast.run_tree(tree, masks, port.crop_tiles(frames[t], centres, (64, 64)))
+        check_items(items, got, as_float_pairs(want)[0])
+    assert len(ex._graph_cache) == 1
+
+
+def _cpm_reference(tree, masks, pixels, cp_kwargs):
+    """Per (object, instruction) dicts of oracle/cpm.py, in the reference's item order (parity self-defined: the
+    cp_measure source is not available)."""
+    from oracle import cpm, port
+
+    if not isinstance(masks, list):
+        masks = [masks]
+    insts = port.tree_instructions(tree)
+    out = []
+    for tile_i, lab in enumerate(masks):
+        for k in range(1, int(lab.max()) + 1 if lab.size else 1):
+            for ch, red, metric in insts:
+                img = None if ch == "None" else port.project_z(pixels[tile_i, ch], port.Z_REDUCERS[red])
+                out.append(cpm.FEATURES[metric](lab == k, img, **cp_kwargs.get(metric, {})))
+    return out
+
+
+def _check_cp(items, got, want):
+    assert len(got) == len(want) == len(items)
+    loose = {"Intensity_StdIntensity", "AreaShape_MeanRadius", "AreaShape_Eccentricity", "AreaShape_MajorAxisLength",
+             "AreaShape_MinorAxisLength", "Intensity_MassDisplacement", "Location_CenterMassIntensity_X",
+             "Location_CenterMassIntensity_Y", "AreaShape_Center_X", "AreaShape_Center_Y", "Intensity_MeanIntensity",
+             "AreaShape_Extent", "AreaShape_EquivalentDiameter"}
+    for it, g, w in zip(items, got, want):
+        assert isinstance(g, dict) and list(g) == list(w), it
+        for key in w:
+            a, b = float(g[key][0]), float(w[key][0])
+            if b != b:
+                assert a != a, (it, key, a)
+            elif key in loose:
+                assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (it, key, a, b)
+            else:
+                assert a == b, (it, key, a, b)
+
+
+def test_cp_measure_intensity_and_sizeshape(ab):
+    """The trees the reference's stock builder emits (pipe_builder.py:115-120: sizeshape on the masks, intensity per
+    channel, edge features switched off): dict-valued results with CellProfiler's feature names, checked against
+    oracle/cpm.py — absent ids, 1-6 pixel cells, a constant and a saturated cell, narrow and full-range values (the
+    radix-select path), uint8 and uint16 — and the wide table the reference's format_extraction builds from them."""
+    from aliby_b200 import synth
+
+    kw = {"intensity": {"edge_measurements": False}}
+    tree = {"None": {"None": ("sizeshape",)}, 1: {"max": ("intensity",)}, 0: {"max": ("intensity",)}}
+    pixels, labels = synth.make_field(4711, (320, 384), 2, 60, semi_axes=(3, 24))
+    rng = np.random.default_rng(5)
+    cases = [(pixels, labels), (rng.integers(0, 65536, size=pixels.shape).astype(np.uint16), labels),
+             (rng.integers(0, 256, size=pixels.shape).astype(np.uint8), labels)]
+    for px, lab in cases:
+        items, got = ab.process_tree_masks(tree, lab, px, ab.extract_tree, cp_measure_kwargs=kw)
+        _check_cp(items, got, _cpm_reference(tree, lab, px, kw))
+    table = ab.format_extraction((items, got))
+    assert table.num_rows == int(labels.max())
+    assert "1/max/intensity/Intensity_MADIntensity" in table.column_names
+    assert "None/None/sizeshape/AreaShape_BoundingBoxMaximum_X" in table.column_names
+    assert table.column_names[2:] == sorted(table.column_names[2:])
+    # the same numbers through the generic (per item) formatter of the reference's contract
+    plain = ab.format_extraction((tuple(items), list(got)))
+    assert plain.column_names == table.column_names
+    for c in table.column_names:
+        x, y = table.column(c).to_pylist(), plain.column(c).to_pylist()
+        assert all((p == q) or (p != p and q != q) for p, q in zip(x, y)), c
+    # mixed with the cell.py functions, several tiles, and the dense fast entry
+    tree2 = {"None": {"None": ["area", "sizeshape"]}, 0: {"max": ["mean", "intensity", "median"]}}
+    tiles = [synth.make_field(4800 + t, (128, 192), 1, 8, semi_axes=(3, 12)) for t in range(3)]
+    px2 = np.concatenate([t[0] for t in tiles])
+    masks2 = [t[1] for t in tiles]
+    items2, got2 = ab.process_tree_masks(tree2, masks2, px2, ab.extract_tree, cp_measure_kwargs=kw)
+    want2 = _cpm_reference({"None": {"None": ["sizeshape"]}, 0: {"max": ["intensity"]}}, masks2, px2, kw)
+    dict_items = [(it, g) for it, g in zip(items2, got2) if isinstance(g, dict)]
+    _check_cp([it for it, _ in dict_items], [g for _, g in dict_items], want2)
+    fast_table = ab.extract_table(tree2, masks2, px2, cp_measure_kwargs=kw)
+    assert "0/max/intensity/Intensity_UpperQuartileIntensity" in fast_table.names and len(fast_table.names) == 1 + 15 + 1 + 16 + 1
+    # edge features and cp_measure functions without a kernel say so
+    with pytest.raises(NotImplementedError, match="edge_measurements"):
+        ab.process_tree_masks(tree, labels, pixels, ab.extract_tree)
+    with pytest.raises(KeyError, match="radial_zernikes"):
+        ab.process_tree_masks({0: {"max": ("radial_zernikes",)}}, labels, pixels, ab.extract_tree)

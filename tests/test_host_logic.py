@@ -250,10 +250,78 @@ def test_init_step_seam_matches_reference_partial_shape():
     assert baby.func is extract.process_tree_masks_overlap and baby.keywords["measure_fn"].keywords == {"overlap": True}
     with pytest.raises(ValueError, match="missing required 'tree'"):
         pipe.init_step("extract_nuclei", {})
-    with pytest.raises(NotImplementedError):
+    # extractmulti_* (cp_measure colocalisation) and every non-extract step belong to the reference's own init_step
+    with pytest.raises(ImportError, match="colocalisation"):  # the reference is not installed next to us in this container
         pipe.init_step("extractmulti_nuclei", {"tree": tree})
-    with pytest.raises(ImportError):  # the reference is not installed next to us in this container
+    with pytest.raises(ImportError):
         pipe.init_step("segment_nuclei", {})
+
+
+def test_init_step_serves_tile_steps_with_the_fused_tiler():
+    """tile* through the seam (pipe.py:56-57, tiler.py:393-448): pre-located tiles give a FusedTiler whose run_tp returns
+    {"drift", "pixels": TileView}; a reference Tiler keeps everything but its crop (fuse_reference_tiler)."""
+    from aliby_b200 import pipe
+    from aliby_b200.tile import FusedTiler, TileView, fuse_reference_tiler, tile_origins
+
+    pixels = np.zeros((3, 2, 1, 200, 240), np.uint16)
+    centres = [(60, 70), (120, 150)]
+    step = pipe.init_step("tile", {"pixels": pixels, "tile_centres": centres, "tile_size": 64})
+    assert isinstance(step, FusedTiler)
+    out = step.run_tp(1)
+    assert set(out) == {"drift", "pixels"} and isinstance(out["pixels"], TileView)
+    assert out["pixels"].shape == (2, 2, 1, 64, 64)
+    assert np.array_equal(out["pixels"].origins, tile_origins(centres, 64))
+    with pytest.raises(ValueError, match="tile_size"):
+        pipe.init_step("tile", {"pixels": pixels, "tile_centres": centres})
+    with pytest.raises(ImportError, match="image readers"):  # anything else needs the reference's Tiler (absent here)
+        pipe.init_step("tile", {"image_kwargs": {"source": "x.tiff"}, "tile_size": 64})
+
+    class Tile:  # stand-in with the reference's interface (tiles.py:109-166 as_range, tiler.py tile_locs / pixels)
+        def __init__(self, c):
+            self.c = c
+
+        def as_range(self, tp):
+            return slice(self.c[0] - 32, self.c[0] + 32), slice(self.c[1] - 32, self.c[1] + 32)
+
+    class Locs:
+        tiles = [Tile(c) for c in centres]
+        tile_size = 64
+
+    class RefTiler:
+        def __init__(self):
+            self.pixels, self.tile_locs, self.tile_size = pixels, Locs(), 64
+
+        def get_fczyx(self, tp):
+            raise AssertionError("the reference crop must not run")
+
+        def run_tp(self, tp):
+            return {"drift": [0.0, 0.0], "pixels": self.get_fczyx(tp)}
+
+    fused = fuse_reference_tiler(RefTiler())
+    view = fused.run_tp(2)["pixels"]
+    assert isinstance(view, TileView) and np.array_equal(view.origins, tile_origins(centres, 64))
+
+
+def test_stock_pipeline_steps_initialise():
+    """The step dicts the reference's builder emits (pipe_builder.py:115-134, restated here because aliby.pipe_builder
+    imports modules that are absent in this container): extract steps with cp_measure `sizeshape` + `intensity`
+    compile to a plan with dict-valued columns; features without a kernel are reported at init time."""
+    from aliby_b200 import engine, pipe
+
+    channels = [1, 0]
+    kw = {"ncores": None, "cp_measure_kwargs": {"intensity": {"edge_measurements": False}}}
+    tree = {"None": {"None": ("sizeshape",)}, **{ch: {"max": ("intensity",)} for ch in channels}}
+    step = pipe.init_step("extract_nuclei", {"tree": tree, "kwargs": kw})
+    assert step.func.__name__ == "process_tree_masks" and step.keywords["cp_measure_kwargs"] == kw["cp_measure_kwargs"]
+    plan = engine.compile_tree(tree, kw["cp_measure_kwargs"])
+    assert plan.error is None and plan.need_edt == 7
+    assert plan.inst_keys[0][0] == "AreaShape_Area" and "Intensity_MADIntensity" in plan.inst_keys[1]
+    # default builder features (radial_zernikes, feret, texture, ...) and edge intensities have no kernel
+    assert isinstance(engine.compile_tree({0: {"max": ("texture",)}}).error, KeyError)
+    assert isinstance(engine.compile_tree({0: {"max": ("intensity",)}}).error, NotImplementedError)
+    step = pipe.init_step("extract_cell", {"tree": {0: {"max": ("zernike",)}}, "kwargs": {"ncores": None}})
+    with pytest.raises(KeyError, match="zernike"):  # (reference absent: the step raises at its first call with objects)
+        step(masks=np.ones((8, 8), np.uint16), pixels=np.zeros((1, 1, 1, 8, 8), np.uint16))
 
 
 def test_ctypes_mirrors_match_the_c_header(tmp_path):

@@ -7,7 +7,7 @@ TAG=${1:-run}
 MODE=${2:-full}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-configs"
 if [ "$MODE" = "full" ]; then
   python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1
   echo "pytest rc=$?"; tail -3 $OUT/pytest_$TAG.log

@@ -137,7 +137,8 @@ extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* reco
   if (!records) return abx_set_error(ABX_ERR_INVALID, "records is NULL");
   if (!args->workspace || args->workspace_bytes < kCounterWords * sizeof(u32))
     return abx_set_error(ABX_ERR_WORKSPACE, "abx_label_scan needs a 128-byte workspace for its flags");
-  return launch_label_scan(args, records, static_cast<u32*>(args->workspace), nullptr, static_cast<cudaStream_t>(args->stream));
+  return launch_label_scan(args, records, static_cast<u32*>(args->workspace), nullptr, nullptr, 0,
+                           static_cast<cudaStream_t>(args->stream));
 }
 
 // One helper stream and a fork / join event pair per (host thread, device), created on first use and kept.
@@ -177,7 +178,9 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   void* const* ev = args->stage_events;
   auto mark = [&](int i) { if (ev && ev[i]) cudaEventRecord(static_cast<cudaEvent_t>(ev[i]), st); };
   mark(0);
-  if ((rc = launch_label_scan(args, ws.recs, ws.err, ws.bitmaps, st))) return rc;
+  const bool edt = (args->need_edt & 3) && args->n_objects > 0;
+  if ((rc = launch_label_scan(args, ws.recs, ws.err, ws.bitmaps, edt ? ws.sqrt_tab : nullptr, abx_sqrt_table_entries(), st)))
+    return rc;
   mark(1);
   // Z stacks: every requested (tile, channel) stack is reduced once, streaming, into planes of the workspace (max: pixel
   // dtype, add: uint32), and the window-sized objects then see a Z = 1 problem on those planes (zreduce.cu).
@@ -199,6 +202,18 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   // the pixel layout allows, plain gathers otherwise.  The plan kernel routes every object first.
   const bool sweep = abx_sweep_ok(&red);
   if ((rc = launch_plan(&red, ws, st, sweep))) return rc;
+  // From here the shape metrics (label planes and bitmaps only) and the intensity statistics are independent: the
+  // shape kernels go to a helper stream.  A big launch gains the overlap of one chain's tail with the other's start; a
+  // small one (a time point of a yeast position: a few hundred objects, every kernel a few microseconds) halves its
+  // chain of dependent launches.  With stage events (a profiling run) the two chains stay in line on the caller's
+  // stream so that each stage can be timed on its own.
+  Helper* hp = (edt && !ev) ? helper_stream() : nullptr;
+  if (hp) {
+    cudaEventRecord(hp->fork, st);
+    cudaStreamWaitEvent(hp->stream, hp->fork, 0);
+    if ((rc = launch_object_edt_warp(args, ws, hp->stream))) return rc;
+    if ((rc = launch_shape_edt(args, ws, hp->stream))) return rc;
+  }
   if (sweep) {
     if ((rc = launch_object_sweep(&red, ws, st))) return rc;
   } else if ((rc = launch_object_stats_warp(&red, ws, st, false))) {
@@ -206,31 +221,26 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   }
   if (zred && (rc = launch_object_stats_rest(args, ws, st))) return rc;  // the Z-add requests, from their uint32 sum planes
   mark(2);
-  // The few (object, request) pairs the sweep kernel left over (windows too wide at their alignment, wide value ranges
-  // of chunked windows) go through the gather kernel on a helper stream, one warp per CTA, next to the shape kernel:
-  // their cost is one warp's latency, which hides behind the EDT launch.
-  const bool edt = (args->need_edt & 3) && args->n_objects > 0;
-  Helper* hp = (sweep && edt) ? helper_stream() : nullptr;
-  if (sweep && !hp && (rc = launch_object_stats_warp(&red, ws, st, true))) return rc;
-  if (hp) cudaEventRecord(hp->fork, st);
-  if ((rc = launch_object_edt_warp(args, ws, st))) return rc;  // first: its CTAs take their places on the SMs
-  if (hp) {
-    cudaStreamWaitEvent(hp->stream, hp->fork, 0);
-    if ((rc = launch_object_stats_warp(&red, ws, hp->stream, true))) return rc;
-    cudaEventRecord(hp->join, hp->stream);
-    cudaStreamWaitEvent(st, hp->join, 0);
+  if (!hp && edt && (rc = launch_object_edt_warp(args, ws, st))) return rc;
+  // the few (object, request) pairs the sweep kernel left over (windows too wide at their alignment, wide value ranges
+  // of chunked windows): the gather kernel, one warp per CTA — behind the shape kernels on the helper stream when
+  // there is one (their cost is a few warps' latency: off the caller's chain)
+  if (sweep) {
+    if (hp) {
+      cudaEventRecord(hp->fork, st);  // the sweep kernel has written the pair list
+      cudaStreamWaitEvent(hp->stream, hp->fork, 0);
+    }
+    if ((rc = launch_object_stats_warp(&red, ws, hp ? hp->stream : st, true))) return rc;
   }
+  if (hp) cudaEventRecord(hp->join, hp->stream);
   mark(3);
   if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
   if ((rc = launch_big_background(args, ws, st))) return rc;  // backgrounds of large planes: streaming histogram
   if ((rc = launch_object_float(args, ws, st))) return rc;  // floating-point requests (float pixels, `div`)
-  if ((rc = launch_shape_edt(args, ws, st))) return rc;
+  if (!hp && (rc = launch_shape_edt(args, ws, st))) return rc;
   mark(4);
-  if ((rc = launch_finalize(args, ws, st))) return rc;
-  if (args->status) {
-    cudaError_t e = cudaMemcpyAsync(args->status, ws.err, sizeof(u32), cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) return abx_check_cuda(e, "status copy");
-  }
+  if (hp) cudaStreamWaitEvent(st, hp->join, 0);
+  if ((rc = launch_finalize(args, ws, st))) return rc;  // (also copies the error flags to args->status)
   mark(5);
   return ABX_OK;
 }

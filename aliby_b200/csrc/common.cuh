@@ -110,7 +110,8 @@ int abx_check_cuda(cudaError_t e, const char* what);
 int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws);
 int abx_validate(const abx_extract_args* a);
 
-int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err /* [kCounterWords] */, u64* bitmaps, cudaStream_t st);
+int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err /* [kCounterWords] */, u64* bitmaps,
+                      double* sqrt_tab, int n_sqrt, cudaStream_t st);
 int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool sweep_ok);
 int launch_object_sweep(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 bool abx_sweep_ok(const abx_extract_args* a);
@@ -122,7 +123,7 @@ int launch_object_float(const abx_extract_args* a, const Workspace& ws, cudaStre
 int launch_big_background(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 bool abx_big_background(const abx_extract_args* a);
 size_t abx_big_background_bytes(const abx_extract_args* a);
-int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);  // also copies the error flags to a->status
 bool abx_zreduce_ok(const abx_extract_args* a);
 size_t abx_zreduce_bytes(const abx_extract_args* a);
 int launch_zreduce(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);

@@ -214,8 +214,10 @@ finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __rest
                                 const int32_t* __restrict__ plane_base,
                                 int n_planes, int n_objects, const abx_request* __restrict__ requests,
                                 int n_requests, const abx_column* __restrict__ columns, int n_columns,
-                                int pixel_dtype, double* __restrict__ table) {
+                                int pixel_dtype, double* __restrict__ table, const u32* __restrict__ err,
+                                u32* __restrict__ status) {
   __shared__ double tile[kFinObjects][kFinColChunk + 1];
+  if (status != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *status = *err;  // every other kernel of the call has finished
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int obj0 = blockIdx.x * kFinObjects;
   const int obj = obj0 + lane;
@@ -243,10 +245,13 @@ finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __rest
 
 int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
   const i64 cells = (i64)a->n_objects * a->n_columns;
-  if (cells == 0) return ABX_OK;
+  if (cells == 0) {
+    if (a->status) return abx_check_cuda(cudaMemcpyAsync(a->status, ws.err, sizeof(u32), cudaMemcpyDeviceToDevice, st), "status copy");
+    return ABX_OK;
+  }
   const unsigned blocks = (unsigned)((a->n_objects + kFinObjects - 1) / kFinObjects);
   finalize_kernel<<<blocks, kFinWarps * 32, 0, st>>>(ws.recs, ws.chan, ws.shape, ws.mom, a->plane_base, a->n_planes,
                                                    a->n_objects, a->requests, a->n_requests, a->columns,
-                                                   a->n_columns, a->pixel_dtype, a->table);
+                                                   a->n_columns, a->pixel_dtype, a->table, ws.err, a->status);
   return abx_check_cuda(cudaGetLastError(), "finalize");
 }

@@ -25,8 +25,14 @@ namespace {
 constexpr int kScanThreads = 128;  // 4 warps x 8 KB of staging = 32 KB static shared memory per CTA
 constexpr int kScanWarps = kScanThreads / 32;
 
-__global__ void init_records_kernel(abx_object_rec* recs, int n_objects, int n_planes, int H, int W, u32* err) {
+// Records, counters, and — in the same launch, so that a small call has one node less in its chain — the zeroed torus
+// bitmaps (grid-stride over 16-byte words) and the sqrt table of the shape kernel.
+__global__ void init_records_kernel(abx_object_rec* recs, int n_objects, int n_planes, int H, int W, u32* err,
+                                    uint4* __restrict__ bitmap_words, size_t n_bitmap_words, double* __restrict__ sqrt_tab,
+                                    int n_sqrt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t k = (size_t)i; k < n_bitmap_words; k += (size_t)gridDim.x * blockDim.x) bitmap_words[k] = make_uint4(0, 0, 0, 0);
+  if (i < n_sqrt) sqrt_tab[i] = sqrt((double)i);
   if (i < kCounterWords) err[i] = 0;  // error flags, the work-list lengths, the work counters of the per-object kernels
   if (i < n_objects + n_planes) {
     abx_object_rec r;
@@ -119,7 +125,8 @@ template <bool kTma, bool kBits>
 __global__ void __launch_bounds__(kScanThreads)
 label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __restrict__ labels, int n_planes, int H, int W,
                   i64 plane_stride, i64 row_stride, const int32_t* __restrict__ plane_base,
-                  abx_object_rec* __restrict__ recs, int n_objects, int vec_ok, u32* err, u64* __restrict__ bitmaps) {
+                  abx_object_rec* __restrict__ recs, int n_objects, int vec_ok, u32* err, u64* __restrict__ bitmaps,
+                  int count_background) {
   __shared__ __align__(128) uint4 stage_all[kScanWarps][2][kRowBatch][32];  // 8 KB per warp
   __shared__ __align__(8) u64 bars[kScanWarps][2];
   const u32 lane = lane_id();
@@ -194,6 +201,10 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
     Piece cur;
     cur.label = 0; cur.n = 0; cur.sum_row = 0; cur.sum_col = 0; cur.rmin = 0; cur.rmax = 0; cur.cmask = 0;
     BitCol cur_bits{nullptr, 0};  // the tracked object's bitmap column for this strip
+    // label-0 pixels of this strip that lie inside the plane (a box that sticks out is zero-filled: not background)
+    const u32 vmask = c0 >= (u32)W ? 0u : (c0 + 8u <= (u32)W ? 0xFFu : (0xFFu >> (c0 + 8u - (u32)W)));
+    const u32 vcount = (u32)__popc(vmask);
+    u32 zeros = 0;
     issue(r_begin, 0);
     int buf = 0;
 #pragma unroll 1
@@ -213,10 +224,13 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
             cur.n += 8u; cur.sum_row += 8u * (r + 1u); cur.sum_col += 8u * c0 + 36u;
             cur.cmask = 0xFFu; cur.rmax = r;
             if (kBits) bitmap_or(cur_bits, r, 0xFFu);
+          } else {
+            zeros += vcount;
           }
           continue;
         }
         u32 rest = 0xFFu & ~eq_mask8(w, 0u);  // labelled pixels of this row
+        zeros += (u32)__popc(~rest & vmask);
         if (cur.label) {
           const u32 m = eq_mask8(w, cur.label);
           if (m) {
@@ -251,23 +265,10 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
       }
     }
     if (cur.label) emit_piece(recs, base, n_labels, cur, c0, err);
-  }
-}
-
-// background pixel count of every plane = H * W - labelled pixels (label 0 is never accumulated)
-__global__ void background_count_kernel(abx_object_rec* __restrict__ recs, const int32_t* __restrict__ plane_base,
-                                        int n_objects, int H, int W) {
-  __shared__ u32 part[8];
-  const int p = blockIdx.x;
-  u32 s = 0;
-  for (int i = plane_base[p] + threadIdx.x; i < plane_base[p + 1]; i += blockDim.x) s += recs[i].n;
-  s = __reduce_add_sync(0xFFFFFFFFu, s);
-  if (lane_id() == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    u32 tot = 0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += part[k];
-    recs[n_objects + p].n = (u32)H * (u32)W - tot;
+    if (count_background) {  // the plane's background record counts its own pixels (one atomic per warp and unit)
+      zeros = __reduce_add_sync(0xFFFFFFFFu, zeros);
+      if (lane == 0 && zeros) atomicAdd(&recs[n_objects + p].n, zeros);
+    }
   }
 }
 
@@ -321,13 +322,16 @@ static bool make_label_tensor_map(const abx_extract_args* a, CUtensorMap* tm) {
 }
 
 // bitmaps: [n_objects + 1][64] u64 torus bitmaps (the last one is a dummy for out-of-range labels), or nullptr
-int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, u64* bitmaps, cudaStream_t st) {
+int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err, u64* bitmaps, double* sqrt_tab, int n_sqrt,
+                      cudaStream_t st) {
   const int n_rec = a->n_objects + a->n_planes;
-  init_records_kernel<<<(n_rec + 255) / 256, 256, 0, st>>>(recs, a->n_objects, a->n_planes, a->H, a->W, err);
-  if (bitmaps) {
-    cudaError_t e = cudaMemsetAsync(bitmaps, 0, ((size_t)a->n_objects + 1) * 512, st);
-    if (e != cudaSuccess) return abx_check_cuda(e, "bitmap memset");
-  }
+  const size_t n_words = bitmaps ? ((size_t)a->n_objects + 1) * 32 : 0;  // 512 bytes per bitmap
+  size_t threads = (size_t)n_rec > n_words / 8 ? (size_t)n_rec : n_words / 8;  // <= 8 words per thread
+  if (threads < (size_t)n_sqrt) threads = (size_t)n_sqrt;
+  if (threads < (size_t)kCounterWords) threads = kCounterWords;
+  init_records_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(recs, a->n_objects, a->n_planes, a->H, a->W, err,
+                                                                          reinterpret_cast<uint4*>(bitmaps), n_words, sqrt_tab,
+                                                                          sqrt_tab ? n_sqrt : 0);
   const i64 units = (i64)a->n_planes * ((a->H + kBandRows - 1) / kBandRows) * ((a->W + 255) / 256);
   if (units == 0) return abx_check_cuda(cudaGetLastError(), "init_records");
   i64 blocks = (units + kScanWarps - 1) / kScanWarps;
@@ -341,14 +345,12 @@ int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err,
 #define ABX_SCAN(TMA, BITS)                                                                                              \
   label_scan_kernel<TMA, BITS><<<(int)blocks, kScanThreads, 0, st>>>(                                                     \
       tm, static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,  \
-      a->plane_base, recs, a->n_objects, vec_ok, err, bitmaps)
+      a->plane_base, recs, a->n_objects, vec_ok, err, bitmaps, a->with_background)
   if (tma && bitmaps) ABX_SCAN(true, true);
   else if (tma) ABX_SCAN(true, false);
   else if (bitmaps) ABX_SCAN(false, true);
   else ABX_SCAN(false, false);
 #undef ABX_SCAN
-  if (a->with_background)
-    background_count_kernel<<<a->n_planes, 256, 0, st>>>(recs, a->plane_base, a->n_objects, a->H, a->W);
   return abx_check_cuda(cudaGetLastError(), "label_scan");
 }
 

@@ -66,11 +66,6 @@ object_edt_grid(const abx_object_rec* __restrict__ recs, const u64* __restrict__
   }
 }
 
-__global__ void sqrt_table_kernel(double* tab, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) tab[i] = sqrt((double)i);
-}
-
 }  // namespace
 
 // sqrt(d2) for every squared distance the first EDT of a 64 x 64 window can produce (exact: IEEE sqrt)
@@ -87,8 +82,7 @@ int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaS
     if (e != cudaSuccess) return abx_check_cuda(e, "object_edt_grid smem attribute");
     done[dev] = true;
   }
-  const int n_tab = abx_sqrt_table_entries();
-  sqrt_table_kernel<<<(n_tab + 255) / 256, 256, 0, st>>>(ws.sqrt_tab, n_tab);
+  // (ws.sqrt_tab was filled by the label scan's first kernel)
   int grid = (a->n_objects + kGridWarps - 1) / kGridWarps;
   if (grid > 148 * 2) grid = 148 * 2;  // persistent: 2 CTAs per SM, warps pull objects from a counter
   object_edt_grid<<<grid, kGridWarps * 32, smem, st>>>(ws.recs, ws.bitmaps, ws.order_edt, ws.list_counts + kCntEdtBig,

@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
       const i64 row0 = org / a.row_stride;
       const int col0 = (int)(org - row0 * a.row_stride);
       const u32 s_px = (u32)col0 & (u32)(a.align - 1);
-      if (org < 0 || (u32)w + s_px > (u32)kSide) {
-        too_wide = true;  // (or a window that starts in front of the buffer): the gather kernel addresses anything
+      if (org < 0) {
+        too_wide = true;  // a window that starts in front of the buffer: the gather kernel addresses anything
       } else {
         ObjPlan pl;
         pl.tma_x = col0 - (int)s_px;
@@ -213,7 +213,7 @@ __device__ __forceinline__ Geo make_geo(const ObjPlan& pl, int obj, u32 flex_byt
   g.w = ((pl.geom >> 6) & 63u) + 1u;
   g.row0 = (pl.geom >> 12) & 63u;
   g.s_px = pl.geom >> 24;
-  g.rot = (((pl.geom >> 18) & 63u) - g.s_px) & 63u;
+  g.rot = (pl.geom >> 18) & 63u;  // the masks stay in bbox coordinates: the window is up to 15 columns wider than 64
   g.pitchB = ((g.w + g.s_px) * (u32)sizeof(PX) + 15u) & ~15u;
   g.h8 = (g.h + 7u) & ~7u;
   const u32 list_bytes = ((g.n + 1u) & ~1u) * 2u;
@@ -242,8 +242,8 @@ __device__ __forceinline__ void accumulate(Acc& a, u32 v, u32 hbase) {
 // moment-of-inertia terms of one pixel: (r, c) are window coordinates recovered from the entry's offset inside the window
 template <typename PX>
 __device__ __forceinline__ void accumulate_moi(Acc& a, u32 v, u32 off, u32 inv_pitch, u32 pitchB) {
-  // off = r * pitchB + c * sizeof(PX), off < 8192: r = off / pitchB by a reciprocal multiply, inv = 2^32 / pitchB + 1
-  // (exact for off < 2^13 and pitchB = 16, 32 ... 128: checked exhaustively in tests/test_host_logic.py)
+  // off = r * pitchB + c * sizeof(PX), off < 64 * pitchB: r = off / pitchB by a reciprocal multiply, inv = 2^32 / pitchB + 1
+  // (exact for pitchB = 16, 32 ... 144: checked exhaustively in tests/test_host_logic.py)
   const u32 r = __umulhi(off, inv_pitch);
   const u32 c = (off - r * pitchB) >> (sizeof(PX) == 1 ? 0 : 1);
   a.m10 += v * c;
@@ -484,8 +484,9 @@ constexpr u32 kSwHead = 1024 + kSwWarps * 128;  // request table | per warp: scr
 
 struct SweepMaps {
   // the pixel buffer as rows of row_stride elements; map [i][j]: box of 16 (i + 1) bytes x 8 (j + 1) rows, so that one
-  // copy brings a whole window (or window chunk)
-  CUtensorMap px[8][8];
+  // copy brings a whole window (or window chunk).  Up to 144 bytes wide: 64 columns of the bounding box plus the
+  // columns between the 16-byte aligned start of the box and the bounding box.
+  CUtensorMap px[9][8];
 };
 
 struct ReqEntry {   // one request this kernel computes
@@ -617,7 +618,7 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         const bool single = ((run0 & (run0 + 1ull)) == 0ull) && ((run1 & (run1 + 1ull)) == 0ull);
         if (__all_sync(kFull, single)) {
           // one run per row (convex cells): the row's entries are consecutive addresses
-          u32 p = list_addr + 2u * base0, v = win_base + rr0 * g.pitchB + a0 * (u32)sizeof(PX);
+          u32 p = list_addr + 2u * base0, v = win_base + rr0 * g.pitchB + (a0 + g.s_px) * (u32)sizeof(PX);
           const u32 e0 = p + 2u * c0;
           const u32 it0 = __reduce_max_sync(kFull, c0);
 #pragma unroll 4
@@ -626,7 +627,7 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
             p += 2u; v += (u32)sizeof(PX);
           }
           if (g.h > 32u) {
-            p = list_addr + 2u * base1; v = win_base + rr1 * g.pitchB + a1 * (u32)sizeof(PX);
+            p = list_addr + 2u * base1; v = win_base + rr1 * g.pitchB + (a1 + g.s_px) * (u32)sizeof(PX);
             const u32 e1 = p + 2u * c1;
             const u32 it1 = __reduce_max_sync(kFull, c1);
 #pragma unroll 4
@@ -641,7 +642,7 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
           for (int half = 0; half < 2; ++half) {
             u64 mm = half ? m1 : m0;
             u32 p = list_addr + 2u * (half ? base1 : base0);
-            const u32 row_a = win_base + (half ? rr1 : rr0) * g.pitchB;
+            const u32 row_a = win_base + (half ? rr1 : rr0) * g.pitchB + g.s_px * (u32)sizeof(PX);
             while (__any_sync(kFull, mm != 0ull)) {
               if (mm) {
                 const u32 b = (u32)__ffsll((long long)mm) - 1u;
@@ -834,7 +835,7 @@ bool make_maps(const abx_extract_args* a, SweepMaps* m) {
   EncodeFn encode = tensor_map_encoder();
   if (!encode || a->Z != 1 || a->pixel_elems <= 0 || a->n_requests > kMaxRequests - 2) return false;
   const size_t es = a->pixel_dtype == ABX_U8 ? 1 : 2;
-  if ((reinterpret_cast<uintptr_t>(a->pixels) & 15u) || (a->row_stride * (i64)es) % 16 || a->row_stride * (i64)es < 128 ||
+  if ((reinterpret_cast<uintptr_t>(a->pixels) & 15u) || (a->row_stride * (i64)es) % 16 || a->row_stride * (i64)es < 144 ||
       a->chan_stride % a->row_stride || a->chan_stride / a->row_stride > 0x7FFFFFFF / (a->C > 0 ? a->C : 1))
     return false;
   const i64 rows = a->pixel_elems / a->row_stride;  // whole rows inside the caller's buffer
@@ -850,7 +851,7 @@ bool make_maps(const abx_extract_args* a, SweepMaps* m) {
   const cuuint32_t estr[2] = {1u, 1u};
   const cuuint64_t pdim[2] = {(cuuint64_t)a->row_stride, (cuuint64_t)rows};
   const cuuint64_t pstr[1] = {(cuuint64_t)a->row_stride * es};
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 9; ++i)
     for (int j = 0; j < 8; ++j) {
       const cuuint32_t pbox[2] = {(cuuint32_t)(16u * (i + 1) / es), (cuuint32_t)(8 * (j + 1))};
       if (encode(&m->px[i][j], es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,

@@ -801,3 +801,59 @@ def test_cp_measure_intensity_and_sizeshape(ab):
         ab.process_tree_masks(tree, labels, pixels, ab.extract_tree)
     with pytest.raises(KeyError, match="radial_zernikes"):
         ab.process_tree_masks({0: {"max": ("radial_zernikes",)}}, labels, pixels, ab.extract_tree)
+
+
+SHARD_WORKER = r'''
+import sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from aliby_b200 import synth
+from aliby_b200.sharding import extract_sharded
+from aliby_b200.extract import extract_table
+
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=rank, world_size=2)
+torch.cuda.set_device(0)  # both ranks share the one GPU of the test box: the sharding logic is what is under test
+tree = {"None": {"None": ["area", "eccentricity"]}, 0: {"max": ["mean", "median", "max5px_median"]}, 1: {"max": ["total", "std"]}}
+
+def load(seed):
+    px, lab = synth.make_field(seed, (192, 256), 2, 25, semi_axes=(4, 14))
+    return lab, px
+
+units = list(range(500, 509))
+out = extract_sharded(tree, units, load)  # compute = the CUDA path
+if rank == 0:
+    assert [u for u, *_ in out] == units
+    for u, objs, names, vals in out:
+        t = extract_table(tree, *load(u))
+        assert np.array_equal(objs, t.objects) and names == t.names
+        assert np.array_equal(np.nan_to_num(vals, nan=-1), np.nan_to_num(t.values, nan=-1))
+    print("SHARD_GPU_OK", len(out))
+else:
+    assert out is None
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_extraction_on_the_gpu(ab, tmp_path):
+    """sharding.extract_sharded with its default compute (the CUDA path): one rank in-process, then two ranks (two
+    processes over gloo, both on the test box's GPU) whose gathered tables equal the single-rank ones."""
+    import os
+    import subprocess
+    import sys
+
+    from aliby_b200 import sharding, synth
+    from conftest import ROOT
+
+    tree = {"None": {"None": ["area"]}, 0: {"max": ["mean", "median"]}}
+    fields = {s: synth.make_field(s, (128, 160), 1, 10, semi_axes=(3, 10)) for s in (1, 2, 3)}
+    out = sharding.extract_sharded(tree, [1, 2, 3], lambda s: (fields[s][1], fields[s][0]), rank=0, world=1)
+    assert [u for u, *_ in out] == [1, 2, 3] and all(len(o) == int(fields[u][1].max()) for u, o, _, _ in out)
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER)
+    port = 29700 + (os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_GPU_OK 9" in outs[0]

@@ -453,3 +453,12 @@ def test_dense_profile_path_matches_the_reference_table():
         for a, b in zip(got.column(c).to_pylist(), want):
             assert (a == b) or (a != a and b != b), (c, a, b)
         assert str(got.schema.field(c).type) == json.loads(str(g["types"]))[j], c
+
+
+def test_reciprocal_row_index():
+    """object_sweep.cu recovers the window row of a list entry as umulhi(off, 2^32 / pitch + 1): exact for every offset of
+    a 64-row window at every pitch the kernel uses (16 ... 144 bytes)."""
+    for pitch in range(16, 145, 16):
+        inv = 0xFFFFFFFF // pitch + 1
+        off = np.arange(64 * pitch, dtype=np.uint64)
+        assert np.array_equal((off * np.uint64(inv)) >> np.uint64(32), off // np.uint64(pitch)), pitch

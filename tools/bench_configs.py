@@ -224,6 +224,33 @@ def measure_configs(device, peak_gbs, iters=10, which=("C1", "C2_single_field", 
             "yeast position: 5 channels, 40 tiles of 96^2 fused out of 1200^2 frames, cell + per-tile background metrics, "
             "one call per time point (numbers per time point)", n_obj / T, len(plan.instructions), algo_tp, d1, e1, s1,
             peak_gbs, note)
+        # the same per-time-point call captured once in a CUDA graph and replayed (engine.GraphedExtract: what the drop-in
+        # does from the third call with identical shapes on); every plane owns `cap` table rows
+        g = engine.GraphedExtract(plan, NT, TILE, TILE, tiles, (NC, 1, H, W), torch.uint16, off1, H * W, H * W, W, NC, 1, 16,
+                                  device)
+
+        def replay(events):
+            for t in range(T):
+                g.run(lab[t * NT:(t + 1) * NT], fr[t])  # device-to-device refresh of the static inputs + replay
+
+        d3 = _timed_calls(torch, replay, max(3, iters // 2), flush) / T
+
+        def replay_only(events):
+            for t in range(T):
+                g.run()
+
+        d3b = _timed_calls(torch, replay_only, max(3, iters // 2), flush) / T
+
+        def dropin_tp():  # process_tree_masks on the fused tile view, host frame in, item lists out (graph path inside)
+            for t in range(T):
+                extract.process_tree_masks(tree, masks[t], TileView(frames_pin[t], org, TILE), extract.extract_tree)
+
+        e3 = _e2e(torch, dropin_tp, 3) / T
+        out["C3_per_timepoint_graph"] = _entry(
+            "one call per time point replayed from a CUDA graph (static input buffers refreshed by device copies; "
+            "e2e_ms: process_tree_masks + extract_tree on the fused tile view, host frame in, Python item lists out)",
+            n_obj / T, len(plan.instructions), algo_tp, d3, e3, s1, peak_gbs, {**note, "replay_only_device_ms": d3b})
+        del g
         out["C3_batched"] = _entry(
             "the same 25 time points in ONE call (tile offsets into the (T, C, Z, Y, X) stack; numbers per time point)",
             n_obj / T, len(plan.instructions), algo_tp, d2, None, s2, peak_gbs, note)
@@ -309,3 +336,83 @@ def reference_configs(cores):
         out["C3_per_timepoint"] = {"items": len(jobs), "seconds": dt, "object_features_per_s": len(jobs) / dt, "cores": cores,
                                    "sample": "one time point: 40 tiles of 96^2, every cell x every instruction (in full)"}
     return out
+
+
+# ------------------------------------------------------------------------------------------ C5: plate sweep
+def c5_sweep(args):
+    """BASELINE.json configs[4] at a bounded size: ``--fields`` (default 64) DISTINCT C2 fields sharded over the ranks by
+    ``aliby_b200.sharding.extract_sharded`` (contiguous blocks, no collective on the data path), host arrays in, the
+    per-field tables gathered on rank 0.  Timed end to end (uploads, kernels, table download, gather) between barriers;
+    strong scaling: the sweep is the same whatever the number of ranks.  Rank 0 recomputes a few units on its own and
+    checks that the gathered tables are identical."""
+    import json
+
+    import torch
+
+    import bench
+    from aliby_b200 import extract, sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    n_units = max(world, args.fields if args.fields != 32 else 64)
+    units = [7000 + i for i in range(n_units)]
+    mine = sharding.shard_units(n_units, rank, world)
+    px, lab = bench.make_fields(len(mine), 7000 + int(mine[0]), workers=max(1, (os.cpu_count() or 1) // world))
+    px, lab = torch.from_numpy(px).pin_memory().numpy(), torch.from_numpy(lab).pin_memory().numpy()  # a reader's staging buffers
+    store = {units[i]: (lab[k], px[k][None]) for k, i in enumerate(mine)}
+    tree = bench.c2_tree()
+
+    def load(u):
+        return store[u]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sharding.extract_sharded(tree, units[: world], lambda u: store.get(u, next(iter(store.values()))), gather=False)  # warm-up
+    times = []
+    out = None
+    for _ in range(max(1, args.steps // 5)):
+        barrier()
+        t0 = time.perf_counter()
+        out = sharding.extract_sharded(tree, units, load)
+        barrier()
+        times.append(time.perf_counter() - t0)
+    t = torch.tensor([min(times)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        assert [u for u, *_ in out] == units
+        n_feat = sum(v.size for _, _, _, v in out)
+        n_obj = sum(len(o) for _, o, _, _ in out)
+        for u, objs, names, vals in out[:: max(1, len(out) // 4)][:4]:  # spot check against this rank alone
+            f_px, f_lab = bench._make(u)
+            ref = extract.extract_table(tree, f_lab, f_px[None], device=device)
+            assert np.array_equal(objs, ref.objects) and names == ref.names
+            assert np.array_equal(np.nan_to_num(vals, nan=-1.0), np.nan_to_num(ref.values, nan=-1.0)), u
+        line = {
+            "metric": "object_features_per_s", "value": n_feat / float(t[0]), "unit": "object-features/s", "n_gpus": world,
+            "steps": len(times), "warmup": 1, "ms_per_step": 1e3 * float(t[0]), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": f"C5 plate sweep at a bounded size: {n_units} distinct C2 fields (5ch x 2160^2 uint16, ~2k cells, "
+                                   "full cell-function set) through sharding.extract_sharded, host arrays in, tables gathered on rank 0",
+                       "fields": n_units, "objects": n_obj, "gathered_tables_checked_against_single_rank": True},
+            "e2e": {"value": n_feat / float(t[0]), "unit": "object-features/s",
+                    "h2d_bytes_per_step": n_units * (5 * 2160 * 2160 * 2 + 2160 * 2160 * 2), "d2h_bytes_per_step": n_feat * 8},
+            "gpu_launches": n_units * bench.LAUNCHES_PER_STEP,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0

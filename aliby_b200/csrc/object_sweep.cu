@@ -194,17 +194,57 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
 // ------------------------------------------------------------------------------------------------
 // sweep kernel
 // ------------------------------------------------------------------------------------------------
+// ---- tensor memory: the pixel list of the warp's object lives in TMEM (tcgen05.ld / tcgen05.st) ----
+// A CTA of four warps allocates 64 columns; warp w owns TMEM lanes [32 w, 32 w + 32), i.e. 32 lanes x 64 columns x
+// 32 bits = 4096 list entries of 16 bits.  Word (lane L, column c) = entries (2 c) * 32 + L (low half) and
+// (2 c + 1) * 32 + L (high half): for a fixed column and half the 32 lanes hold 32 CONSECUTIVE list positions —
+// consecutive pixels of a row, i.e. conflict-free shared-memory reads of the window.  The list never touches shared
+// memory: the 9 KB a window can take plus the 4 KB histogram are all an object needs there, so 16 objects are in
+// flight per SM instead of 12.
+constexpr u32 kTmemCols = 64;
+__device__ __forceinline__ void tmem_ld4(u32 taddr, u32 (&w)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ u32 tmem_ld1(u32 taddr) {
+  u32 w;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(w) : "r"(taddr) : "memory");
+  tmem_wait_ld();
+  return w;
+}
+__device__ __forceinline__ void tmem_st4(u32 taddr, const u32 (&w)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// f(shared address of the pixel, list position) for every list entry of this lane (positions lane, lane + 32, ...);
+// warp-collective: every lane calls it with the same n.  For the rare passes; the hot sweep has its own loop.
+template <typename F>
+__device__ __forceinline__ void for_each_entry(u32 tlist, u32 n, F f) {
+  const u32 lane = lane_id();
+  const u32 cols = (n + 63u) >> 6;
+#pragma unroll 1
+  for (u32 c = 0; c < cols; ++c) {
+    const u32 w = tmem_ld1(tlist + c);
+    const u32 e0 = 64u * c + lane, e1 = e0 + 32u;
+    if (e0 < n) f(w & 0xFFFFu, e0);
+    if (e1 < n) f(w >> 16, e1);
+  }
+}
+
 struct Geo {  // one object's window as the kernel sees it (warp-uniform)
   int obj;
   int tma_x, tma_y;  // box coordinates of the window in channel 0
   u32 n, h, w, s_px;
   u32 rot, row0;     // bitmap rotation (columns) and first bitmap row
-  u32 pitchB;        // window row pitch in bytes (a multiple of 16)
-  u32 h8, R;         // rows rounded up to whole boxes of 8; rows per chunk (a multiple of 8; == h8: one chunk)
+  u32 pitchB;        // window row pitch in bytes (a multiple of 16, at most 144)
+  u32 h8;            // rows rounded up to whole boxes of 8
 };
 
 template <typename PX>
-__device__ __forceinline__ Geo make_geo(const ObjPlan& pl, int obj, u32 flex_bytes) {
+__device__ __forceinline__ Geo make_geo(const ObjPlan& pl, int obj) {
   Geo g;
   g.obj = obj;
   g.tma_x = pl.tma_x; g.tma_y = pl.tma_y;
@@ -216,9 +256,6 @@ __device__ __forceinline__ Geo make_geo(const ObjPlan& pl, int obj, u32 flex_byt
   g.rot = (pl.geom >> 18) & 63u;  // the masks stay in bbox coordinates: the window is up to 15 columns wider than 64
   g.pitchB = ((g.w + g.s_px) * (u32)sizeof(PX) + 15u) & ~15u;
   g.h8 = (g.h + 7u) & ~7u;
-  const u32 list_bytes = ((g.n + 1u) & ~1u) * 2u;
-  g.R = g.h8;
-  if (g.h8 * g.pitchB + list_bytes > flex_bytes) g.R = ((flex_bytes - list_bytes) / g.pitchB) & ~7u;
   return g;
 }
 
@@ -251,51 +288,45 @@ __device__ __forceinline__ void accumulate_moi(Acc& a, u32 v, u32 off, u32 inv_p
   a.q += (u64)v * (u64)(c * c + r * r);
 }
 
-// One pass over list entries [first, first + cnt) (shared addresses of the object's pixels inside the resident window
-// chunk): blocks of 128 entries unpredicated, the last partial block predicated.  win_base: the shared address window
-// row 0 WOULD have (rows of later chunks count on from the rows before them), for the moment-of-inertia coordinates.
+// One pass over the object's n list entries (TMEM, shared addresses of its pixels inside the resident window): blocks
+// of 256 entries — four TMEM columns, eight entries per lane — unpredicated, the last partial block predicated.  The
+// TMEM load of block i + 1 is issued before block i is added up.
 template <typename PX, bool kMoi>
-__device__ __forceinline__ void sweep_chunk(Acc& a, u32 list_addr, u32 cnt, u32 hbase, u32 win_base, u32 inv_pitch, u32 pitchB) {
+__device__ __forceinline__ void sweep_list(Acc& a, u32 tlist, u32 n, u32 hbase, u32 win_base, u32 inv_pitch, u32 pitchB) {
   const u32 lane = lane_id();
-  u32 p = list_addr + 2u * lane;
-  const u32 pend = list_addr + 2u * (cnt & ~127u);
-  if (p < pend) {
-    // software pipeline: entries and pixels of block i + 1 are loaded while block i is added up
-    u32 k[4], v[4], kn[4];
-    k[0] = lds_u16_off<0>(p); k[1] = lds_u16_off<64>(p); k[2] = lds_u16_off<128>(p); k[3] = lds_u16_off<192>(p);
-    p += 256u;
+  const u32 full = n >> 8;
+  u32 w[4];
+  if (full) {
+    tmem_ld4(tlist, w);
+    tmem_wait_ld();
+  }
+#pragma unroll 1
+  for (u32 blk = 0; blk < full; ++blk) {
+    u32 k[8], v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = lds_px<PX>(k[u]);
-#pragma unroll 2
-    while (p < pend) {
-      kn[0] = lds_u16_off<0>(p); kn[1] = lds_u16_off<64>(p); kn[2] = lds_u16_off<128>(p); kn[3] = lds_u16_off<192>(p);
-      p += 256u;
-      u32 vn[4];
+    for (int u = 0; u < 4; ++u) { k[2 * u] = w[u] & 0xFFFFu; k[2 * u + 1] = w[u] >> 16; }
+    if (blk + 1 < full) tmem_ld4(tlist + 4u * (blk + 1u), w);  // (in flight under the arithmetic below)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) vn[u] = lds_px<PX>(kn[u]);
+    for (int u = 0; u < 8; ++u) v[u] = lds_px<PX>(k[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        accumulate<PX>(a, v[u], hbase);
-        if (kMoi) accumulate_moi<PX>(a, v[u], k[u] - win_base, inv_pitch, pitchB);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { k[u] = kn[u]; v[u] = vn[u]; }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       accumulate<PX>(a, v[u], hbase);
       if (kMoi) accumulate_moi<PX>(a, v[u], k[u] - win_base, inv_pitch, pitchB);
     }
+    tmem_wait_ld();
   }
-  // the last partial block
-  const u32 rem = cnt & 127u;
+  const u32 rem = n & 255u;
+  if (rem) {
+    tmem_ld4(tlist + 4u * full, w);
+    tmem_wait_ld();
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (lane + 32u * u < rem) {
-      const u32 k = lds_u16(pend + 2u * (lane + 32u * u));
-      const u32 v = lds_px<PX>(k);
-      accumulate<PX>(a, v, hbase);
-      if (kMoi) accumulate_moi<PX>(a, v, k - win_base, inv_pitch, pitchB);
+    for (int u = 0; u < 8; ++u) {
+      if (lane + 32u * (u32)u < rem) {
+        const u32 k = (u & 1) ? (w[u >> 1] >> 16) : (w[u >> 1] & 0xFFFFu);
+        const u32 v = lds_px<PX>(k);
+        accumulate<PX>(a, v, hbase);
+        if (kMoi) accumulate_moi<PX>(a, v, k - win_base, inv_pitch, pitchB);
+      }
     }
   }
 }
@@ -399,9 +430,8 @@ struct XfAbsDev {
 };
 
 template <typename PX, typename Xf>
-__device__ __forceinline__ void wide_select(u32 list_addr, u32 n, u32 lo, u32 hi, const Xf& xf, const u32 (&ranks)[4], u32* hist,
+__device__ __forceinline__ void wide_select(u32 tlist, u32 n, u32 lo, u32 hi, const Xf& xf, const u32 (&ranks)[4], u32* hist,
                                             u32* t, u32 (&key)[4]) {
-  const u32 lane = lane_id();
   const u32 range = hi - lo;
   int s0 = 0;
   while ((range >> s0) >= 1024u) ++s0;
@@ -409,8 +439,7 @@ __device__ __forceinline__ void wide_select(u32 list_addr, u32 n, u32 lo, u32 hi
   __syncwarp();
   hist_zero(hist, 1024u);
   __syncwarp();
-#pragma unroll 1
-  for (u32 i = lane; i < n; i += 32) hist_add(hist, (xf(lds_px<PX>(lds_u16(list_addr + 2u * i))) - lo) >> s0);
+  for_each_entry(tlist, n, [&](u32 k, u32) { hist_add(hist, (xf(lds_px<PX>(k)) - lo) >> s0); });
   __syncwarp();
   find_ranks32(hist, nb, ranks, t);
   int cur = s0;
@@ -423,15 +452,14 @@ __device__ __forceinline__ void wide_select(u32 list_addr, u32 n, u32 lo, u32 hi
     __syncwarp();
     hist_zero(hist, 512u);
     __syncwarp();
-#pragma unroll 1
-    for (u32 i = lane; i < n; i += 32) {
-      const u32 d = xf(lds_px<PX>(lds_u16(list_addr + 2u * i))) - lo;
+    for_each_entry(tlist, n, [&](u32 k, u32) {
+      const u32 d = xf(lds_px<PX>(k)) - lo;
       const u32 hi_bits = d >> cur;
       const u32 sb = (d >> nxt) & (nsub - 1u);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (hi_bits == key[j]) hist_add(hist, 128u * j + sb);
-    }
+    });
     __syncwarp();
     find_ranks32_x4(hist, t);
 #pragma unroll
@@ -445,11 +473,10 @@ __device__ __forceinline__ void wide_select(u32 list_addr, u32 n, u32 lo, u32 hi
 
 // The four ranks of the cell functions (two medians, top 2.5 %, top 5) of a wide-range request.
 template <typename PX>
-__device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32 vmax, u64 sum, u32 feats, u32* hist, u32* t,
+__device__ __forceinline__ Ranked wide_ranks(u32 tlist, u32 n, u32 vmin, u32 vmax, u64 sum, u32 feats, u32* hist, u32* t,
                                              const u32 (&ranks)[4]) {
-  const u32 lane = lane_id();
   u32 key[4];
-  wide_select<PX>(list_addr, n, vmin, vmax, XfIdentity(), ranks, hist, t, key);
+  wide_select<PX>(tlist, n, vmin, vmax, XfIdentity(), ranks, hist, t, key);
   Ranked r;
   r.med_lo = vmin + key[0]; r.med_hi = vmin + key[1];
   const u32 v2 = vmin + key[2], v3 = vmin + key[3];
@@ -457,12 +484,11 @@ __device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32
   if (feats & (ABX_F_TOP2P5 | ABX_F_TOP5)) {
     u64 sb2 = 0, sb3 = 0;
     u32 cb2 = 0, cb3 = 0;
-#pragma unroll 1
-    for (u32 i = lane; i < n; i += 32) {
-      const u32 x = lds_px<PX>(lds_u16(list_addr + 2u * i));
+    for_each_entry(tlist, n, [&](u32 k, u32) {
+      const u32 x = lds_px<PX>(k);
       if (x < v2) { sb2 += x; ++cb2; }
       if (x < v3) { sb3 += x; ++cb3; }
-    }
+    });
     sb2 = warp_sum64(sb2); sb3 = warp_sum64(sb3);
     cb2 = __reduce_add_sync(kFull, cb2); cb3 = __reduce_add_sync(kFull, cb3);
     below2 = sb2 + (u64)(ranks[2] - cb2) * (u64)v2;
@@ -475,17 +501,20 @@ __device__ __forceinline__ Ranked wide_ranks(u32 list_addr, u32 n, u32 vmin, u32
 }
 
 
-// Three warps per CTA, four CTAs per SM: twelve objects in flight per SM, and every shared address of a CTA stays below
-// 2^16 (1 KB reserved + 56 KB), so that a list entry can be the 16-bit shared address of its pixel.
-constexpr int kSwWarps = 3, kSwCtasPerSm = 4;
+// Four warps per CTA (one TMEM lane quarter each), four CTAs per SM: sixteen objects in flight per SM, and every
+// shared address of a CTA stays below 2^16 (1 KB reserved + 56 KB), so that a list entry can be the 16-bit shared
+// address of its pixel.
+constexpr int kSwWarps = 4, kSwCtasPerSm = 4;
 constexpr int kMaxRequests = 64;   // request table in shared memory
 constexpr u32 kSwSmem = 57344;     // 4 x (56 KB + 1 KB reserved) = the 228 KB of an SM
-constexpr u32 kSwHead = 1024 + kSwWarps * 128;  // request table | per warp: scratch u32[16], mbarrier
+// head: request table 1 KB | per warp 512 B: scratch u32[16], mbarrier (@64), row table u32[65] (@128)
+constexpr u32 kWarpHead = 512, kSwHead = 1024 + kSwWarps * kWarpHead;
+constexpr u32 kMaxWindow = 64 * 144;  // 64 rows of at most 144 bytes
 
 struct SweepMaps {
   // the pixel buffer as rows of row_stride elements; map [i][j]: box of 16 (i + 1) bytes x 8 (j + 1) rows, so that one
-  // copy brings a whole window (or window chunk).  Up to 144 bytes wide: 64 columns of the bounding box plus the
-  // columns between the 16-byte aligned start of the box and the bounding box.
+  // copy brings a whole window.  Up to 144 bytes wide: 64 columns of the bounding box plus the columns between the
+  // 16-byte aligned start of the box and the bounding box.
   CUtensorMap px[9][8];
 };
 
@@ -501,22 +530,23 @@ __global__ void __launch_bounds__(kSwWarps * 32, kSwCtasPerSm)
 object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__ plan, const int* __restrict__ order,
              const u32* __restrict__ order_counts /* [0] big, [1] small */, int order_cap, u32* __restrict__ work_counter,
              const u64* __restrict__ bitmaps, int chan_rows, const abx_request* __restrict__ requests, int n_requests,
-             ChanStats* __restrict__ chan, int* __restrict__ pair_list, u32* __restrict__ pair_count, int split_log2,
-             u32* __restrict__ err) {
+             ChanStats* __restrict__ chan, int split_log2) {
   const u32 lane = lane_id();
   const u32 warp = threadIdx.x >> 5;
   const u32 sbase = smem_addr_of(dyn);
-  // ---- shared memory: head | histograms (4 KB each, 4 KB aligned in the shared window) | flex areas ----
+  // ---- shared memory: head | histograms (4 KB each, 4 KB aligned in the shared window) | one window per warp ----
   ReqEntry* rtab = reinterpret_cast<ReqEntry*>(dyn);
-  int* n_valid_p = reinterpret_cast<int*>(dyn + kMaxRequests * sizeof(ReqEntry) - 16);  // (the table holds < 64 entries then)
+  int* n_valid_p = reinterpret_cast<int*>(dyn + kMaxRequests * sizeof(ReqEntry) - 16);  // (the table holds < 63 entries)
+  u32* tmem_base_p = reinterpret_cast<u32*>(dyn + kMaxRequests * sizeof(ReqEntry) - 12);
   const u32 hist0 = (sbase + kSwHead + 4095u) & ~4095u;
   const u32 flex0 = hist0 + kSwWarps * 4096u;
   const u32 flex_bytes = ((sbase + kSwSmem - flex0) / kSwWarps) & ~127u;
   const u32 hbase = hist0 + warp * 4096u;
   const u32 win_base = flex0 + warp * flex_bytes;
   u32* hist = reinterpret_cast<u32*>(dyn + (hbase - sbase));
-  u32* t = reinterpret_cast<u32*>(dyn + 1024u + warp * 128u);
-  const u32 bar = sbase + 1024u + warp * 128u + 64u;
+  u32* t = reinterpret_cast<u32*>(dyn + 1024u + warp * kWarpHead);
+  const u32 bar = sbase + 1024u + warp * kWarpHead + 64u;
+  u32* rowinfo = reinterpret_cast<u32*>(dyn + 1024u + warp * kWarpHead + 128u);  // [65]: list start | row address << 16
   if (threadIdx.x == 0) {  // the requests this kernel computes (div requests belong to object_float.cu)
     int nv = 0;
     for (int q = 0; q < n_requests; ++q) {
@@ -528,14 +558,24 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
     }
     *n_valid_p = nv;
   }
+  if (warp == 0) {  // tensor memory for the four pixel lists of this CTA
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_of(tmem_base_p)), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   if (lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   hist_zero(hist, 1024u);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int n_valid = *n_valid_p;
+  const u32 tmem_base = *tmem_base_p;
+  const u32 tlist = tmem_base + ((warp * 32u) << 16);  // this warp's lane quarter, column 0
   u32 parity = 0;
+  if (flex_bytes < kMaxWindow) __trap();  // (layout constants out of step)
 
   const u32 n_big = order_counts[0], n_small = order_counts[1];
   const int n_items = (int)(n_big + n_small) << split_log2;
@@ -555,19 +595,17 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
     lo = (part * n_valid) >> split_log2;
     hi = ((part + 1) * n_valid) >> split_log2;
   };
-  // One copy = rows [c R, c R + rows) of the window of one request: a single box.
-  auto issue = [&](const Geo& g, int row_off, u32 c) {  // every lane is done with the window (syncwarp by the caller)
+  // One copy = the whole window of one request: a single box of h8 rows.
+  auto issue = [&](const Geo& g, int row_off) {  // every lane is done with the window (syncwarp by the caller)
     if (lane == 0) {
-      const u32 rows = min(g.R, g.h8 - c * g.R);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, rows * g.pitchB);
-      tma_box_2d(win_base, &maps.px[(g.pitchB >> 4) - 1u][(rows >> 3) - 1u], g.tma_x, g.tma_y + row_off + (int)(c * g.R), bar);
+      mbar_expect_tx(bar, g.h8 * g.pitchB);
+      tma_box_2d(win_base, &maps.px[(g.pitchB >> 4) - 1u][(g.h8 >> 3) - 1u], g.tma_x, g.tma_y + row_off, bar);
     }
   };
-  auto prefetch = [&](const Geo& g, int row_off) {  // first chunk of a window, into L2
+  auto prefetch = [&](const Geo& g, int row_off) {  // the same box, into L2
 #ifndef ABX_NO_PREFETCH
-    if (lane == 0)
-      tma_prefetch_2d(&maps.px[(g.pitchB >> 4) - 1u][(g.R >> 3) - 1u], g.tma_x, g.tma_y + row_off);
+    if (lane == 0) tma_prefetch_2d(&maps.px[(g.pitchB >> 4) - 1u][(g.h8 >> 3) - 1u], g.tma_x, g.tma_y + row_off);
 #endif
   };
 
@@ -578,85 +616,103 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
   bool have = item < n_items;
   if (have) {
     const int obj = object_of(item);
-    g = make_geo<PX>(plan[obj], obj, flex_bytes);
+    g = make_geo<PX>(plan[obj], obj);
     item_requests(item, i_lo, i_hi);
-    if (i_lo < i_hi) issue(g, rtab[i_lo].row_off, 0);
+    if (i_lo < i_hi) issue(g, rtab[i_lo].row_off);
   }
   while (have) {
     // the warp's next object (its first window is requested by this object's last sweep)
     const bool have_next = nxt_item < n_items;
     if (have_next) {
       const int nobj = object_of(nxt_item);
-      gn = make_geo<PX>(plan[nobj], nobj, flex_bytes);
+      gn = make_geo<PX>(plan[nobj], nobj);
       item_requests(nxt_item, ni_lo, ni_hi);
     }
     const bool next_has = have_next && ni_lo < ni_hi;
     const int after_item = have_next ? fetch() : n_items;
 
     if (i_lo < i_hi) {
-      // ---- pixel list from the torus bitmap (while the first window is in flight) ----
-      const u32 list_addr = win_base + g.R * g.pitchB;
-      const u64* bm = bitmaps + (size_t)g.obj * 64u;
-      u64 m0 = bm[(g.row0 + lane) & 63u], m1 = bm[(g.row0 + lane + 32u) & 63u];
-      m0 = (m0 >> g.rot) | (g.rot ? (m0 << (64u - g.rot)) : 0ull);
-      m1 = (m1 >> g.rot) | (g.rot ? (m1 << (64u - g.rot)) : 0ull);
-      const u32 c0 = (u32)__popcll(m0), c1 = (u32)__popcll(m1);
-      u32 i0 = c0, i1 = c1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 a = __shfl_up_sync(kFull, i0, o), b = __shfl_up_sync(kFull, i1, o);
-        if (lane >= (u32)o) { i0 += a; i1 += b; }
-      }
-      const u32 tot0 = __shfl_sync(kFull, i0, 31);
-      const u32 base0 = i0 - c0, base1 = tot0 + i1 - c1;  // list position of the first pixel of rows lane, lane + 32
-      const bool multi = g.R < g.h8;
+      // ---- pixel list from the torus bitmap, into TMEM (while the first window is in flight) ----
       {
-        // row r of chunk r / R: entry = shared address of its pixel inside the chunk buffer
-        const u32 rr0 = multi ? lane % g.R : lane, rr1 = multi ? (lane + 32u) % g.R : lane + 32u;
+        const u64* bm = bitmaps + (size_t)g.obj * 64u;
+        u64 m0 = bm[(g.row0 + lane) & 63u], m1 = bm[(g.row0 + lane + 32u) & 63u];
+        m0 = (m0 >> g.rot) | (g.rot ? (m0 << (64u - g.rot)) : 0ull);
+        m1 = (m1 >> g.rot) | (g.rot ? (m1 << (64u - g.rot)) : 0ull);
+        const u32 c0 = (u32)__popcll(m0), c1 = (u32)__popcll(m1);
+        u32 i0 = c0, i1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 a = __shfl_up_sync(kFull, i0, o), b = __shfl_up_sync(kFull, i1, o);
+          if (lane >= (u32)o) { i0 += a; i1 += b; }
+        }
+        const u32 tot0 = __shfl_sync(kFull, i0, 31);
+        const u32 base0 = i0 - c0, base1 = tot0 + i1 - c1;  // list position of the first pixel of rows lane, lane + 32
         const u32 a0 = m0 ? (u32)__ffsll((long long)m0) - 1u : 0u, a1 = m1 ? (u32)__ffsll((long long)m1) - 1u : 0u;
         const u64 run0 = m0 >> a0, run1 = m1 >> a1;
-        const bool single = ((run0 & (run0 + 1ull)) == 0ull) && ((run1 & (run1 + 1ull)) == 0ull);
-        if (__all_sync(kFull, single)) {
-          // one run per row (convex cells): the row's entries are consecutive addresses
-          u32 p = list_addr + 2u * base0, v = win_base + rr0 * g.pitchB + (a0 + g.s_px) * (u32)sizeof(PX);
-          const u32 e0 = p + 2u * c0;
-          const u32 it0 = __reduce_max_sync(kFull, c0);
-#pragma unroll 4
-          for (u32 it = 0; it < it0; ++it) {
-            if (p < e0) sts_u16(p, v);
-            p += 2u; v += (u32)sizeof(PX);
-          }
-          if (g.h > 32u) {
-            p = list_addr + 2u * base1; v = win_base + rr1 * g.pitchB + (a1 + g.s_px) * (u32)sizeof(PX);
-            const u32 e1 = p + 2u * c1;
-            const u32 it1 = __reduce_max_sync(kFull, c1);
-#pragma unroll 4
-            for (u32 it = 0; it < it1; ++it) {
-              if (p < e1) sts_u16(p, v);
-              p += 2u; v += (u32)sizeof(PX);
+        const bool single = __all_sync(kFull, ((run0 & (run0 + 1ull)) == 0ull) && ((run1 & (run1 + 1ull)) == 0ull));
+        constexpr u32 es = (u32)sizeof(PX);
+        const u32 cols = (g.n + 63u) >> 6;
+        __syncwarp();
+        if (single) {
+          // One run per row (convex cells): the entry of list position e in row r is A_r + e * es, with
+          // A_r = window row address + (first column - list start of the row) * es.  Row table: start | A << 16.
+          rowinfo[lane] = base0 | ((win_base + lane * g.pitchB + (a0 + g.s_px) * es - base0 * es) << 16);
+          rowinfo[lane + 32] = base1 | ((win_base + (lane + 32u) * g.pitchB + (a1 + g.s_px) * es - base1 * es) << 16);
+          if (lane == 0) rowinfo[64] = 0xFFFFu;  // sentinel: no list position reaches it
+          __syncwarp();
+          u32 r = 0, cur = rowinfo[0], nx = rowinfo[1];
+#pragma unroll 1
+          for (u32 c = 0; c < cols; c += 4) {
+            u32 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              u32 e = 64u * (c + (u32)u) + lane, pair = 0;
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf, e += 32u) {
+                while (e >= (nx & 0xFFFFu)) { cur = nx; ++r; nx = rowinfo[r + 1u]; }  // (rows only ever advance)
+                pair |= (((cur >> 16) + e * es) & 0xFFFFu) << (16 * hf);
+              }
+              w[u] = pair;
             }
+            tmem_st4(tlist + c, w);
           }
         } else {
-          // any shape: bit by bit
+          // Any shape: the row masks go through the (clean) histogram area, the column of a list position is the
+          // (e - start)-th set bit of its row's mask.
+          hist[2u * lane] = (u32)m0; hist[2u * lane + 1u] = (u32)(m0 >> 32);
+          hist[2u * (lane + 32u)] = (u32)m1; hist[2u * (lane + 32u) + 1u] = (u32)(m1 >> 32);
+          rowinfo[lane] = base0; rowinfo[lane + 32] = base1;
+          if (lane == 0) rowinfo[64] = 0xFFFFu;
+          __syncwarp();
+          u32 r = 0, start = rowinfo[0], nx = rowinfo[1];
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            u64 mm = half ? m1 : m0;
-            u32 p = list_addr + 2u * (half ? base1 : base0);
-            const u32 row_a = win_base + (half ? rr1 : rr0) * g.pitchB + g.s_px * (u32)sizeof(PX);
-            while (__any_sync(kFull, mm != 0ull)) {
-              if (mm) {
-                const u32 b = (u32)__ffsll((long long)mm) - 1u;
-                mm &= mm - 1ull;
-                sts_u16(p, row_a + b * (u32)sizeof(PX));
-                p += 2u;
+          for (u32 c = 0; c < cols; c += 4) {
+            u32 w[4];
+#pragma unroll 1
+            for (int u = 0; u < 4; ++u) {
+              u32 e = 64u * (c + (u32)u) + lane, pair = 0;
+#pragma unroll 1
+              for (int hf = 0; hf < 2; ++hf, e += 32u) {
+                while (e >= nx) { start = nx; ++r; nx = rowinfo[r + 1u]; }
+                u32 addr = 0;
+                if (e < g.n) {
+                  const u32 lo = hist[2u * r], hi = hist[2u * r + 1u], nth = e - start, pl = (u32)__popc(lo);
+                  const u32 col = nth < pl ? __fns(lo, 0u, (int)nth + 1) : 32u + __fns(hi, 0u, (int)(nth - pl) + 1);
+                  addr = win_base + r * g.pitchB + (col + g.s_px) * es;
+                }
+                pair |= (addr & 0xFFFFu) << (16 * hf);
               }
+              w[u] = pair;
             }
+            tmem_st4(tlist + c, w);
           }
+          __syncwarp();
+          *reinterpret_cast<uint4*>(hist + 4u * lane) = make_uint4(0, 0, 0, 0);  // the 128 words of the masks
         }
+        tmem_wait_st();
+        __syncwarp();
       }
-      __syncwarp();
       const u32 inv_pitch = 0xFFFFFFFFu / g.pitchB + 1u;
-      const u32 n_chunks = multi ? (g.h8 + g.R - 1u) / g.R : 1u;
       const u32 k2p5 = (u32)ceil((double)g.n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
       const u32 ranks[4] = {(g.n - 1) / 2, g.n / 2, g.n - k2p5, g.n - min(g.n, 5u)};
 
@@ -668,118 +724,98 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         const bool want_moi = (rq.features & ABX_F_MOI) != 0;
         const bool want_ranks = (rq.features & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) != 0;
         const bool want_cp = (rq.features & (ABX_F_CPQ | ABX_F_CPMAD)) != 0;  // cp_measure `intensity` order statistics
-        u32 vmin = 0, vmax = 0;
         Ranked rk;
         rk.med_lo = rk.med_hi = 0; rk.top2p5_sum = rk.top5_sum = 0;
         u32 cpq[6] = {0, 0, 0, 0, 0, 0}, mad_lo = 0, mad_hi = 0, maxpos = 0;
-        bool wide = false, wide_done = false;  // wide_done: order statistics found and histogram cleaned before the next copy
+        bool ranks_done = false;  // order statistics found and histogram cleaned before the next copy was issued
         u64 sum64 = 0;
-#pragma unroll 1
-        for (u32 c = 0; c < n_chunks; ++c) {
-          // entries of this chunk: rows [c R, (c + 1) R)
-          u32 first = 0, cnt = g.n;
-          if (multi) {
-            const u32 ra = c * g.R, rb = min(ra + g.R, 64u);
-            const u32 fa = __shfl_sync(kFull, ra < 32u ? base0 : base1, ra & 31u);
-            const u32 fb = rb >= 64u ? g.n : __shfl_sync(kFull, rb < 32u ? base0 : base1, rb & 31u);
-            first = fa; cnt = fb - fa;
-          }
-          mbar_wait(bar, parity);
-          parity ^= 1u;
-          const u32 la = list_addr + 2u * first;
-          const u32 wb = win_base - c * g.R * g.pitchB;  // (wraps below zero for later chunks: only differences are used)
-          if (want_moi) sweep_chunk<PX, true>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
-          else sweep_chunk<PX, false>(a, la, cnt, hbase, wb, inv_pitch, g.pitchB);
-          __syncwarp();
-          const bool last_chunk = c + 1u == n_chunks;
-          if (last_chunk) {
-            vmin = __reduce_min_sync(kFull, a.vmin);
-            vmax = __reduce_max_sync(kFull, a.vmax);
-            wide = (want_ranks || want_cp) && vmax - (vmin & ~3u) > 1023u;
-            if (want_cp && multi) {
-              if (lane == 0) atomicOr(err, 2u);  // cp_measure statistics of a chunked window: not served (status bit 1)
-            } else if (want_cp) {
-              // ---- cp_measure `intensity`: every order statistic now, while the window is resident (the MAD needs
-              // a second pass over it) ----
-              sum64 = (u64)__reduce_add_sync(kFull, a.sum);
-              const u32 n = g.n, last = n - 1u;
-              const u32 i1 = n >> 2, i2 = n >> 1, i3 = (3u * n) >> 2;  // floor(n f): CellProfiler's rank rule
-              const u32 rb1[4] = {i1, min(i1 + 1u, last), i2, min(i2 + 1u, last)};
-              const u32 rb2[4] = {i3, min(i3 + 1u, last), i3, min(i3 + 1u, last)};
-              const u32 vbase = vmin & ~3u, rot = vbase & 1023u, nb = vmax - vbase + 1u;
-              if (!wide) {
-                if (want_ranks) {
-                  find_ranks_rot<false>(hist, rot, nb, ranks, t);
-                  rk.med_lo = vbase + t[0]; rk.med_hi = vbase + t[1];
-                  const u32 v2 = vbase + t[2], v3 = vbase + t[3];
-                  rk.top2p5_sum = sum64 - ((u64)vbase * t[10] + t[14] + (u64)t[6] * v2);
-                  rk.top5_sum = sum64 - ((u64)vbase * t[11] + t[15] + (u64)t[7] * v3);
-                }
-                find_ranks_rot<false>(hist, rot, nb, rb1, t);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) cpq[j] = vbase + t[j];
-                find_ranks_rot<true>(hist, rot, nb, rb2, t);
-                cpq[4] = vbase + t[0]; cpq[5] = vbase + t[1];
-              } else {
-                if (want_ranks) rk = wide_ranks<PX>(list_addr, n, vmin, vmax, sum64, rq.features, hist, t, ranks);
-                u32 key[4];
-                wide_select<PX>(list_addr, n, vmin, vmax, XfIdentity(), rb1, hist, t, key);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) cpq[j] = vmin + key[j];
-                wide_select<PX>(list_addr, n, vmin, vmax, XfIdentity(), rb2, hist, t, key);
-                cpq[4] = vmin + key[0]; cpq[5] = vmin + key[1];
-              }
-              if (rq.features & ABX_F_CPMAD) {
-                // twice the median (an integer): f = 1/2 exactly when n is odd
-                const u32 med2 = ((n & 1u) && i2 < last) ? cpq[2] + cpq[3] : 2u * cpq[2];
-                const XfAbsDev xf{med2};
-                const u32 rmad[4] = {i2, min(i2 + 1u, last), i2, min(i2 + 1u, last)};
-                u32 first = kFull;  // list index of the first maximum (row-major order)
-                __syncwarp();
-#pragma unroll 1
-                for (u32 k = lane; k < n; k += 32) {
-                  const u32 v = lds_px<PX>(lds_u16(list_addr + 2u * k));
-                  if (v == vmax) first = min(first, k);
-                  if (!wide) hist_add(hist, xf(v));  // deviations fit the histogram: <= max - min <= 1023
-                }
-                __syncwarp();
-                u32 key[4];
-                if (!wide) {
-                  find_ranks_rot<true>(hist, 0u, vmax - vmin + 1u, rmad, t);
-                  key[0] = t[0]; key[1] = t[1];
-                } else {
-                  wide_select<PX>(list_addr, n, 0u, vmax - vmin, xf, rmad, hist, t, key);
-                }
-                mad_lo = key[0];
-                mad_hi = key[1] | ((med2 & 1u) << 31);
-                first = __reduce_min_sync(kFull, first);
-                const u32 off = lds_u16(list_addr + 2u * first) - win_base;
-                const u32 r = __umulhi(off, inv_pitch);
-                maxpos = (r << 16) | (((off - r * g.pitchB) >> (sizeof(PX) == 1 ? 0 : 1)) - g.s_px);
-              }
-              wide_done = true;
-            } else if (wide && !multi) {  // the window is still here: refine now, before it is overwritten
-              sum64 = (u64)__reduce_add_sync(kFull, a.sum);
-              rk = wide_ranks<PX>(list_addr, g.n, vmin, vmax, sum64, rq.features, hist, t, ranks);
-              wide_done = true;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        if (want_moi) sweep_list<PX, true>(a, tlist, g.n, hbase, win_base, inv_pitch, g.pitchB);
+        else sweep_list<PX, false>(a, tlist, g.n, hbase, win_base, inv_pitch, g.pitchB);
+        __syncwarp();
+        const u32 vmin = __reduce_min_sync(kFull, a.vmin), vmax = __reduce_max_sync(kFull, a.vmax);
+        const bool wide = (want_ranks || want_cp) && vmax - (vmin & ~3u) > 1023u;
+        if (want_cp) {
+          // ---- cp_measure `intensity`: every order statistic now, while the window is resident (the MAD needs
+          // a second pass over it) ----
+          sum64 = (u64)__reduce_add_sync(kFull, a.sum);
+          const u32 n = g.n, last = n - 1u;
+          const u32 i1 = n >> 2, i2 = n >> 1, i3 = (3u * n) >> 2;  // floor(n f): CellProfiler's rank rule
+          const u32 rb1[4] = {i1, min(i1 + 1u, last), i2, min(i2 + 1u, last)};
+          const u32 rb2[4] = {i3, min(i3 + 1u, last), i3, min(i3 + 1u, last)};
+          const u32 vbase = vmin & ~3u, rot = vbase & 1023u, nb = vmax - vbase + 1u;
+          if (!wide) {
+            if (want_ranks) {
+              find_ranks_rot<false>(hist, rot, nb, ranks, t);
+              rk.med_lo = vbase + t[0]; rk.med_hi = vbase + t[1];
+              const u32 v2 = vbase + t[2], v3 = vbase + t[3];
+              rk.top2p5_sum = sum64 - ((u64)vbase * t[10] + t[14] + (u64)t[6] * v2);
+              rk.top5_sum = sum64 - ((u64)vbase * t[11] + t[15] + (u64)t[7] * v3);
             }
+            find_ranks_rot<false>(hist, rot, nb, rb1, t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cpq[j] = vbase + t[j];
+            find_ranks_rot<true>(hist, rot, nb, rb2, t);
+            cpq[4] = vbase + t[0]; cpq[5] = vbase + t[1];
+          } else {
+            if (want_ranks) rk = wide_ranks<PX>(tlist, n, vmin, vmax, sum64, rq.features, hist, t, ranks);
+            u32 key[4];
+            wide_select<PX>(tlist, n, vmin, vmax, XfIdentity(), rb1, hist, t, key);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cpq[j] = vmin + key[j];
+            wide_select<PX>(tlist, n, vmin, vmax, XfIdentity(), rb2, hist, t, key);
+            cpq[4] = vmin + key[0]; cpq[5] = vmin + key[1];
           }
-          // ---- the next window: next chunk, next request, or the first request of the warp's next object; the
-          // window after that one goes to L2 ----
-          if (!last_chunk) {
-            issue(g, rq.row_off, c + 1u);
-          } else if (i + 1 < i_hi) {
-            issue(g, rtab[i + 1].row_off, 0);
-            if (i + 2 < i_hi) prefetch(g, rtab[i + 2].row_off);
-            else if (next_has) prefetch(gn, rtab[ni_lo].row_off);
-          } else if (next_has) {
-            issue(gn, rtab[ni_lo].row_off, 0);
-            if (ni_lo + 1 < ni_hi) prefetch(gn, rtab[ni_lo + 1].row_off);
+          if (rq.features & ABX_F_CPMAD) {
+            // twice the median (an integer): f = 1/2 exactly when n is odd
+            const u32 med2 = ((n & 1u) && i2 < last) ? cpq[2] + cpq[3] : 2u * cpq[2];
+            const XfAbsDev xf{med2};
+            const u32 rmad[4] = {i2, min(i2 + 1u, last), i2, min(i2 + 1u, last)};
+            u32 first = kFull;  // list position of the first maximum (row-major order)
+            __syncwarp();
+            for_each_entry(tlist, n, [&](u32 k, u32 e) {
+              const u32 v = lds_px<PX>(k);
+              if (v == vmax) first = min(first, e);
+              if (!wide) hist_add(hist, xf(v));  // deviations fit the histogram: <= max - min <= 1023
+            });
+            __syncwarp();
+            u32 key[4];
+            if (!wide) {
+              find_ranks_rot<true>(hist, 0u, vmax - vmin + 1u, rmad, t);
+              key[0] = t[0]; key[1] = t[1];
+            } else {
+              wide_select<PX>(tlist, n, 0u, vmax - vmin, xf, rmad, hist, t, key);
+            }
+            mad_lo = key[0];
+            mad_hi = key[1] | ((med2 & 1u) << 31);
+            first = __reduce_min_sync(kFull, first);
+            // the entry at list position `first`: lane first & 31, column first >> 6, half (first >> 5) & 1
+            const u32 word = __shfl_sync(kFull, tmem_ld1(tlist + (first >> 6)), first & 31u);
+            const u32 off = (((first >> 5) & 1u) ? word >> 16 : word & 0xFFFFu) - win_base;
+            const u32 r = __umulhi(off, inv_pitch);
+            maxpos = (r << 16) | (((off - r * g.pitchB) >> (sizeof(PX) == 1 ? 0 : 1)) - g.s_px);
           }
+          ranks_done = true;
+        } else if (wide) {  // the window is still here: refine now, before it is overwritten
+          sum64 = (u64)__reduce_add_sync(kFull, a.sum);
+          rk = wide_ranks<PX>(tlist, g.n, vmin, vmax, sum64, rq.features, hist, t, ranks);
+          ranks_done = true;
+        }
+        __syncwarp();
+        // ---- the next window: next request, or the first request of the warp's next object; the window after that
+        // one goes to L2 ----
+        if (i + 1 < i_hi) {
+          issue(g, rtab[i + 1].row_off);
+          if (i + 2 < i_hi) prefetch(g, rtab[i + 2].row_off);
+          else if (next_has) prefetch(gn, rtab[ni_lo].row_off);
+        } else if (next_has) {
+          issue(gn, rtab[ni_lo].row_off);
+          if (ni_lo + 1 < ni_hi) prefetch(gn, rtab[ni_lo + 1].row_off);
         }
         // ---- reductions (under the copy that was just issued) ----
         ChanStats cs;
-        cs.sum = wide_done ? sum64 : (u64)__reduce_add_sync(kFull, a.sum);  // n * 65535 < 2^32
+        cs.sum = (want_cp || wide) ? sum64 : (u64)__reduce_add_sync(kFull, a.sum);  // n * 65535 < 2^32
         cs.sumsq = warp_sum64(a.sq);
         constexpr int kShift = (sizeof(PX) == 1) ? 12 : 8;
         cs.wrapsq = cs.sumsq - ((u64)__reduce_add_sync(kFull, a.wh) << (32 - 2 * kShift));
@@ -797,9 +833,9 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         cs.vmin = vmin; cs.vmax = vmax;
         cs.med_lo = rk.med_lo; cs.med_hi = rk.med_hi;
         cs.top2p5_sum = rk.top2p5_sum; cs.top5_sum = rk.top5_sum;
-        if (!wide_done) {
+        if (!ranks_done) {
           const u32 vbase = vmin & ~3u;
-          if (want_ranks && !wide) {
+          if (want_ranks) {
             find_ranks_rot<true>(hist, vbase & 1023u, vmax - vbase + 1u, ranks, t);
             cs.med_lo = vbase + t[0]; cs.med_hi = vbase + t[1];
             const u32 v2 = vbase + t[2], v3 = vbase + t[3];
@@ -808,26 +844,26 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
             const u64 below3 = (u64)vbase * t[11] + t[15] + (u64)t[7] * v3;
             cs.top2p5_sum = cs.sum - below2;
             cs.top5_sum = cs.sum - below3;
-          } else {  // no order statistics wanted (or a wide range in a chunked window): just clean up
+          } else {  // no order statistics wanted: just clean up
             const u32 span = vmax - vbase;
             zero_touched(hist, vbase & 1023u, span > 1023u ? 32u : bins_per_lane(span + 1u));
           }
         }
-        if (lane == 0) {
-          chan[(i64)g.obj * n_requests + rq.q] = cs;
-          if (wide && !wide_done && want_ranks)
-            pair_list[atomicAdd(pair_count, 1u)] = g.obj * n_requests + rq.q;  // chunked and wide (rare): the gather kernel
-        }
+        if (lane == 0) chan[(i64)g.obj * n_requests + rq.q] = cs;
         __syncwarp();
       }
     } else if (next_has) {
-      issue(gn, rtab[ni_lo].row_off, 0);  // this item had no request for this kernel: start the next object's first window
+      issue(gn, rtab[ni_lo].row_off);  // this item had no request for this kernel: start the next object's first window
     }
     g = gn; i_lo = ni_lo; i_hi = ni_hi;
     have = have_next;
     item = nxt_item;
     nxt_item = after_item;
   }
+  // ---- give the tensor memory back ----
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
 }
 
 // The tensor maps, or false when the pixel layout does not qualify for TMA (the caller then takes object_stats_warp).
@@ -885,7 +921,7 @@ int launch_sweep(const abx_extract_args* a, const Workspace& ws, const SweepMaps
                                                         n_total /* the plan kernel's capacity of the order array */,
                                                         ws.list_counts + kCntSweepWork, ws.bitmaps,
                                                         (int)(a->chan_stride / a->row_stride), a->requests, a->n_requests,
-                                                        ws.chan, ws.pair_list, ws.list_counts + kCntLeftover, split_log2, ws.err);
+                                                        ws.chan, split_log2);
   return abx_check_cuda(cudaGetLastError(), "object_sweep");
 }
 

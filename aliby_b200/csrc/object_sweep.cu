@@ -654,27 +654,46 @@ object_sweep(const __grid_constant__ SweepMaps maps, const ObjPlan* __restrict__
         const u32 cols = (g.n + 63u) >> 6;
         __syncwarp();
         if (single) {
-          // One run per row (convex cells): the entry of list position e in row r is A_r + e * es, with
-          // A_r = window row address + (first column - list start of the row) * es.  Row table: start | A << 16.
-          rowinfo[lane] = base0 | ((win_base + lane * g.pitchB + (a0 + g.s_px) * es - base0 * es) << 16);
-          rowinfo[lane + 32] = base1 | ((win_base + (lane + 32u) * g.pitchB + (a1 + g.s_px) * es - base1 * es) << 16);
-          if (lane == 0) rowinfo[64] = 0xFFFFu;  // sentinel: no list position reaches it
-          __syncwarp();
-          u32 r = 0, cur = rowinfo[0], nx = rowinfo[1];
+          // One run per row (convex cells).  The lanes own ROWS (two each) but a TMEM lane holds the list positions
+          // congruent to it, so the entries take one hop through shared memory: the row owners scatter them — position p
+          // of the list at staging[p] — into the (clean) histogram area, 2048 positions per round, and every lane
+          // then collects its own positions into TMEM words.
+          const u32 f0 = win_base + lane * g.pitchB + (a0 + g.s_px) * es;          // first pixel of row `lane`
+          const u32 f1 = win_base + (lane + 32u) * g.pitchB + (a1 + g.s_px) * es;  // and of row `lane + 32`
+          const u32 it0 = __reduce_max_sync(kFull, c0), it1 = g.h > 32u ? __reduce_max_sync(kFull, c1) : 0u;
 #pragma unroll 1
-          for (u32 c = 0; c < cols; c += 4) {
-            u32 w[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              u32 e = 64u * (c + (u32)u) + lane, pair = 0;
-#pragma unroll
-              for (int hf = 0; hf < 2; ++hf, e += 32u) {
-                while (e >= (nx & 0xFFFFu)) { cur = nx; ++r; nx = rowinfo[r + 1u]; }  // (rows only ever advance)
-                pair |= (((cur >> 16) + e * es) & 0xFFFFu) << (16 * hf);
-              }
-              w[u] = pair;
+          for (u32 lo = 0; lo < g.n; lo += 2048u) {
+            const u32 hi = min(g.n, lo + 2048u);
+            // staging address of the row's first entry (may lie below or above the staged range: unsigned compare)
+            u32 p = 2u * (base0 - lo), v = f0;
+#pragma unroll 4
+            for (u32 it = 0; it < it0; ++it) {
+              if (it < c0 && p < 4096u) sts_u16(hbase + p, v);
+              p += 2u; v += es;
             }
-            tmem_st4(tlist + c, w);
+            p = 2u * (base1 - lo); v = f1;
+#pragma unroll 4
+            for (u32 it = 0; it < it1; ++it) {
+              if (it < c1 && p < 4096u) sts_u16(hbase + p, v);
+              p += 2u; v += es;
+            }
+            __syncwarp();
+            const u32 c_end = (hi + 63u) >> 6;
+#pragma unroll 1
+            for (u32 c = lo >> 6; c < c_end; c += 4) {
+              u32 w[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const u32 q = hbase + 2u * (64u * (c + (u32)u) + lane - lo);  // (columns past the list read zeros or stale
+                w[u] = (q < hbase + 4032u) ? (lds_u16(q) | (lds_u16(q + 64u) << 16)) : 0u;  //  entries: never used)
+              }
+              tmem_st4(tlist + c, w);
+            }
+            __syncwarp();
+            // the staging area becomes a clean histogram again
+            for (u32 k = lane; k < ((2u * (hi - lo) + 15u) >> 4); k += 32u)
+              *reinterpret_cast<uint4*>(hist + 4u * k) = make_uint4(0, 0, 0, 0);
+            __syncwarp();
           }
         } else {
           // Any shape: the row masks go through the (clean) histogram area, the column of a list position is the

@@ -7,20 +7,23 @@
 //
 //   plan kernel   one thread per object: window geometry and TMA coordinates (ObjPlan), the work order (big objects
 //                 first), zero records for absent labels, hand-over lists for what this kernel does not take
-//                 (windows above 64 x 64 and backgrounds -> object_stats.cu; windows too wide at their alignment ->
-//                 object_stats_warp), and the same routing for the shape kernel (object_edt.cu)
-//   sweep kernel  slot of 16.5 KB per CTA, 13 CTAs per SM:
-//                   flex: window chunk [rows][pitch] PX | list u16[n]   (list entry = SHARED ADDRESS of the pixel)
+//                 (windows above 64 x 64 and backgrounds -> object_stats.cu; windows that start in front of the buffer ->
+//                 object_stats_warp), the same routing for the shape kernel (object_edt.cu), and the second moments of
+//                 the pixel coordinates for cp_measure `sizeshape`
+//   sweep kernel  four warps per CTA, four CTAs per SM, warp per object.  Shared memory per warp:
+//                   window [rows][pitch] PX (one TMA box, at most 64 rows x 144 bytes)
 //                   hist u32[1024], 4 KB aligned in the shared window (bin address = base | (v << 2) & 0xFFC)
-//                   scratch u32[32], mbarrier
-//                 per request ONE pass over the list: moments, extrema and a histogram of the LOW 10 BITS of every
+//                   scratch u32[16], mbarrier, row table
+//                 The pixel list lives in TENSOR MEMORY (tcgen05.alloc / st / ld, 64 columns per CTA, one lane
+//                 quarter per warp): 16-bit entries, each the SHARED ADDRESS of a pixel.
+//                 Per request ONE pass over the list: moments, extrema and a histogram of the LOW 10 BITS of every
 //                 value.  When max - min < 1021 (checked afterwards) that circular histogram is exact — bin
 //                 (v & 1023) holds one value only — and the four ranks (two medians, top 2.5 %, top 5) come out of
 //                 it by warp scans; wider ranges take a coarse histogram + 7-bit refinement sweeps on the window
 //                 that is still resident.  The TMA copy of the NEXT window (next request, or first request of the
-//                 warp's next object) is issued right after the sweep, so that it runs under the rank search, and
+//                 warp's next object) is issued right after the pass, so that it runs under the rank search, and
 //                 the window after that one is prefetched into L2 by cp.async.bulk.prefetch.tensor.
-//                 Windows that do not fit the flex area next to their list are swept in row chunks.
+//                 cp_measure `intensity` adds six CellProfiler-rule ranks and a second pass (MAD, first maximum).
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include <cstring>

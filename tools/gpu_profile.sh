@@ -19,5 +19,5 @@ if [ "$MODE" = "full" ]; then
 fi
 # warm-up 3 steps + timed step 1 = 4 x (label_scan, stats_warp, edt_warp) launches skipped, then one step captured
 $BENCH > $OUT/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'object_sweep|edt_grid|label_scan' -s 12 -c 3 -f -o $OUT/prof_$TAG $BENCH > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'object_sweep|edt_grid|label_scan_kernel|finalize_kernel|plan_kernel|init_records|label_max' -s 28 -c 7 -f -o $OUT/prof_$TAG $BENCH > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"; tail -2 $OUT/ncu_full_$TAG.log

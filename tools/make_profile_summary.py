@@ -22,12 +22,13 @@ PROF = os.path.join(ROOT, "profiles")
 rep = os.path.join(OUT, f"prof_{tag}.ncu-rep")
 launches = os.path.join(OUT, f"launches_{tag}.csv")
 bench = os.path.join(OUT, f"bench_{tag}.json")
-STAGE_OF = {"label_scan_kernel": "label_scan", "object_stats_tma": "object_stats", "object_stats_warp": "object_stats",
+STAGE_OF = {"label_scan_kernel": "label_scan", "object_sweep": "object_stats", "object_stats_warp": "object_stats",
             "object_edt_grid": "object_edt", "finalize_kernel": "finalize"}
 
 md = [f"# ncu summary {tag}", "",
       "Produced by `tools/gpu_profile.sh` on a B200 (sm_100a) and `tools/make_profile_summary.py`; command profiled: "
-      "`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e` (C2: 8 fields of 5ch x 2160^2 per step).", ""]
+      "`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-configs` (C2: 32 fields of 5ch x 2160^2 per step; "
+      "the step's two chains run in line under the stage events / under ncu's serialisation).", ""]
 
 if os.path.exists(bench):
     try:

@@ -67,6 +67,15 @@ METRIC = {
     "cp_eccentricity": 57,
     "cp_major_axis_length": 58,
     "cp_minor_axis_length": 59,
+    # two-image features of extractmulti steps (ABX_M_CO_*): the column's request indexes pairs[]
+    "co_pearson": 64,
+    "co_manders_1": 65,
+    "co_manders_2": 66,
+    "co_rwc_1": 67,
+    "co_rwc_2": 68,
+    "co_overlap": 69,
+    "co_k_1": 70,
+    "co_k_2": 71,
 }
 EDT_METRICS = {4, 5, 6, 7, 8, 55}       # need_edt bit 0 (three chained EDTs; 55: the maximum of the first)
 CONICAL_METRICS = {6, 56}               # need_edt bit 1 (sum of the first EDT)
@@ -75,6 +84,7 @@ CONICAL_METRIC = 6
 
 F_MEDIAN, F_TOP2P5, F_TOP5, F_WRAPSQ, F_MOI, F_CPQ, F_CPMAD = 1, 2, 4, 8, 16, 32, 64
 F_HAS_DIV = 0x40000000
+PF_THRESHOLDED, PF_RWC = 1, 2
 
 EXPORTS = (
     "abx_version",
@@ -93,6 +103,11 @@ EXPORTS = (
 
 class Request(C.Structure):
     _fields_ = [("channel", C.c_int32), ("reduction", C.c_int32), ("features", C.c_uint32), ("bg_features", C.c_uint32)]
+
+
+class Pair(C.Structure):
+    _fields_ = [("request_a", C.c_int32), ("request_b", C.c_int32), ("features", C.c_uint32), ("pad_", C.c_uint32),
+                ("threshold_fraction", C.c_double)]
 
 
 class Column(C.Structure):
@@ -147,10 +162,13 @@ class ExtractArgs(C.Structure):
         ("stage_events", C.POINTER(C.c_void_p)),
         ("pixel_elems", C.c_int64),
         ("status", C.c_void_p),
+        ("pairs", C.c_void_p),
+        ("n_pairs", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
-ABI_VERSION = 3  # include/aliby_b200.h ABX_VERSION
+ABI_VERSION = 4  # include/aliby_b200.h ABX_VERSION
 
 
 class NativeError(RuntimeError):

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(CSRC, "libaliby_b200.so")
-SOURCES = ["abi.cu", "label_scan.cu", "object_warp.cu", "object_sweep.cu", "object_edt.cu", "zreduce.cu", "object_stats.cu", "object_float.cu", "background.cu", "shape_edt.cu", "finalize.cu"]
+SOURCES = ["abi.cu", "label_scan.cu", "object_warp.cu", "object_sweep.cu", "object_edt.cu", "zreduce.cu", "object_stats.cu", "object_float.cu", "object_pair.cu", "background.cu", "shape_edt.cu", "finalize.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "warp_common.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(CSRC, "edt_phases.cuh"), os.path.join(INCLUDE, "aliby_b200.h")]
 
 NVCC_FLAGS = [

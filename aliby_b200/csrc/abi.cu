@@ -44,6 +44,14 @@ int abx_validate(const abx_extract_args* a) {
       return abx_set_error(ABX_ERR_INVALID, "pixel row stride %lld outside [1, 2^25)", (long long)a->row_stride);
     if (a->pixel_dtype == ABX_U16 && a->Z > 65536) return abx_set_error(ABX_ERR_INVALID, "Z too large for 32-bit sums");
   }
+  if (a->n_pairs < 0) return abx_set_error(ABX_ERR_INVALID, "negative count");
+  if (a->n_pairs > 0) {
+    if (a->n_requests < 1) return abx_set_error(ABX_ERR_INVALID, "pairs need requests");
+    if (a->pixel_dtype != ABX_U8 && a->pixel_dtype != ABX_U16)
+      return abx_set_error(ABX_ERR_UNSUPPORTED,
+                           "two-image features have a kernel for uint8/uint16 pixels only (pixel dtype %d); there is no CPU fallback",
+                           a->pixel_dtype);
+  }
   return ABX_OK;
 }
 
@@ -55,6 +63,8 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   off = align_up(off + n_rec * sizeof(abx_object_rec));
   ws->chan = reinterpret_cast<ChanStats*>(b + off);
   off = align_up(off + n_rec * (size_t)a->n_requests * sizeof(ChanStats));
+  ws->pairs = reinterpret_cast<PairStats*>(b + off);
+  off = align_up(off + (size_t)a->n_objects * (size_t)a->n_pairs * sizeof(PairStats));
   ws->shape = reinterpret_cast<ShapeStats*>(b + off);
   off = align_up(off + (a->need_edt ? (size_t)a->n_objects * sizeof(ShapeStats) : 0));
   ws->err = reinterpret_cast<u32*>(b + off);
@@ -124,6 +134,7 @@ static int check_pointers(const abx_extract_args* a, const Workspace& ws) {
     return abx_set_error(ABX_ERR_INVALID, "labels / plane_tile / plane_base is NULL");
   if (a->n_requests > 0 && (!a->pixels || !a->tile_offset || !a->requests))
     return abx_set_error(ABX_ERR_INVALID, "pixels / tile_offset / requests is NULL");
+  if (a->n_pairs > 0 && !a->pairs) return abx_set_error(ABX_ERR_INVALID, "pairs is NULL");
   if (!a->workspace || a->workspace_bytes < ws.total)
     return abx_set_error(ABX_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", a->workspace_bytes, ws.total);
   if ((reinterpret_cast<uintptr_t>(a->workspace) & 15u) != 0)
@@ -237,6 +248,10 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
   if ((rc = launch_big_background(args, ws, st))) return rc;  // backgrounds of large planes: streaming histogram
   if ((rc = launch_object_float(args, ws, st))) return rc;  // floating-point requests (float pixels, `div`)
+  if (args->n_pairs > 0) {  // two-image features: they start from the minima / maxima of both requests
+    if (hp) cudaStreamWaitEvent(st, hp->join, 0);  // (the left-over pairs of the sweep kernel ran on the helper stream)
+    if ((rc = launch_object_pair(args, ws, st))) return rc;
+  }
   if (!hp && (rc = launch_shape_edt(args, ws, st))) return rc;
   mark(4);
   if (hp) cudaStreamWaitEvent(st, hp->join, 0);

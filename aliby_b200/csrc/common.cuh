@@ -77,8 +77,24 @@ struct MaskMoments {
   u64 pad_;
 };
 
+// Raw per-(object, pair of requests) sums of the two-image features (object_pair.cu), all exact integers.
+// x, y: the object's values in the two requests; "both": pixels with x >= tx and y >= ty.
+struct PairStats {
+  u64 sxy;           // sum x y over the object
+  u64 tot_x, tot_y;  // sum x [x >= tx], sum y [y >= ty]
+  u64 cx, cy;        // sum x, sum y over both
+  u64 cxy, cxx, cyy; // sum x y, x^2, y^2 over both
+  u64 wx, wy;        // sum x (R - |rank x - rank y|), the same for y, over both
+  u32 big_r;         // R = max(number of distinct x, number of distinct y)
+  u32 n_both;        // pixels in both
+  u32 flags;         // bit 0: not computed (values of 65536 or more)
+  u32 pad_;
+};
+static_assert(sizeof(PairStats) == 96, "PairStats layout");
+
 struct Workspace {
   abx_object_rec* recs;  // [n_objects + n_planes]
+  PairStats* pairs;      // [n_objects * n_pairs]
   MaskMoments* mom;      // [n_objects] when need_edt bit 2
   u64* bitmaps;          // [n_objects + 1][64] torus bitmaps written by the label scan (label_scan.cu)
   ObjPlan* plan;         // [n_objects + n_planes]
@@ -120,6 +136,7 @@ int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaS
 int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_float(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_object_pair(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);  // after every statistics kernel
 int launch_big_background(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 bool abx_big_background(const abx_extract_args* a);
 size_t abx_big_background_bytes(const abx_extract_args* a);

@@ -69,9 +69,37 @@ __device__ __forceinline__ double cp_quantile(u32 n, u32 k, double lo, double hi
   return i < n - 1u ? lo * (1.0 - frac) + hi * frac : lo;
 }
 
+// Two-image features from the exact sums of object_pair.cu (CellProfiler MeasureColocalization, one object at a time)
+__device__ double pair_metric(const PairStats& p, const ChanStats& ca, const ChanStats& cb, u32 n_px, int metric) {
+  const double kNaN = nan("");
+  if (n_px == 0 || (p.flags & 1u)) return kNaN;
+  if (metric == ABX_M_CO_PEARSON) {
+    // n sum(xy) - sum(x) sum(y) over sqrt of the two variances' numerators, each an exact 128-bit integer
+    const unsigned __int128 n = n_px;
+    const unsigned __int128 vx = n * ca.sumsq - (unsigned __int128)ca.sum * ca.sum;
+    const unsigned __int128 vy = n * cb.sumsq - (unsigned __int128)cb.sum * cb.sum;
+    if (vx == 0 || vy == 0) return kNaN;  // a constant image: 0 / 0
+    const unsigned __int128 pos = n * p.sxy, neg = (unsigned __int128)ca.sum * cb.sum;
+    const double cov = pos >= neg ? u128_to_double(pos - neg) : -u128_to_double(neg - pos);
+    return cov / (sqrt(u128_to_double(vx)) * sqrt(u128_to_double(vy)));
+  }
+  if (p.n_both == 0) return 0.0;  // no pixel above both thresholds
+  switch (metric) {
+    case ABX_M_CO_MANDERS_1: return (double)p.cx / (double)p.tot_x;
+    case ABX_M_CO_MANDERS_2: return (double)p.cy / (double)p.tot_y;
+    case ABX_M_CO_RWC_1: return (double)p.wx / (double)p.big_r / (double)p.tot_x;
+    case ABX_M_CO_RWC_2: return (double)p.wy / (double)p.big_r / (double)p.tot_y;
+    case ABX_M_CO_OVERLAP: return (double)p.cxy / sqrt((double)p.cxx * (double)p.cyy);
+    case ABX_M_CO_K_1: return (double)p.cxy / (double)p.cxx;
+    case ABX_M_CO_K_2: return (double)p.cxy / (double)p.cyy;
+    default: return kNaN;
+  }
+}
+
 __device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const abx_object_rec* __restrict__ recs,
                                 const ChanStats* __restrict__ chan, const ShapeStats* __restrict__ shape,
-                                const MaskMoments* __restrict__ mom,
+                                const MaskMoments* __restrict__ mom, const PairStats* __restrict__ pair_stats,
+                                const abx_pair* __restrict__ pairs, int n_pairs,
                                 const int32_t* __restrict__ plane_base, int n_planes, int n_objects,
                                 const abx_request* __restrict__ requests, int n_requests,
                                 const abx_column* __restrict__ columns, int pixel_dtype) {
@@ -79,7 +107,11 @@ __device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const
   const double n = (double)r.n;
   const double kNaN = nan("");
   double v = kNaN;
-  if (cd.metric >= ABX_M_CP_BBOX_AREA) {
+  if (cd.metric >= ABX_M_CO_PEARSON) {
+    const abx_pair pr = pairs[cd.request];
+    v = pair_metric(pair_stats[(i64)obj * n_pairs + cd.request], chan[(i64)obj * n_requests + pr.request_a],
+                    chan[(i64)obj * n_requests + pr.request_b], r.n, cd.metric);
+  } else if (cd.metric >= ABX_M_CP_BBOX_AREA) {
     // ---- cp_measure `sizeshape` subset (label plane only) ----
     if (r.n) {
       const double hh = (double)(r.rmax - r.rmin + 1u), ww = (double)(r.cmax - r.cmin + 1u);
@@ -211,6 +243,7 @@ constexpr int kFinObjects = 32, kFinWarps = 8, kFinColChunk = 64;
 __global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __restrict__ chan,
                                 const ShapeStats* __restrict__ shape, const MaskMoments* __restrict__ mom,
+                                const PairStats* __restrict__ pair_stats, const abx_pair* __restrict__ pairs, int n_pairs,
                                 const int32_t* __restrict__ plane_base,
                                 int n_planes, int n_objects, const abx_request* __restrict__ requests,
                                 int n_requests, const abx_column* __restrict__ columns, int n_columns,
@@ -227,7 +260,7 @@ finalize_kernel(const abx_object_rec* __restrict__ recs, const ChanStats* __rest
     const int ncol = min(kFinColChunk, n_columns - cbase);
     for (int cl = warp; cl < ncol; cl += kFinWarps) {
       const int col = cbase + cl;
-      tile[lane][cl] = live ? finalize_cell(r, obj, col, recs, chan, shape, mom, plane_base, n_planes, n_objects, requests,
+      tile[lane][cl] = live ? finalize_cell(r, obj, col, recs, chan, shape, mom, pair_stats, pairs, n_pairs, plane_base, n_planes, n_objects, requests,
                                             n_requests, columns, pixel_dtype)
                             : 0.0;
     }
@@ -250,7 +283,7 @@ int launch_finalize(const abx_extract_args* a, const Workspace& ws, cudaStream_t
     return ABX_OK;
   }
   const unsigned blocks = (unsigned)((a->n_objects + kFinObjects - 1) / kFinObjects);
-  finalize_kernel<<<blocks, kFinWarps * 32, 0, st>>>(ws.recs, ws.chan, ws.shape, ws.mom, a->plane_base, a->n_planes,
+  finalize_kernel<<<blocks, kFinWarps * 32, 0, st>>>(ws.recs, ws.chan, ws.shape, ws.mom, ws.pairs, a->pairs, a->n_pairs, a->plane_base, a->n_planes,
                                                    a->n_objects, a->requests, a->n_requests, a->columns,
                                                    a->n_columns, a->pixel_dtype, a->table, ws.err, a->status);
   return abx_check_cuda(cudaGetLastError(), "finalize");

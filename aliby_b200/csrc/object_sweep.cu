@@ -174,10 +174,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
           m = (len + c0 >= 64u) ? 0ull : (m & (~0ull << (c0 + len)));
         }
       }
-    } else if (rec.n > 0) {
-      atomicOr(a.err, 2u);  // a cell above 64 x 64 has no bitmap
-    }
-    a.mom[i] = mm;
+      a.mom[i] = mm;
+    } else if (rec.n == 0) {
+      a.mom[i] = mm;
+    }  // (a cell above 64 x 64 has no bitmap: large_moments_kernel reads its label window)
   }
   // ---- shape ----
   if (a.need_edt) {
@@ -191,6 +191,51 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
     append(take, rec.n > kBigFirst, i, a.order_edt, a.n_objects, a.counts + kCntEdtBig, a.counts + kCntEdtSmall);
     const bool hand = obj && rec.n > 0 && !take;
     if (hand) a.edt_list[atomicAdd(a.counts + kCntEdtList, 1u)] = i;  // rare
+  }
+}
+
+// Second coordinate moments of the cells above 64 x 64 (no bitmap): one CTA per such cell walks its label window.
+// Every CTA looks at the records of its share of the objects and skips the window-sized ones (a record load each).
+__global__ void __launch_bounds__(256) large_moments_kernel(const abx_object_rec* __restrict__ recs, int n_objects,
+                                                            const uint16_t* __restrict__ labels, i64 plane_stride,
+                                                            i64 row_stride, const int32_t* __restrict__ plane_base,
+                                                            int n_planes, MaskMoments* __restrict__ mom) {
+  __shared__ u64 acc[3];
+  for (int i = blockIdx.x; i < n_objects; i += gridDim.x) {
+    const abx_object_rec rec = recs[i];
+    const u32 h = rec.rmax - rec.rmin + 1u, w = rec.cmax - rec.cmin + 1u;
+    if (rec.n == 0 || (h <= (u32)kSide && w <= (u32)kSide)) continue;  // (block-uniform)
+    if (threadIdx.x < 3) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int p = find_plane(plane_base, n_planes, i);
+    const u32 id = (u32)(i - plane_base[p]) + 1u;
+    const uint16_t* lab = labels + (i64)p * plane_stride + (i64)rec.rmin * row_stride + rec.cmin;
+    u64 s_rr = 0, s_cc = 0, s_rc = 0;
+    for (u32 r = threadIdx.x >> 5; r < h; r += 8u)
+      for (u32 c = threadIdx.x & 31u; c < w; c += 32u)
+        if (lab[(i64)r * row_stride + c] == id) {
+          s_rr += (u64)r * r;
+          s_cc += (u64)c * c;
+          s_rc += (u64)r * c;
+        }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+      s_rr += __shfl_xor_sync(kFull, s_rr, k);
+      s_cc += __shfl_xor_sync(kFull, s_cc, k);
+      s_rc += __shfl_xor_sync(kFull, s_rc, k);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&acc[0]), s_rr);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&acc[1]), s_cc);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&acc[2]), s_rc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      MaskMoments mm;
+      mm.s_rr = acc[0]; mm.s_cc = acc[1]; mm.s_rc = acc[2]; mm.pad_ = 0;
+      mom[i] = mm;
+    }
+    __syncthreads();
   }
 }
 
@@ -995,6 +1040,11 @@ int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st,
   p.mom = ws.mom;
   p.err = ws.err;
   plan_kernel<<<(n_total + 255) / 256, 256, 0, st>>>(p);
+  if (p.want_moments && a->n_objects > 0 && (a->H > kSide || a->W > kSide)) {  // cells above the window can exist
+    const int grid = a->n_objects < 148 * 8 ? a->n_objects : 148 * 8;
+    large_moments_kernel<<<grid, 256, 0, st>>>(ws.recs, a->n_objects, static_cast<const uint16_t*>(a->labels),
+                                               a->label_plane_stride, a->label_row_stride, a->plane_base, a->n_planes, ws.mom);
+  }
   return abx_check_cuda(cudaGetLastError(), "plan");
 }
 

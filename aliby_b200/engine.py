@@ -95,6 +95,17 @@ CP_SIZESHAPE = (  # (key, building block)
     ("AreaShape_MinorAxisLength", "cp_minor_axis_length"),
 )
 CP_FEATURE_NAMES = ("intensity", "sizeshape")
+# cp_measure two-image features of `extractmulti_*` trees (loaders.py:75-77,153-168; extract.py:200-237) with a kernel:
+# (key, building block) per feature and the pair features they need.  CellProfiler MeasureColocalization for objects,
+# self-defined against oracle/cpm.py like the features above; the keys are CellProfiler's feature stems.
+CP_CORRELATION = {
+    "pearson": ((("Correlation_Pearson", "co_pearson"),), 0),
+    "manders_fold": ((("Correlation_Manders_1", "co_manders_1"), ("Correlation_Manders_2", "co_manders_2")), nat.PF_THRESHOLDED),
+    "rwc": ((("Correlation_RWC_1", "co_rwc_1"), ("Correlation_RWC_2", "co_rwc_2")), nat.PF_THRESHOLDED | nat.PF_RWC),
+    "overlap": ((("Correlation_Overlap", "co_overlap"), ("Correlation_K_1", "co_k_1"), ("Correlation_K_2", "co_k_2")),
+                nat.PF_THRESHOLDED),
+}
+CP_CORRELATION_WITHOUT_KERNEL = ("costes",)  # known to the reference's registry, no CUDA kernel here
 
 CELL_FUN_NAMES = tuple(
     sorted(
@@ -129,7 +140,8 @@ class Plan:
 
     instructions: list
     requests: list = field(default_factory=list)  # [(channel, red_enum, features, bg_features)]
-    columns: list = field(default_factory=list)  # [(request_idx, metric_enum)]
+    columns: list = field(default_factory=list)  # [(request_idx, metric_enum)] (pair index for the two-image metrics)
+    pairs: list = field(default_factory=list)  # [(request_a, request_b, pair features, threshold fraction)]
     inst_cols: list = field(default_factory=list)  # per instruction: tuple of dense column indices
     inst_keys: list = field(default_factory=list)  # per instruction: None, or the dict keys of a dict-valued metric
     need_edt: int = 0  # bit 0: axes (eccentricity/volume/min/maj), bit 1: conical_volume
@@ -158,6 +170,20 @@ class Plan:
             for i, c in enumerate(self.columns):
                 col[i] = c
             self._dev[key] = (torch.from_numpy(req).to(device), torch.from_numpy(col).to(device))
+        return self._dev[key]
+
+    def device_pairs(self, device):
+        """``abx_pair[]`` as a device tensor (None without two-image metrics)."""
+        import torch
+
+        if not self.pairs:
+            return None
+        key = ("pairs", str(device))
+        if key not in self._dev:
+            arr = (nat.Pair * len(self.pairs))()
+            for i, (ra, rb, feats, frac) in enumerate(self.pairs):
+                arr[i].request_a, arr[i].request_b, arr[i].features, arr[i].threshold_fraction = ra, rb, feats, frac
+            self._dev[key] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
         return self._dev[key]
 
 
@@ -191,8 +217,43 @@ def compile_instructions(instructions: list, cp_measure_kwargs=None) -> Plan:
                 plan.need_edt |= 4
         return col_index[key]
 
+    pair_index: dict = {}
+
+    def multi(inst):
+        """((ch0, ch1), red_ch, red_z, metric) of an extractmulti tree (extract.py:200-237)."""
+        chs, red_ch, red, metric = inst
+        ch0, ch1 = chs
+        if red_ch not in REDUCERS or red not in REDUCERS:
+            raise KeyError(red if red_ch in REDUCERS else red_ch)
+        if metric in CP_CORRELATION_WITHOUT_KERNEL:
+            raise NotImplementedError(f"two-image feature '{metric}' has no CUDA kernel in aliby_b200 and there is no CPU fallback")
+        if red_ch != "None":
+            # the reference's other branch combines the two channels and calls measure_mono without its registries
+            # (extract.py:227-235): a TypeError there
+            raise NotImplementedError("extractmulti branches with a channel reduction (red_ch != 'None') have no CUDA kernel")
+        if metric not in CP_CORRELATION:
+            raise KeyError(metric)
+        if REDUCERS[red] != "ufunc":
+            raise Exception(f"{REDUCERS[red]} is an invalid reducer.")  # distributors.py:24
+        if red == "div":
+            raise NotImplementedError("two-image features of `div`-reduced (floating point) stacks have no CUDA kernel")
+        blocks, feats = CP_CORRELATION[metric]
+        thr = cp_kw.get(metric, {}).get("thr", 15)
+        key = (request(ch0, red), request(ch1, red), thr)
+        if key not in pair_index:
+            pair_index[key] = len(plan.pairs)
+            plan.pairs.append([key[0], key[1], 0, thr / 100])
+        p = pair_index[key]
+        plan.pairs[p][2] |= feats
+        return tuple(column(p, block) for _, block in blocks), [k for k, _ in blocks]
+
     for inst in instructions:
         try:
+            if len(inst) == 4:
+                cols, keys = multi(inst)
+                plan.inst_cols.append(cols)
+                plan.inst_keys.append(keys)
+                continue
             ch, red, metric = inst
             if red not in REDUCERS:
                 raise KeyError(red)  # REDUCTION_FUNS[red_z], extract.py:151
@@ -267,6 +328,17 @@ def raise_on_status(word: int) -> None:
         raise IndexError(
             "a label id exceeds the number of labels given for its plane (n_labels / plane_base): the masks changed "
             "after their maximum was taken, or n_labels is stale — the table would be missing those pixels"
+        )
+    if int(word) & 2:
+        raise NotImplementedError(
+            "cp_measure 'intensity' met an object the sweep kernel does not serve (a bounding box above 64 x 64 pixels, or a "
+            "pixel layout the TMA unit cannot address): its quartiles / MAD / maximum position have no CUDA kernel and "
+            "there is no CPU fallback"
+        )
+    if int(word) & 4:
+        raise NotImplementedError(
+            "a two-image feature met values of 65536 or more (the `add` reduction of a Z stack): no CUDA kernel covers "
+            "them and there is no CPU fallback"
         )
 
 
@@ -396,6 +468,11 @@ def run_planes(
         raise NotImplementedError("cp_measure 'intensity' has a CUDA kernel for uint8/uint16 pixels only; there is no CPU fallback")
     if plan.requests:  # extent of the pixel buffer behind data_ptr(), for the TMA description of it
         a.pixel_elems = (pixels.untyped_storage().nbytes() // pixels.element_size()) - pixels.storage_offset()
+    pairs_t = plan.device_pairs(device)
+    if pairs_t is not None:
+        if a.pixel_dtype not in (nat.U8, nat.U16):
+            raise NotImplementedError("two-image features have a CUDA kernel for uint8/uint16 pixels only; there is no CPU fallback")
+        a.pairs, a.n_pairs = pairs_t.data_ptr(), len(plan.pairs)
     a.table = out.data_ptr()
     a.stream = torch.cuda.current_stream(device).cuda_stream
     if stage_events is not None:  # 6 handles from abx_event_create (bench.py: live per-stage timing)

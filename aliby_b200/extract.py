@@ -6,6 +6,7 @@ this module unchanged (see ``aliby_b200.pipe.init_step``):
 
 * :func:`process_tree_masks`, :func:`process_tree_masks_overlap`  (extract.py:240-301, 456-517)
 * :func:`extract_tree`                                            (extract.py:304-375)
+* :func:`extract_tree_multi`                                      (extract.py:378-453)
 * :func:`format_extraction`                                       (extract.py:520-599)
 * :func:`flatten`, :func:`kv`                                     (extract.py:33-74)
 
@@ -545,6 +546,26 @@ def extract_tree(
     results.objects = np.asarray(objects, dtype=np.int64).reshape(len(objects), -1)
     results.obj_rows = obj_rows
     return results
+
+
+def extract_tree_multi(
+    tileid_instructions,
+    masks,
+    pixels,
+    ncores=None,
+    progress_bar: bool = False,
+    cp_measure_kwargs=None,
+):
+    """Two-channel measurements of an ``extractmulti_*`` step in one pass on the GPU (extract.py:378-453).
+
+    Items are ``((tile, label), ((ch0, ch1), red_ch, red_z, metric))`` (extract.py:222); ``red_ch`` must be ``"None"``
+    (the two-image branch of ``measure_multi``, extract.py:223-226) and ``metric`` one of ``pearson``, ``manders_fold``,
+    ``rwc``, ``overlap`` — CellProfiler MeasureColocalization for one object at a time, what ``wrap_cp_corr_features``
+    (loaders.py:153-168) obtains from cp_measure; results are dicts ``{key: ndarray(1)}`` like theirs.  ``costes`` has
+    no kernel: :func:`aliby_b200.pipe.init_step` splits such a tree between this function and the reference."""
+    assert isinstance(masks, list) or masks.ndim >= 3, "Masks dimensions < 2. It should include batch/tile dimension."
+    return extract_tree(tileid_instructions, masks, pixels, ncores=ncores, progress_bar=progress_bar,
+                        cp_measure_kwargs=cp_measure_kwargs)
 
 
 def format_extraction(instructions_result):

@@ -7,8 +7,10 @@ provides exactly that:
 
 * :func:`init_step` — returns our extractor for ``extract_*`` steps (same ``partial`` shape as
   ``pipe_core._init_extract``, ``pipe_core.py:68-81``), our fused tiler for ``tile*`` steps (the crop of
-  ``tiler.py:309-366`` becomes a view that the extraction kernels read in place) and defers every other step —
-  ``extractmulti_*`` included — to the reference's own ``aliby.pipe.init_step`` when ALIBY is importable;
+  ``tiler.py:309-366`` becomes a view that the extraction kernels read in place), our two-image extractor for
+  ``extractmulti_*`` steps (``pipe_core._init_extract_multi``, ``pipe_core.py:84-92``; features without a kernel are
+  measured by the reference's step next to ours) and defers every other step to the reference's own
+  ``aliby.pipe.init_step`` when ALIBY is importable;
 * :func:`run_pipeline_and_post` — ``partial(_run_pipeline_and_post_impl, init_step_fn=init_step)``
   (what ``aliby/pipe.py:75-77`` does with its own ``init_step``), available when ALIBY is importable;
 * :func:`get_profiles_from_state` — table assembly of ``pipe_core.py:453-512`` (rename
@@ -22,7 +24,8 @@ from functools import partial
 
 import numpy as np
 
-from .extract import extract_tree, format_extraction, process_tree_masks, process_tree_masks_overlap
+from .extract import (extract_tree, extract_tree_multi, format_extraction, process_tree_masks,
+                      process_tree_masks_overlap)
 
 
 def _init_extract(step_name: str, parameters: dict, *, overlap: bool = False):
@@ -35,6 +38,53 @@ def _init_extract(step_name: str, parameters: dict, *, overlap: bool = False):
         process = process_tree_masks_overlap
         measure_fn = partial(extract_tree, overlap=True)
     return partial(process, measure_fn=measure_fn, tree=parameters["tree"], **parameters.get("kwargs", {}))
+
+
+def _split_multi_tree(tree: dict, cp_measure_kwargs=None):
+    """``(ours, theirs)``: the branches of an extractmulti tree with and without a CUDA kernel (same nesting)."""
+    from . import engine
+
+    ours: dict = {}
+    theirs: dict = {}
+    for inst in engine.kv(engine.flatten(tree)):
+        ok = len(inst) == 4 and engine.compile_instructions([inst], cp_measure_kwargs).error is None
+        node = ours if ok else theirs
+        for key in inst[:-2]:
+            node = node.setdefault(key, {})
+        node.setdefault(inst[-2], []).append(inst[-1])
+    return ours, theirs
+
+
+def _init_extract_multi(step_name: str, parameters: dict, other_steps: dict | None = None):
+    """``extractmulti_*`` steps (pipe.py:65-66, pipe_core.py:84-92): ``partial(process_tree_masks,
+    measure_fn=extract_tree_multi, tree=..., **kwargs)`` on the GPU.
+
+    A tree that also names two-image features without a kernel (``costes``, which the stock builder requests,
+    pipe_builder.py:19-43) is split: our kernels measure their part, the reference's own step — when ALIBY is importable —
+    measures the rest with the same arguments, and the two ``(instructions, results)`` lists are concatenated
+    (``format_extraction`` pivots by (tile, label) and sorts the columns, so the table is the one the reference builds).
+    Without the reference the step raises at its first call with objects, naming the feature."""
+    if "tree" not in parameters:
+        raise ValueError(f"Step '{step_name}' is missing required 'tree'.")
+    kwargs = dict(parameters.get("kwargs", {}))
+    ours, theirs = _split_multi_tree(parameters["tree"], kwargs.get("cp_measure_kwargs"))
+    if not theirs:
+        return partial(process_tree_masks, measure_fn=extract_tree_multi, tree=parameters["tree"], **kwargs)
+    try:
+        reference_step = _reference_init_step(step_name, {**parameters, "tree": theirs}, other_steps,
+                                              "names two-image features without a CUDA kernel")
+    except ImportError:
+        return partial(process_tree_masks, measure_fn=extract_tree_multi, tree=parameters["tree"], **kwargs)
+    if not ours:
+        return reference_step
+    gpu_step = partial(process_tree_masks, measure_fn=extract_tree_multi, tree=ours, **kwargs)
+
+    def split_step(masks, pixels, **kw):
+        items_a, res_a = gpu_step(masks=masks, pixels=pixels, **kw)
+        items_b, res_b = reference_step(masks=masks, pixels=pixels, **kw)
+        return tuple(items_a) + tuple(items_b), list(res_a) + list(res_b)
+
+    return split_step
 
 
 def _reference_init_step(step_name: str, parameters: dict, other_steps: dict | None, why: str):
@@ -69,9 +119,9 @@ def init_step(step_name: str, parameters: dict, other_steps: dict | None = None,
     """Drop-in ``init_step_fn``: ours for ``extract_*`` and ``tile*``, the reference's for everything else.
 
     An ``extract_*`` step whose tree names a metric without a CUDA kernel (cp_measure features beyond ``intensity`` /
-    ``sizeshape``, decided here with the plan compiler) and every ``extractmulti_*`` step (cp_measure colocalisation)
-    go to the reference's own implementation when ALIBY is importable; otherwise the error names the metric — there
-    is no CPU fallback inside this package."""
+    ``sizeshape``, decided here with the plan compiler) goes to the reference's own implementation when ALIBY is
+    importable, and so do the branches of an ``extractmulti_*`` tree without a kernel (:func:`_init_extract_multi`);
+    otherwise the error names the metric — there is no CPU fallback inside this package."""
     if step_name.startswith("extract_"):
         if "tree" in parameters:
             from . import engine
@@ -84,8 +134,7 @@ def init_step(step_name: str, parameters: dict, other_steps: dict | None = None,
                     pass  # the step then raises KeyError(metric) at its first call with objects, like the reference would
         return _init_extract(step_name, parameters, overlap=overlap)
     if step_name.startswith("extractmulti_"):
-        return _reference_init_step(step_name, parameters, other_steps,
-                                    "(cp_measure colocalisation, extract.py:200-237) has no CUDA kernel in aliby_b200")
+        return _init_extract_multi(step_name, parameters, other_steps)
     if step_name.startswith("tile"):
         return _init_tile(step_name, parameters, other_steps)
     return _reference_init_step(step_name, parameters, other_steps, "is not an extract or tile step")

@@ -17,6 +17,8 @@
  *                      standard_scale tiler.py:95-102, or the `div` reducer) take a generic fp64 kernel.
  *   abx_shape_edt      src/extraction/core/functions/cell.py:30-40,160-229 (eccentricity,
  *                      volume, conical_volume, min_maj_approximation: three chained EDTs)
+ *   abx_extract (pairs) src/extraction/extract.py:200-237 (measure_multi: two channels, one mask) with the two-image
+ *                      features that loaders.py:75-77,153-168 takes from cp_measure (CellProfiler MeasureColocalization)
  *   abx_finalize       the scalar arithmetic of the functions above + the dense
  *                      [objects x columns] table that replaces the long->wide pivot of
  *                      src/extraction/extract.py:574-598
@@ -44,7 +46,7 @@
 extern "C" {
 #endif
 
-#define ABX_VERSION 3
+#define ABX_VERSION 4
 
 typedef enum abx_status {
   ABX_OK = 0,
@@ -60,7 +62,7 @@ typedef enum abx_dtype { ABX_U8 = 0, ABX_U16 = 1, ABX_U32 = 2, ABX_F32 = 3, ABX_
  * left fold of true divisions whose result is float64 whatever the pixel dtype (distributors.py:19-21). */
 typedef enum abx_reduction { ABX_RED_MAX = 0, ABX_RED_ADD = 1, ABX_RED_DIV = 2 } abx_reduction;
 
-/* Dense-table column kinds. 0-15 and 48-63 need only the label plane, 16-47 a pixel request. */
+/* Dense-table column kinds. 0-15 and 48-63 need only the label plane, 16-47 a pixel request, 64-79 a pair of requests. */
 typedef enum abx_metric {
   ABX_M_AREA = 0,
   ABX_M_CENTROID_X = 1,
@@ -118,7 +120,20 @@ typedef enum abx_metric {
   ABX_M_CP_MEAN_RADIUS = 56,
   ABX_M_CP_ECCENTRICITY = 57,
   ABX_M_CP_MAJOR_AXIS_LENGTH = 58,
-  ABX_M_CP_MINOR_AXIS_LENGTH = 59
+  ABX_M_CP_MINOR_AXIS_LENGTH = 59,
+  /* Two-image features of `extractmulti_*` steps (extract.py:200-237; CellProfiler MeasureColocalization for objects,
+   * one object at a time).  abx_column.request indexes pairs[].  x, y: the object's values in the pair's two requests;
+   * tx = threshold_fraction * max x, ty alike; "both" = pixels with x >= tx and y >= ty (an object without such a pixel
+   * has 0 in 65-71).  Integer pixels only (uint8 / uint16, values below 65536 after the Z reduction: otherwise status
+   * bit 2). */
+  ABX_M_CO_PEARSON = 64,   /* correlation of x and y over the object (NaN when either is constant) */
+  ABX_M_CO_MANDERS_1 = 65, /* sum x [both] / sum x [x >= tx] */
+  ABX_M_CO_MANDERS_2 = 66,
+  ABX_M_CO_RWC_1 = 67,     /* sum x w [both] / sum x [x >= tx], w = (R - |rank x - rank y|) / R, dense ranks in the object */
+  ABX_M_CO_RWC_2 = 68,
+  ABX_M_CO_OVERLAP = 69,   /* sum x y / sqrt(sum x^2 sum y^2) over both */
+  ABX_M_CO_K_1 = 70,       /* sum x y / sum x^2 over both */
+  ABX_M_CO_K_2 = 71
 } abx_metric;
 
 /* What a pixel request has to compute (bit mask). Sums/min/max are always produced. */
@@ -141,9 +156,19 @@ typedef struct abx_request {
   uint32_t bg_features; /* ABX_F_* needed for the per-plane background object (0 = none) */
 } abx_request;
 
+/* Two requests measured together on every object (one (channel, channel) branch of an extractmulti tree). */
+#define ABX_PF_THRESHOLDED 1u /* the sums over "both" (Manders, overlap, K) */
+#define ABX_PF_RWC 2u         /* the rank-weighted sums (a second pass and two rank tables) */
+typedef struct abx_pair {
+  int32_t request_a, request_b; /* indices into requests[]; both requests exist there (their sums, minima and maxima are used) */
+  uint32_t features;            /* ABX_PF_*; sum x y is always produced */
+  uint32_t pad_;
+  double threshold_fraction;    /* thr / 100 of CellProfiler's "threshold as percentage of maximum intensity" (15 -> 0.15) */
+} abx_pair; /* 24 bytes */
+
 /* One column of the dense output table. */
 typedef struct abx_column {
-  int32_t request; /* index into requests[], -1 for label-only metrics */
+  int32_t request; /* index into requests[] (into pairs[] for ABX_M_CO_*), -1 for label-only metrics */
   int32_t metric;  /* abx_metric */
 } abx_column;
 
@@ -203,8 +228,13 @@ typedef struct abx_extract_args {
    * (plane_base[p + 1] - plane_base[p]) was met — those pixels belong to no row of the table and the background
    * statistics of that plane are not meaningful; the caller passed a stale or wrong plane_base.  Bit 1: an
    * ABX_M_CP_* intensity column was requested for an object that the sweep kernel does not serve (window above
-   * 64 x 64, or a chunked window with a wide value range): that cell of the table is not meaningful. */
+   * 64 x 64, or a chunked window with a wide value range): that cell of the table is not meaningful.  Bit 2: an
+   * ABX_M_CO_* column met an object with values of 65536 or more (a Z-add of a stack): that cell is NaN. */
   uint32_t* status;
+  /* optional (ABI 4): pairs of requests for the ABX_M_CO_* columns */
+  const abx_pair* pairs; /* device, [n_pairs] */
+  int32_t n_pairs;
+  int32_t pad_;
 } abx_extract_args;
 
 int abx_version(void);

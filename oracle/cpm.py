@@ -30,6 +30,17 @@ Conventions taken from CellProfiler:
   eigenvalues ``l1 >= l2``: axes ``4 sqrt(l)``, eccentricity ``sqrt(1 - l2 / l1)``).
   Orientation, Perimeter, FormFactor, Compactness, ConvexArea, Solidity, EulerNumber, Feret diameters, MedianRadius
   and the Zernike moments are not restated.
+* ``Correlation_*`` (the two-image features of ``extractmulti_*`` steps, ``extract.py:200-237``,
+  ``loaders.py:75-77,153-168``: ``fun(pixels1, pixels2, mask)``), after CellProfiler's MeasureColocalization for
+  objects, one binary mask at a time: ``pearson`` = correlation of the two images over the object's pixels;
+  ``manders_fold`` = with ``t1 = thr/100 * max(first)``, ``t2 = thr/100 * max(second)`` over the object (``thr`` = 15)
+  and ``both = (first >= t1) & (second >= t2)``: ``M1 = sum(first[both]) / sum(first[first >= t1])``, M2 alike;
+  ``rwc`` = the same sums weighted by ``(R - |rank1 - rank2|) / R`` with dense 0-based ranks of the object's values in
+  each image and ``R = max(rank) + 1``; ``overlap`` = ``sum(f s) / sqrt(sum(f^2) sum(s^2))`` over ``both`` with
+  ``K1 = sum(f s) / sum(f^2)``, ``K2 = sum(f s) / sum(s^2)``.  An object without a pixel in ``both`` has 0 for the
+  thresholded features.  Integer images are taken as they are, in float64 (no wrap-around of squares).
+  ``costes`` (an iterative search for a threshold whose scale depends on how cp_measure normalises integer images) is
+  not restated.  The key names are CellProfiler's feature stems; cp_measure's own spelling could not be checked.
 """
 
 from __future__ import annotations
@@ -163,4 +174,66 @@ def get_sizeshape(mask: np.ndarray, pixels=None) -> dict:
     return {k: np.array([val]) for k, val in out.items()}
 
 
+CORRELATION_FEATURES = {
+    "pearson": ("Correlation_Pearson",),
+    "manders_fold": ("Correlation_Manders_1", "Correlation_Manders_2"),
+    "rwc": ("Correlation_RWC_1", "Correlation_RWC_2"),
+    "overlap": ("Correlation_Overlap", "Correlation_K_1", "Correlation_K_2"),
+}
+
+
+def _dense_rank(v: np.ndarray) -> np.ndarray:
+    """0-based dense ranks (equal values share a rank), MeasureColocalization's lexsort / cumsum construction."""
+    order = np.argsort(v, kind="stable")
+    step = np.concatenate([[False], v[order[:-1]] != v[order[1:]]])
+    rank = np.zeros(len(v), dtype=np.int64)
+    rank[order] = np.cumsum(step)
+    return rank
+
+
+def get_correlation(pixels1: np.ndarray, pixels2: np.ndarray, mask: np.ndarray, thr: float = 15) -> dict:
+    """Every restated two-image feature of one binary mask: ``{key: ndarray(1)}``."""
+    m = np.asarray(mask) > 0
+    fi = np.asarray(pixels1)[m].astype(np.float64)
+    si = np.asarray(pixels2)[m].astype(np.float64)
+    nan = float("nan")
+    out = {k: nan for keys in CORRELATION_FEATURES.values() for k in keys}
+    if len(fi):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            x, y = fi - fi.mean(), si - si.mean()
+            std1, std2 = np.sqrt((x * x).sum()), np.sqrt((y * y).sum())
+            out["Correlation_Pearson"] = float((x * y / (std1 * std2)).sum())
+            t1, t2 = (thr / 100) * fi.max(), (thr / 100) * si.max()
+            both = (fi >= t1) & (si >= t2)
+            tot1, tot2 = fi[fi >= t1].sum(), si[si >= t2].sum()
+            thresholded = [k for name in ("manders_fold", "rwc", "overlap") for k in CORRELATION_FEATURES[name]]
+            if both.any():
+                f, s = fi[both], si[both]
+                out["Correlation_Manders_1"] = float(f.sum() / tot1)
+                out["Correlation_Manders_2"] = float(s.sum() / tot2)
+                r1, r2 = _dense_rank(fi), _dense_rank(si)
+                big_r = max(r1.max(), r2.max()) + 1
+                weight = ((big_r - np.abs(r1 - r2)) / big_r)[both]
+                out["Correlation_RWC_1"] = float((f * weight).sum() / tot1)
+                out["Correlation_RWC_2"] = float((s * weight).sum() / tot2)
+                fs, ff, ss = (f * s).sum(), (f * f).sum(), (s * s).sum()
+                out["Correlation_Overlap"] = float(fs / np.sqrt(ff * ss))
+                out["Correlation_K_1"] = float(fs / ff)
+                out["Correlation_K_2"] = float(fs / ss)
+            else:
+                for k in thresholded:
+                    out[k] = 0.0
+    return {k: np.array([v]) for k, v in out.items()}
+
+
+def _correlation_subset(name):
+    def fun(pixels1, pixels2, mask, **kw):
+        full = get_correlation(pixels1, pixels2, mask, **kw)
+        return {k: full[k] for k in CORRELATION_FEATURES[name]}
+
+    fun.__name__ = f"get_correlation_{name}"
+    return fun
+
+
 FEATURES = {"intensity": get_intensity, "sizeshape": get_sizeshape}
+CORRELATIONS = {name: _correlation_subset(name) for name in CORRELATION_FEATURES}

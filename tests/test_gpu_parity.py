@@ -801,6 +801,146 @@ def test_cp_measure_intensity_and_sizeshape(ab):
         ab.process_tree_masks(tree, labels, pixels, ab.extract_tree)
     with pytest.raises(KeyError, match="radial_zernikes"):
         ab.process_tree_masks({0: {"max": ("radial_zernikes",)}}, labels, pixels, ab.extract_tree)
+    # an object above the 64 x 64 window has no kernel for the rank statistics: the call says so instead of returning them
+    wide = np.zeros((160, 200), np.uint16)
+    wide[20:100, 30:130] = 1
+    with pytest.raises(NotImplementedError, match="64 x 64"):
+        ab.process_tree_masks({0: {"max": ("intensity",)}}, wide, pixels[:, :, :, :160, :200], ab.extract_tree, cp_measure_kwargs=kw)
+    items_w, got_w = ab.process_tree_masks({"None": {"None": ("sizeshape",)}}, wide, pixels[:, :, :, :160, :200], ab.extract_tree)
+    _check_cp(items_w, got_w, _cpm_reference({"None": {"None": ("sizeshape",)}}, wide, pixels[:, :, :, :160, :200], {}))
+
+
+def _colocalisation_reference(tree, masks, pixels, cp_kwargs=None):
+    """Per (object, instruction) dicts of oracle/cpm.py for an extractmulti tree, in the reference's item order
+    (extract.py:200-226: both channels Z-reduced, then ``fun(pixels1, pixels2, mask)``)."""
+    from oracle import cpm, port
+
+    if not isinstance(masks, list):
+        masks = [masks]
+    cp_kwargs = cp_kwargs or {}
+    insts = port.tree_instructions(tree)
+    out = []
+    for tile_i, lab in enumerate(masks):
+        for k in range(1, int(lab.max()) + 1 if lab.size else 1):
+            for (ch0, ch1), red_ch, red, metric in insts:
+                assert red_ch == "None"
+                a = port.project_z(pixels[tile_i, ch0], port.Z_REDUCERS[red])
+                b = port.project_z(pixels[tile_i, ch1], port.Z_REDUCERS[red])
+                out.append(cpm.CORRELATIONS[metric](a, b, lab == k, **cp_kwargs.get(metric, {})))
+    return out
+
+
+def _check_colocalisation(items, got, want):
+    assert len(got) == len(want) == len(items)
+    for it, g, w in zip(items, got, want):
+        assert isinstance(g, dict) and list(g) == list(w), it
+        for key in w:
+            a, b = float(g[key][0]), float(w[key][0])
+            if b != b:
+                assert a != a, (it, key, a)
+            else:  # exact integer sums on the GPU, float64 sums in the oracle: 1e-9 (absolute for a correlation near 0)
+                assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (it, key, a, b)
+
+
+def test_extractmulti_colocalisation(ab):
+    """``extractmulti_*`` trees (pipe_builder.py:19-43 without `costes`): Pearson, Manders, rank-weighted colocalisation
+    and overlap of every channel pair per object against oracle/cpm.py (parity self-defined, like cp_measure's other
+    features) — correlated and independent channels, absent ids, one-pixel and constant cells, a cell wider than the
+    64 x 64 window, a Z stack under `max`, uint8 pixels, a non-default threshold — and the reference's column names."""
+    from itertools import combinations
+
+    from aliby_b200 import synth
+
+    rng = np.random.default_rng(77)
+    pixels, labels = synth.make_field(909, (320, 384), 3, 50, semi_axes=(3, 24))
+    labels = labels.copy()
+    labels[200:300, 20:140][labels[200:300, 20:140] == 0] = int(labels.max()) + 2  # wide cell, and one absent id below it
+    pixels = pixels.copy()
+    pixels[0, 1] = (pixels[0, 0] // 3 + rng.integers(0, 900, size=labels.shape)).astype(np.uint16)  # correlated with channel 0
+    one = int(labels[labels > 0][0])
+    pixels[0, 2, 0][labels == one] = 1234  # a constant cell in channel 2
+    labels[5, 7] = int(labels.max()) + 1  # one-pixel cell
+    tree = {pair: {"None": {"max": ["pearson", "manders_fold", "rwc", "overlap"]}} for pair in combinations(range(3), 2)}
+    items, got = ab.process_tree_masks(tree, labels, pixels, ab.extract_tree_multi)
+    assert items[0] == ((0, 1), ((0, 1), "None", "max", "pearson"))
+    _check_colocalisation(items, got, _colocalisation_reference(tree, labels, pixels))
+    table = ab.format_extraction((items, got))
+    assert table.num_rows == int(labels.max())
+    assert "(0, 1)/None/max/pearson/Correlation_Pearson" in table.column_names
+    assert "(1, 2)/None/max/rwc/Correlation_RWC_2" in table.column_names
+    plain = ab.format_extraction((tuple(items), list(got)))
+    assert plain.column_names == table.column_names
+    for c in table.column_names:
+        x, y = table.column(c).to_pylist(), plain.column(c).to_pylist()
+        assert all((p == q) or (p != p and q != q) for p, q in zip(x, y)), c
+    # a Z stack (max), several tiles, uint8, a different threshold, a subset of the features
+    kw = {"manders_fold": {"thr": 40}}
+    tiles = [synth.make_field(930 + t, (96, 128), 2, 6, n_z=3, semi_axes=(3, 12)) for t in range(3)]
+    px8 = (np.concatenate([t[0] for t in tiles]) >> 8).astype(np.uint8)
+    masks = [t[1] for t in tiles]
+    tree2 = {(1, 0): {"None": {"max": ["manders_fold", "pearson"]}}}
+    for px in (np.concatenate([t[0] for t in tiles]), px8):
+        items2, got2 = ab.process_tree_masks(tree2, masks, px, ab.extract_tree_multi, cp_measure_kwargs=kw)
+        _check_colocalisation(items2, got2, _colocalisation_reference(tree2, masks, px, kw))
+    # what has no kernel says so: costes, a channel reduction, sums of a stack beyond 16 bits
+    with pytest.raises(NotImplementedError, match="costes"):
+        ab.process_tree_masks({(0, 1): {"None": {"max": ["costes"]}}}, labels, pixels, ab.extract_tree_multi)
+    with pytest.raises(NotImplementedError, match="red_ch"):
+        ab.process_tree_masks({(0, 1): {"add": {"max": ["pearson"]}}}, labels, pixels, ab.extract_tree_multi)
+    with pytest.raises(KeyError, match="colocalise"):
+        ab.process_tree_masks({(0, 1): {"None": {"max": ["colocalise"]}}}, labels, pixels, ab.extract_tree_multi)
+    big = np.full((1, 2, 2, 64, 64), 40000, dtype=np.uint16)
+    lab = np.zeros((64, 64), np.uint16)
+    lab[10:20, 10:20] = 1
+    with pytest.raises(NotImplementedError, match="65536"):
+        ab.process_tree_masks({(0, 1): {"None": {"add": ["pearson"]}}}, lab, big, ab.extract_tree_multi)
+    small = np.full((1, 2, 2, 64, 64), 300, dtype=np.uint16)
+    small[0, 1, 1, 12:15] = 900
+    small[0, 0, 0, 11:14, 11] = 70
+    tree3 = {(0, 1): {"None": {"add": ["pearson", "rwc"]}}}
+    items3, got3 = ab.process_tree_masks(tree3, lab, small, ab.extract_tree_multi)
+    _check_colocalisation(items3, got3, _colocalisation_reference(tree3, lab, small))
+
+
+def test_extractmulti_step_splits_with_the_reference(ab, monkeypatch):
+    """``init_step('extractmulti_*')`` (pipe.py:65-66): the branches with a kernel run on the GPU, the others (costes)
+    go to the reference's step, and the concatenated result pivots into one table with every requested column."""
+    from aliby_b200 import pipe, synth
+
+    pixels, labels = synth.make_field(941, (128, 160), 2, 9, semi_axes=(3, 12))
+    seen = {}
+
+    def fake_reference_init_step(step_name, parameters, other_steps, why):
+        seen["tree"] = parameters["tree"]
+
+        def step(masks, pixels, **kw):
+            masks_ = masks if isinstance(masks, list) else [masks]
+            insts = ab.kv(ab.flatten(parameters["tree"]))
+            objs = [(t, k) for t, m in enumerate(masks_) for k in range(1, int(m.max()) + 1)]
+            items = tuple((o, i) for o in objs for i in insts)
+            return items, [{"Correlation_Costes_1": np.array([0.5]), "Correlation_Costes_2": np.array([0.25])} for _ in items]
+
+        return step
+
+    monkeypatch.setattr(pipe, "_reference_init_step", fake_reference_init_step)
+    params = {"tree": {(0, 1): {"None": {"max": ["pearson", "costes", "manders_fold", "rwc"]}}}, "kwargs": {"ncores": None}}
+    step = pipe.init_step("extractmulti_nuclei", params)
+    assert seen["tree"] == {(0, 1): {"None": {"max": ["costes"]}}}
+    items, results = step(masks=[labels], pixels=pixels)
+    table = ab.format_extraction((items, results))
+    assert table.num_rows == int(labels.max())
+    cols = table.column_names
+    assert "(0, 1)/None/max/costes/Correlation_Costes_2" in cols and "(0, 1)/None/max/rwc/Correlation_RWC_1" in cols
+    want = _colocalisation_reference({(0, 1): {"None": {"max": ["pearson"]}}}, labels, pixels)
+    got = table.column("(0, 1)/None/max/pearson/Correlation_Pearson").to_pylist()
+    for g, w in zip(got, want):
+        w = float(w["Correlation_Pearson"][0])
+        assert (g != g and w != w) or abs(g - w) <= 1e-9
+    # a tree the kernels cover completely never touches the reference
+    monkeypatch.setattr(pipe, "_reference_init_step", lambda *a, **k: (_ for _ in ()).throw(AssertionError("not needed")))
+    step2 = pipe.init_step("extractmulti_nuclei", {"tree": {(0, 1): {"None": {"max": ["pearson", "overlap"]}}}})
+    items2, res2 = step2(masks=[labels], pixels=pixels)
+    assert len(items2) == 2 * int(labels.max()) and list(res2[1]) == ["Correlation_Overlap", "Correlation_K_1", "Correlation_K_2"]
 
 
 SHARD_WORKER = r'''

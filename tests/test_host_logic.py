@@ -25,9 +25,9 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(nat.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert nat.lib().abx_version() == 3
+    assert nat.lib().abx_version() == nat.ABI_VERSION == 4
     # struct mirrors: sizes must agree with the C side (48-byte records, 16-byte requests)
-    assert ctypes.sizeof(nat.ObjectRec) == 48 and ctypes.sizeof(nat.Request) == 16 and ctypes.sizeof(nat.Column) == 8
+    assert ctypes.sizeof(nat.ObjectRec) == 48 and ctypes.sizeof(nat.Request) == 16 and ctypes.sizeof(nat.Column) == 8 and ctypes.sizeof(nat.Pair) == 24
 
 
 def test_abi_rejects_bad_arguments_without_a_gpu():
@@ -250,9 +250,14 @@ def test_init_step_seam_matches_reference_partial_shape():
     assert baby.func is extract.process_tree_masks_overlap and baby.keywords["measure_fn"].keywords == {"overlap": True}
     with pytest.raises(ValueError, match="missing required 'tree'"):
         pipe.init_step("extract_nuclei", {})
-    # extractmulti_* (cp_measure colocalisation) and every non-extract step belong to the reference's own init_step
-    with pytest.raises(ImportError, match="colocalisation"):  # the reference is not installed next to us in this container
-        pipe.init_step("extractmulti_nuclei", {"tree": tree})
+    # extractmulti_* (pipe_core.py:84-92): the same partial with extract_tree_multi; every non-extract step belongs to the
+    # reference's own init_step (not installed next to us in this container)
+    multi_tree = {(0, 1): {"None": {"max": ["pearson", "costes"]}}}
+    multi = pipe.init_step("extractmulti_nuclei", {"tree": multi_tree, "kwargs": {"ncores": 2}})
+    assert multi.func is extract.process_tree_masks and multi.keywords["measure_fn"] is extract.extract_tree_multi
+    assert multi.keywords["tree"] is multi_tree and multi.keywords["ncores"] == 2
+    with pytest.raises(ValueError, match="missing required 'tree'"):
+        pipe.init_step("extractmulti_nuclei", {})
     with pytest.raises(ImportError):
         pipe.init_step("segment_nuclei", {})
 
@@ -340,6 +345,7 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
              '  printf("sizeof_request %zu\\n", sizeof(abx_request));',
              '  printf("sizeof_column %zu\\n", sizeof(abx_column));',
              '  printf("sizeof_rec %zu\\n", sizeof(abx_object_rec));',
+             '  printf("pair %zu %zu %zu %d %d\\n", sizeof(abx_pair), offsetof(abx_pair, features), offsetof(abx_pair, threshold_fraction), ABX_M_CO_K_2, ABX_PF_RWC);',
              '  printf("enums %d %d %d %d %d %d\\n", ABX_F64, ABX_RED_DIV, ABX_M_BACKGROUND_MAX5, ABX_M_MEAN, ABX_F_MOI, ABX_ERR_UNSUPPORTED);',
              "  return 0;", "}"]
     src = tmp_path / "layout.c"
@@ -352,8 +358,43 @@ def test_ctypes_mirrors_match_the_c_header(tmp_path):
     assert int(out["sizeof_args"]) == ctypes.sizeof(nat.ExtractArgs)
     assert int(out["sizeof_request"]) == ctypes.sizeof(nat.Request) and int(out["sizeof_column"]) == ctypes.sizeof(nat.Column)
     assert int(out["sizeof_rec"]) == ctypes.sizeof(nat.ObjectRec)
+    assert out["pair"].split() == [str(v) for v in (ctypes.sizeof(nat.Pair), nat.Pair.features.offset,
+                                                    nat.Pair.threshold_fraction.offset, nat.METRIC["co_k_2"], nat.PF_RWC)]
     assert out["enums"].split() == [str(v) for v in (nat.F64, nat.RED_DIV, nat.METRIC["background_max5"], nat.METRIC["mean"],
                                                      nat.F_MOI, -2)]
+
+
+def test_extractmulti_tree_compiles_into_pairs():
+    """The stock builder's colocalisation tree (pipe_builder.py:19-43): every channel pair becomes one abx_pair over two
+    shared requests, each feature a dict-valued instruction; `costes` is the only part without a kernel and the seam
+    splits the tree along that line (same nesting on both sides)."""
+    from itertools import combinations
+
+    from aliby_b200 import _native as nat
+    from aliby_b200 import engine, pipe
+
+    tree = {pair: {"None": {"max": ["pearson", "costes", "manders_fold", "rwc"]}} for pair in combinations((0, 2, 3), r=2)}
+    plan = engine.compile_tree(tree)
+    assert isinstance(plan.error, NotImplementedError) and "costes" in str(plan.error)
+    ours, theirs = pipe._split_multi_tree(tree)
+    assert theirs == {pair: {"None": {"max": ["costes"]}} for pair in tree}
+    assert ours == {pair: {"None": {"max": ["pearson", "manders_fold", "rwc"]}} for pair in tree}
+    plan = engine.compile_tree(ours, {"manders_fold": {"thr": 15}})
+    assert plan.error is None
+    assert [r[:2] for r in plan.requests] == [[0, nat.RED_MAX], [2, nat.RED_MAX], [3, nat.RED_MAX]]
+    assert plan.pairs == [[0, 1, 3, 0.15], [0, 2, 3, 0.15], [1, 2, 3, 0.15]]
+    assert plan.instructions[0] == ((0, 2), "None", "max", "pearson") and plan.inst_keys[0] == ["Correlation_Pearson"]
+    assert plan.inst_keys[2] == ["Correlation_RWC_1", "Correlation_RWC_2"]
+    assert [plan.columns[j] for j in plan.inst_cols[2]] == [(0, nat.METRIC["co_rwc_1"]), (0, nat.METRIC["co_rwc_2"])]
+    # another threshold is another pair; the reference's error behaviour for unknown names
+    plan = engine.compile_tree({(0, 1): {"None": {"max": ["manders_fold"]}}}, {"manders_fold": {"thr": 40}})
+    assert plan.pairs == [[0, 1, 1, 0.4]]
+    assert isinstance(engine.compile_tree({(0, 1): {"None": {"max": ["nope"]}}}).error, KeyError)
+    assert isinstance(engine.compile_tree({(0, 1): {"None": {"nope": ["pearson"]}}}).error, KeyError)
+    assert "invalid reducer" in str(engine.compile_tree({(0, 1): {"None": {"mean": ["pearson"]}}}).error)
+    # a step whose tree the kernels cover is ours even without the reference installed
+    step = pipe.init_step("extractmulti_cells", {"tree": ours, "kwargs": {"ncores": None}})
+    assert step.func.__module__ == "aliby_b200.extract" and step.keywords["measure_fn"].__name__ == "extract_tree_multi"
 
 
 def _golden_profile_state():

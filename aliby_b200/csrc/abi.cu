@@ -65,6 +65,8 @@ int abx_plan_workspace(const abx_extract_args* a, void* base, Workspace* ws) {
   off = align_up(off + n_rec * (size_t)a->n_requests * sizeof(ChanStats));
   ws->pairs = reinterpret_cast<PairStats*>(b + off);
   off = align_up(off + (size_t)a->n_objects * (size_t)a->n_pairs * sizeof(PairStats));
+  ws->pair_wide = reinterpret_cast<int*>(b + off);
+  off = align_up(off + (size_t)a->n_objects * (size_t)a->n_pairs * sizeof(int));
   ws->shape = reinterpret_cast<ShapeStats*>(b + off);
   off = align_up(off + (a->need_edt ? (size_t)a->n_objects * sizeof(ShapeStats) : 0));
   ws->err = reinterpret_cast<u32*>(b + off);

@@ -69,7 +69,8 @@ struct ObjPlan {
 constexpr int kCounterWords = 32;  // err[0] + list_counts[31], zeroed by the label scan
 // indices into Workspace::list_counts
 constexpr int kCntStatsList = 0, kCntEdtList = 1, kCntGather = 2, kCntLeftover = 3, kCntEdtWork = 4, kCntLeftoverWork = 6,
-              kCntRest = 8, kCntOrderBig = 12, kCntOrderSmall = 13, kCntSweepWork = 14, kCntEdtBig = 15, kCntEdtSmall = 16;
+              kCntRest = 8, kCntOrderBig = 12, kCntOrderSmall = 13, kCntSweepWork = 14, kCntEdtBig = 15, kCntEdtSmall = 16,
+              kCntPairWork = 17, kCntPairWide = 19;
 
 // Raw second moments of an object's pixel coordinates relative to its bounding box origin (plan kernel, from the bitmap)
 struct MaskMoments {
@@ -95,6 +96,7 @@ static_assert(sizeof(PairStats) == 96, "PairStats layout");
 struct Workspace {
   abx_object_rec* recs;  // [n_objects + n_planes]
   PairStats* pairs;      // [n_objects * n_pairs]
+  int* pair_wide;        // [n_objects * n_pairs] items the warp kernel of object_pair.cu leaves to its CTA kernel
   MaskMoments* mom;      // [n_objects] when need_edt bit 2
   u64* bitmaps;          // [n_objects + 1][64] torus bitmaps written by the label scan (label_scan.cu)
   ObjPlan* plan;         // [n_objects + n_planes]

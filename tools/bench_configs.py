@@ -126,7 +126,7 @@ def _entry(workload, n_objects, n_features, algo_bytes, device_ms, e2e_ms, stage
     return d
 
 
-def measure_configs(device, peak_gbs, iters=10, which=("C1", "C2_single_field", "C3", "C4")):
+def measure_configs(device, peak_gbs, iters=10, which=("C1", "C2_single_field", "C2_cp_measure", "C3", "C4")):
     import torch
 
     from aliby_b200 import _native as nat
@@ -138,9 +138,10 @@ def measure_configs(device, peak_gbs, iters=10, which=("C1", "C2_single_field", 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     out = {}
 
-    def dense_case(name, workload, pixels, labels, tree):
+    def dense_case(name, workload, pixels, labels, tree, cp_kwargs=None):
         """One field: pixels (1, C, Z, Y, X), labels (Y, X)."""
-        plan = engine.compile_tree(tree)
+        plan = engine.compile_tree(tree, cp_kwargs)
+        assert plan.error is None, plan.error
         _, C_, Z_, Y, X = pixels.shape
         lab_dev = torch.from_numpy(labels[None]).to(device)
         px_dev = torch.from_numpy(pixels).to(device)
@@ -157,7 +158,8 @@ def measure_configs(device, peak_gbs, iters=10, which=("C1", "C2_single_field", 
         lab_pin = torch.from_numpy(labels).pin_memory().numpy()
         ems = _e2e(torch, lambda: extract.extract_table(tree, lab_pin, px_pin, device=device, plan=plan), max(3, iters // 2))
         algo = pixels.nbytes + labels.nbytes + int(n_labels[0]) * plan.n_columns * 8
-        out[name] = _entry(workload, n_labels[0], len(plan.instructions), algo, dms, ems, st, peak_gbs)
+        n_feat = sum(len(c) for c in plan.inst_cols)  # a dict-valued (cp_measure) instruction counts once per key
+        out[name] = _entry(workload, n_labels[0], n_feat, algo, dms, ems, st, peak_gbs)
         del lab_dev, px_dev, table
 
     if "C1" in which:
@@ -170,6 +172,21 @@ def measure_configs(device, peak_gbs, iters=10, which=("C1", "C2_single_field", 
         px, lab = synth.make_field(synth.CONFIG_SEEDS["C2"], (2160, 2160), 5, 2000)
         dense_case("C2_single_field", "5 channels x 2160^2 uint16, ~2k cells, full cell-function set, ONE field per call "
                    "(what a pipeline step does)", px, lab, bench.c2_tree())
+    if "C2_cp_measure" in which:
+        # what the reference's stock builder asks for (pipe_builder.py:19-43,115-120), restricted to the cp_measure features
+        # with a kernel: sizeshape on the masks, intensity per channel, and the two-image features of every channel pair
+        from itertools import combinations
+
+        px, lab = synth.make_field(synth.CONFIG_SEEDS["C2"] + 1, (2160, 2160), 5, 2000)
+        kw = {"intensity": {"edge_measurements": False}}
+        tree = {"None": {"None": ["sizeshape"]}}
+        for ch in range(5):
+            tree[ch] = {"max": ["intensity"]}
+        dense_case("C2_cp_measure", "C2 field, cp_measure features with a kernel: sizeshape (15 keys) + intensity on 5 channels "
+                   "(16 keys each, edge features off), one field per call", px, lab, tree, kw)
+        multi = {pair: {"None": {"max": ["pearson", "manders_fold", "rwc"]}} for pair in combinations(range(5), r=2)}
+        dense_case("C2_extractmulti", "C2 field, extractmulti tree of the stock builder without costes: pearson, manders_fold, "
+                   "rwc on all 10 channel pairs (5 keys each), one field per call", px, lab, multi)
     if "C4" in which:
         rng = np.random.default_rng(synth.CONFIG_SEEDS["C4"])
         lab = synth.ellipse_labels(rng, (2048, 2048), 1500)

@@ -191,6 +191,24 @@ def compile_tree(tree: dict, cp_measure_kwargs=None) -> Plan:
     return compile_instructions(kv(flatten(tree)), cp_measure_kwargs)
 
 
+_plan_cache: dict = {}
+
+
+def compile_cached(instructions: list, cp_measure_kwargs=None) -> Plan:
+    """:func:`compile_instructions` memoised on the instruction list: a pipeline calls its extract step with the same tree at
+    every time point, and a cached plan also keeps its device copies of the request / column / pair tables."""
+    try:
+        key = (tuple(instructions), repr(sorted((k, sorted(v.items())) for k, v in (cp_measure_kwargs or {}).items())))
+        plan = _plan_cache.get(key)
+    except TypeError:  # an unhashable instruction: compile it for the error message it deserves
+        return compile_instructions(instructions, cp_measure_kwargs)
+    if plan is None:
+        if len(_plan_cache) >= 64:
+            _plan_cache.pop(next(iter(_plan_cache)))
+        plan = _plan_cache[key] = compile_instructions(instructions, cp_measure_kwargs)
+    return plan
+
+
 def compile_instructions(instructions: list, cp_measure_kwargs=None) -> Plan:
     plan = Plan(instructions=list(instructions))
     cp_kw = dict(cp_measure_kwargs or {})
@@ -556,4 +574,7 @@ class GraphedExtract:
         n_labels = np.asarray(n_labels, dtype=np.int64)
         if n_labels.max(initial=0) > self.cap:
             raise IndexError(f"{int(n_labels.max())} labels in a plane exceed the captured capacity {self.cap}")
-        return np.concatenate([p * self.cap + np.arange(k) for p, k in enumerate(n_labels)]) if len(n_labels) else np.zeros(0, np.int64)
+        if not len(n_labels):
+            return np.zeros(0, np.int64)
+        starts = np.cumsum(n_labels) - n_labels  # first output index of every plane
+        return np.arange(int(n_labels.sum())) + np.repeat(np.arange(len(n_labels)) * self.cap - starts, n_labels)

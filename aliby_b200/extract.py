@@ -19,7 +19,8 @@ raise ``KeyError`` naming the metric.
 
 from __future__ import annotations
 
-from itertools import product
+from collections.abc import Sequence
+from itertools import product, repeat
 
 import numpy as np
 
@@ -40,13 +41,49 @@ class ExtractionResults(list):
     items: tuple | None = None
 
 
-class ItemTuple(tuple):
-    """The ``tileid_instructions`` tuple of :func:`process_tree_masks`, carrying what it was built from (the compiled
-    plan and the object list) so that :func:`extract_tree` need not re-derive them from |objects| x |instructions|
-    items.  A plain tuple to every consumer; nothing is kept in module state, so concurrent callers do not interfere."""
+class ItemTuple(Sequence):
+    """The ``tileid_instructions`` of :func:`process_tree_masks`: ``product(objects, instructions)``, object-major, as an
+    immutable sequence that is NOT materialised — a C2 field is 2 000 objects x 52 instructions = 104 000 nested tuples,
+    10 ms of pure allocation per call that the only consumer the reference has (``format_extraction``: one ``zip`` over
+    it, extract.py:536) does not need.  Indexing, slicing, iteration, ``len``, ``==`` with a tuple and ``tuple(items)``
+    behave like the reference's tuple.  It also carries what it was built from (the compiled plan, the object list, the
+    id count of every plane) so that :func:`extract_tree` need not re-derive them; nothing is kept in module state, so
+    concurrent callers do not interfere."""
 
     plan: "engine.Plan | None" = None
-    objects: "list | None" = None
+    counts: "dict | None" = None  # plane key ((tile,) or (tile, stack)) -> number of ids enumerated for it
+
+    def __init__(self, objects: list, instructions: list):
+        self.objects = objects
+        self.instructions = instructions
+
+    def __len__(self):
+        return len(self.objects) * len(self.instructions)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return tuple(self[j] for j in range(*i.indices(len(self))))
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("tuple index out of range")
+        o, k = divmod(i, len(self.instructions))
+        return (self.objects[o], self.instructions[k])
+
+    def __iter__(self):
+        return product(self.objects, self.instructions)
+
+    def __eq__(self, other):
+        if isinstance(other, (tuple, list, ItemTuple)):
+            return len(self) == len(other) and all(a == b for a, b in zip(self, other))
+        return NotImplemented
+
+    def __hash__(self):
+        return hash((tuple(self.objects), tuple(self.instructions)))
+
+    def __repr__(self):
+        return f"ItemTuple({len(self.objects)} objects x {len(self.instructions)} instructions)"
 
 
 def _as_mask_list(masks):
@@ -56,7 +93,13 @@ def _as_mask_list(masks):
 
 
 def _host_label_stack(planes: list[np.ndarray]) -> np.ndarray:
-    """Equally-shaped 2-D label planes as one contiguous uint16 array."""
+    """Equally-shaped 2-D label planes as one contiguous uint16 array (a view when they already are one)."""
+    if all(isinstance(p, np.ndarray) and p.dtype == np.uint16 and p.flags.c_contiguous for p in planes):
+        if len(planes) == 1:
+            return planes[0][None]
+        run = _contiguous_run(planes)
+        if run is not None:
+            return run
     stack = np.stack(planes)
     if stack.dtype != np.uint16:
         if stack.size and (stack.min() < 0 or stack.max() > 65535):
@@ -390,7 +433,12 @@ def _results_from_dense(plan, dense, row_of_item, inst_of_item):
     single = all(len(c) == 1 and k is None for c, k in zip(plan.inst_cols, plan.inst_keys))
     if single and len(row_of_item):
         cols = np.fromiter((c[0] for c in plan.inst_cols), dtype=np.int64)
+        if inst_of_item is None:  # the object-major product over the rows `row_of_item` (one entry per OBJECT)
+            return dense[row_of_item][:, cols].ravel().tolist()
         return dense[row_of_item, cols[inst_of_item]].tolist()
+    if inst_of_item is None:
+        n_inst = len(plan.inst_cols)
+        row_of_item, inst_of_item = np.repeat(row_of_item, n_inst), np.tile(np.arange(n_inst), len(row_of_item))
     out = []
     for r, i in zip(row_of_item, inst_of_item):
         c, keys = plan.inst_cols[i], plan.inst_keys[i]
@@ -416,12 +464,14 @@ def process_tree_masks(
     masks = _as_mask_list(masks)
     instructions = kv(flatten(tree))
     ind_masks = []
+    counts = {}
     for tile_i, masks_in_tile in enumerate(masks):
         if len(masks_in_tile):
-            for mask_i in range(1, int(masks_in_tile.max()) + 1):
-                ind_masks.append((tile_i, mask_i))
-    tileid_instructions = ItemTuple(product(ind_masks, instructions))
-    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions, cp_measure_kwargs), ind_masks
+            counts[(tile_i,)] = k = int(masks_in_tile.max())
+            ind_masks.extend(zip(repeat(tile_i, k), range(1, k + 1)))
+    tileid_instructions = ItemTuple(ind_masks, instructions)
+    tileid_instructions.plan = engine.compile_cached(instructions, cp_measure_kwargs)
+    tileid_instructions.counts = counts
     extra = {}
     if cp_measure_kwargs is not None:
         extra["cp_measure_kwargs"] = cp_measure_kwargs
@@ -455,14 +505,17 @@ def process_tree_masks_overlap(
     instructions = kv(flatten(tree))
     tile_stack_mask = []
     inverse_mappings = {}
+    counts = {}
     for tile_i, masks_in_tile in enumerate(masks):
         for stack_i, stack_pixels in enumerate(masks_in_tile):
             ids = np.unique(stack_pixels)
             ids = ids[ids > 0]
+            counts[(tile_i, stack_i)] = len(ids)
             inverse_mappings[(tile_i, stack_i)] = np.concatenate([[0], ids]).astype(np.int64)
             tile_stack_mask.extend((tile_i, stack_i, mask_i) for mask_i in range(1, len(ids) + 1))
-    tileid_instructions = ItemTuple(product(tile_stack_mask, instructions))
-    tileid_instructions.plan, tileid_instructions.objects = engine.compile_instructions(instructions, cp_measure_kwargs), tile_stack_mask
+    tileid_instructions = ItemTuple(tile_stack_mask, instructions)
+    tileid_instructions.plan = engine.compile_cached(instructions, cp_measure_kwargs)
+    tileid_instructions.counts = counts
     extra = {}
     if cp_measure_kwargs is not None:
         extra["cp_measure_kwargs"] = cp_measure_kwargs
@@ -492,10 +545,13 @@ def extract_tree(
     if not len(tileid_instructions):
         return results
     masks = _as_mask_list(masks)
+    counts = None
     if isinstance(tileid_instructions, ItemTuple) and tileid_instructions.plan is not None:
         plan, objects = tileid_instructions.plan, tileid_instructions.objects
         n_inst = len(plan.instructions)
         row_of_item = inst_of_item = None  # object-major product: implicit
+        if inverse_mappings is None:
+            counts = tileid_instructions.counts  # ids 1..k of every plane, planes in this function's own order
     else:
         inst_index: dict = {}
         obj_index: dict = {}
@@ -504,7 +560,7 @@ def extract_tree(
         for k, (obj, inst) in enumerate(tileid_instructions):
             row_of_item[k] = obj_index.setdefault(tuple(obj), len(obj_index))
             inst_of_item[k] = inst_index.setdefault(tuple(inst), len(inst_index))
-        plan = engine.compile_instructions(list(inst_index), cp_measure_kwargs)
+        plan = engine.compile_cached(list(inst_index), cp_measure_kwargs)
         objects = list(obj_index)
         n_inst = len(inst_index)
 
@@ -516,10 +572,13 @@ def extract_tree(
         stacks = list(m) if overlap else [m]
         for stack_i, plane in enumerate(stacks):
             plane = np.asarray(plane)
-            plane_of[(tile_i, stack_i) if overlap else (tile_i,)] = len(planes)
+            key = (tile_i, stack_i) if overlap else (tile_i,)
+            plane_of[key] = len(planes)
             planes.append(plane)
             plane_tile.append(tile_i)
-            if overlap and inverse_mappings is None:  # ids 1..k, k = number of distinct labels of the stack
+            if counts is not None:  # process_tree_masks* has looked at this plane already
+                n_labels.append(counts[key])
+            elif overlap and inverse_mappings is None:  # ids 1..k, k = number of distinct labels of the stack
                 n_labels.append(int(np.count_nonzero(np.unique(plane))))
             else:
                 n_labels.append(int(plane.max()) if plane.size else 0)
@@ -527,23 +586,31 @@ def extract_tree(
     base = np.concatenate([[0], np.cumsum(n_labels)])
     dense = _run_dense(plan, planes, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels)
 
-    obj_rows = np.empty(len(objects), dtype=np.int64)
-    for k, obj in enumerate(objects):
-        p = plane_of[tuple(obj[:-1])]
-        label = obj[-1]
-        if inverse_mappings is not None:  # sequential id -> original id of its (tile, stack)
-            label = int(inverse_mappings[tuple(obj[:-1])][label])
-        if not (1 <= label <= n_labels[p]):
-            raise IndexError(f"index {label - 1} is out of bounds for axis 0 with size {n_labels[p]}")
-        obj_rows[k] = base[p] + label - 1
+    if counts is not None:
+        # the objects are the ids 1..k of every plane in plane order: row = position, no per-object Python work
+        obj_rows = np.arange(len(objects), dtype=np.int64)
+        keys = np.asarray(list(plane_of), dtype=np.int64).reshape(len(plane_of), -1)
+        starts = base[:-1]
+        objects_arr = np.concatenate(
+            [np.repeat(keys, n_labels, axis=0), (obj_rows - np.repeat(starts, n_labels) + 1)[:, None]], axis=1)
+    else:
+        objects_arr = None
+        obj_rows = np.empty(len(objects), dtype=np.int64)
+        for k, obj in enumerate(objects):
+            p = plane_of[tuple(obj[:-1])]
+            label = obj[-1]
+            if inverse_mappings is not None:  # sequential id -> original id of its (tile, stack)
+                label = int(inverse_mappings[tuple(obj[:-1])][label])
+            if not (1 <= label <= n_labels[p]):
+                raise IndexError(f"index {label - 1} is out of bounds for axis 0 with size {n_labels[p]}")
+            obj_rows[k] = base[p] + label - 1
     if row_of_item is None:
-        row_of_item = np.repeat(obj_rows, n_inst)
-        inst_of_item = np.tile(np.arange(n_inst), len(objects))
+        row_of_item = obj_rows  # (object-major product: _results_from_dense expands it)
     else:
         row_of_item = obj_rows[row_of_item]
     results.extend(_results_from_dense(plan, dense, row_of_item, inst_of_item))
     results.dense, results.plan, results.items = dense, plan, tileid_instructions
-    results.objects = np.asarray(objects, dtype=np.int64).reshape(len(objects), -1)
+    results.objects = objects_arr if objects_arr is not None else np.asarray(objects, dtype=np.int64).reshape(len(objects), -1)
     results.obj_rows = obj_rows
     return results
 

@@ -292,7 +292,8 @@ def dropin_call_ms(device, iters=5):
         return extract.format_extraction(res)
 
     with torch.cuda.device(device):
-        call()
+        for _ in range(4):  # (the third call with the same shapes captures the CUDA graph that later calls replay)
+            call()
         t0 = time.perf_counter()
         for _ in range(iters):
             table = call()

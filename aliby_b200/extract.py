@@ -52,6 +52,7 @@ class ItemTuple(Sequence):
 
     plan: "engine.Plan | None" = None
     counts: "dict | None" = None  # plane key ((tile,) or (tile, stack)) -> number of ids enumerated for it
+    label_stack: "np.ndarray | None" = None  # (tiles, Y, X) uint16 stack of the masks, when process_tree_masks made one
 
     def __init__(self, objects: list, instructions: list):
         self.objects = objects
@@ -147,7 +148,8 @@ def _graphed(key, build):
 
 
 def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
-    """planes: list of (Y, X) arrays; pixels: (tiles, C, Z, Y, X) ndarray / tensor / TileView."""
+    """planes: list of (Y, X) arrays, or the (P, Y, X) uint16 stack of them; pixels: (tiles, C, Z, Y, X) ndarray / tensor /
+    TileView."""
     import torch
 
     from .tile import TileView
@@ -159,7 +161,7 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
         raise plan.error
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    host_labels = _host_label_stack(planes)
+    host_labels = planes if isinstance(planes, np.ndarray) else _host_label_stack(planes)
     # ---- small calls of repeating shapes: replay a captured graph (engine.GraphedExtract) ----
     if (_graphs_enabled() and n_objects <= _GRAPH_MAX_OBJECTS and plan.n_columns and plan.requests
             and isinstance(pixels, (np.ndarray, TileView)) and str(pixels.dtype) in ("uint8", "uint16")
@@ -465,11 +467,21 @@ def process_tree_masks(
     instructions = kv(flatten(tree))
     ind_masks = []
     counts = {}
+    stack = None
+    if len(masks) > 1 and all(isinstance(m, np.ndarray) and m.ndim == 2 and m.size and m.shape == masks[0].shape for m in masks):
+        # many small tiles (a time point of a trap position): one stack, one reduction for all the maxima — and the
+        # stack is what goes to the device afterwards
+        try:
+            stack = _host_label_stack(masks)
+            maxima = stack.reshape(len(masks), -1).max(axis=1).tolist()
+        except OverflowError:
+            stack = None
     for tile_i, masks_in_tile in enumerate(masks):
         if len(masks_in_tile):
-            counts[(tile_i,)] = k = int(masks_in_tile.max())
+            counts[(tile_i,)] = k = int(maxima[tile_i] if stack is not None else masks_in_tile.max())
             ind_masks.extend(zip(repeat(tile_i, k), range(1, k + 1)))
     tileid_instructions = ItemTuple(ind_masks, instructions)
+    tileid_instructions.label_stack = stack
     tileid_instructions.plan = engine.compile_cached(instructions, cp_measure_kwargs)
     tileid_instructions.counts = counts
     extra = {}
@@ -584,7 +596,10 @@ def extract_tree(
                 n_labels.append(int(plane.max()) if plane.size else 0)
     n_labels = np.asarray(n_labels, dtype=np.int64)
     base = np.concatenate([[0], np.cumsum(n_labels)])
-    dense = _run_dense(plan, planes, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels)
+    stack = getattr(tileid_instructions, "label_stack", None) if counts is not None and not overlap else None
+    if stack is not None and len(stack) != len(planes):
+        stack = None
+    dense = _run_dense(plan, planes if stack is None else stack, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels)
 
     if counts is not None:
         # the objects are the ids 1..k of every plane in plane order: row = position, no per-object Python work

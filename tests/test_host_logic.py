@@ -30,6 +30,14 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(nat.ObjectRec) == 48 and ctypes.sizeof(nat.Request) == 16 and ctypes.sizeof(nat.Column) == 8 and ctypes.sizeof(nat.Pair) == 24
 
 
+def test_graft_entry_build_runs_on_cpu():
+    """The driver's "does it build" hook: compiles (or finds) the library, checks its ABI version, imports the oracles."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+
+    __graft_entry__.build()
+
+
 def test_abi_rejects_bad_arguments_without_a_gpu():
     from aliby_b200 import _native as nat
 

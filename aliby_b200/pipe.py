@@ -40,14 +40,14 @@ def _init_extract(step_name: str, parameters: dict, *, overlap: bool = False):
     return partial(process, measure_fn=measure_fn, tree=parameters["tree"], **parameters.get("kwargs", {}))
 
 
-def _split_multi_tree(tree: dict, cp_measure_kwargs=None):
-    """``(ours, theirs)``: the branches of an extractmulti tree with and without a CUDA kernel (same nesting)."""
+def _split_tree(tree: dict, cp_measure_kwargs=None):
+    """``(ours, theirs)``: the branches of an extract / extractmulti tree with and without a CUDA kernel (same nesting)."""
     from . import engine
 
     ours: dict = {}
     theirs: dict = {}
     for inst in engine.kv(engine.flatten(tree)):
-        ok = len(inst) == 4 and engine.compile_instructions([inst], cp_measure_kwargs).error is None
+        ok = engine.compile_instructions([inst], cp_measure_kwargs).error is None
         node = ours if ok else theirs
         for key in inst[:-2]:
             node = node.setdefault(key, {})
@@ -55,36 +55,47 @@ def _split_multi_tree(tree: dict, cp_measure_kwargs=None):
     return ours, theirs
 
 
-def _init_extract_multi(step_name: str, parameters: dict, other_steps: dict | None = None):
-    """``extractmulti_*`` steps (pipe.py:65-66, pipe_core.py:84-92): ``partial(process_tree_masks,
-    measure_fn=extract_tree_multi, tree=..., **kwargs)`` on the GPU.
+_split_multi_tree = _split_tree
 
-    A tree that also names two-image features without a kernel (``costes``, which the stock builder requests,
-    pipe_builder.py:19-43) is split: our kernels measure their part, the reference's own step — when ALIBY is importable —
-    measures the rest with the same arguments, and the two ``(instructions, results)`` lists are concatenated
-    (``format_extraction`` pivots by (tile, label) and sorts the columns, so the table is the one the reference builds).
-    Without the reference the step raises at its first call with objects, naming the feature."""
-    if "tree" not in parameters:
-        raise ValueError(f"Step '{step_name}' is missing required 'tree'.")
+
+def _split_step(step_name: str, parameters: dict, other_steps: dict | None, make_gpu_step, why: str):
+    """A step whose tree names features without a kernel next to features with one: our kernels measure their part, the
+    reference's own step — when ALIBY is importable — measures the rest with the same arguments, and the two
+    ``(instructions, results)`` lists are concatenated.  ``format_extraction`` pivots by (tile, label) and sorts the
+    columns (extract.py:574-598), so the table is the one the reference builds.  Without the reference the whole tree
+    stays with us and raises at its first call with objects, naming the feature."""
     kwargs = dict(parameters.get("kwargs", {}))
-    ours, theirs = _split_multi_tree(parameters["tree"], kwargs.get("cp_measure_kwargs"))
+    ours, theirs = _split_tree(parameters["tree"], kwargs.get("cp_measure_kwargs"))
     if not theirs:
-        return partial(process_tree_masks, measure_fn=extract_tree_multi, tree=parameters["tree"], **kwargs)
+        return make_gpu_step(parameters["tree"], kwargs)
     try:
-        reference_step = _reference_init_step(step_name, {**parameters, "tree": theirs}, other_steps,
-                                              "names two-image features without a CUDA kernel")
+        reference_step = _reference_init_step(step_name, {**parameters, "tree": theirs}, other_steps, why)
     except ImportError:
-        return partial(process_tree_masks, measure_fn=extract_tree_multi, tree=parameters["tree"], **kwargs)
+        return make_gpu_step(parameters["tree"], kwargs)
     if not ours:
         return reference_step
-    gpu_step = partial(process_tree_masks, measure_fn=extract_tree_multi, tree=ours, **kwargs)
+    gpu_step = make_gpu_step(ours, kwargs)
 
     def split_step(masks, pixels, **kw):
+        from .tile import TileView
+
         items_a, res_a = gpu_step(masks=masks, pixels=pixels, **kw)
-        items_b, res_b = reference_step(masks=masks, pixels=pixels, **kw)
+        # (the reference indexes pixels[tile, channel]: a fused tile view is materialised for it)
+        items_b, res_b = reference_step(masks=masks, pixels=np.asarray(pixels) if isinstance(pixels, TileView) else pixels, **kw)
         return tuple(items_a) + tuple(items_b), list(res_a) + list(res_b)
 
     return split_step
+
+
+def _init_extract_multi(step_name: str, parameters: dict, other_steps: dict | None = None):
+    """``extractmulti_*`` steps (pipe.py:65-66, pipe_core.py:84-92): ``partial(process_tree_masks,
+    measure_fn=extract_tree_multi, tree=..., **kwargs)`` on the GPU; two-image features without a kernel (``costes``,
+    which the stock builder requests, pipe_builder.py:19-43) go to the reference's step (:func:`_split_step`)."""
+    if "tree" not in parameters:
+        raise ValueError(f"Step '{step_name}' is missing required 'tree'.")
+    return _split_step(step_name, parameters, other_steps,
+                       lambda tree, kwargs: partial(process_tree_masks, measure_fn=extract_tree_multi, tree=tree, **kwargs),
+                       "names two-image features without a CUDA kernel")
 
 
 def _reference_init_step(step_name: str, parameters: dict, other_steps: dict | None, why: str):
@@ -118,21 +129,16 @@ def _init_tile(step_name: str, parameters: dict, other_steps: dict | None):
 def init_step(step_name: str, parameters: dict, other_steps: dict | None = None, *, overlap: bool = False):
     """Drop-in ``init_step_fn``: ours for ``extract_*`` and ``tile*``, the reference's for everything else.
 
-    An ``extract_*`` step whose tree names a metric without a CUDA kernel (cp_measure features beyond ``intensity`` /
-    ``sizeshape``, decided here with the plan compiler) goes to the reference's own implementation when ALIBY is
-    importable, and so do the branches of an ``extractmulti_*`` tree without a kernel (:func:`_init_extract_multi`);
+    The branches of an ``extract_*`` / ``extractmulti_*`` tree that name a metric without a CUDA kernel (cp_measure
+    features beyond ``intensity`` / ``sizeshape`` / the four two-image features, decided here with the plan compiler) go
+    to the reference's own step when ALIBY is importable, the rest of the tree runs on the GPU (:func:`_split_step`);
     otherwise the error names the metric — there is no CPU fallback inside this package."""
     if step_name.startswith("extract_"):
-        if "tree" in parameters:
-            from . import engine
-
-            err = engine.compile_tree(parameters["tree"], parameters.get("kwargs", {}).get("cp_measure_kwargs")).error
-            if isinstance(err, KeyError):
-                try:
-                    return _reference_init_step(step_name, parameters, other_steps, f"asks for {err} which has no CUDA kernel")
-                except ImportError:
-                    pass  # the step then raises KeyError(metric) at its first call with objects, like the reference would
-        return _init_extract(step_name, parameters, overlap=overlap)
+        if "tree" not in parameters or overlap:
+            return _init_extract(step_name, parameters, overlap=overlap)
+        return _split_step(step_name, parameters, other_steps,
+                           lambda tree, kwargs: _init_extract(step_name, {"tree": tree, "kwargs": kwargs}),
+                           "names features without a CUDA kernel")
     if step_name.startswith("extractmulti_"):
         return _init_extract_multi(step_name, parameters, other_steps)
     if step_name.startswith("tile"):

@@ -337,6 +337,36 @@ def test_stock_pipeline_steps_initialise():
         step(masks=np.ones((8, 8), np.uint16), pixels=np.zeros((1, 1, 1, 8, 8), np.uint16))
 
 
+def test_default_builder_tree_is_split_between_the_gpu_and_the_reference(monkeypatch):
+    """The DEFAULT feature list of build_pipeline_steps (pipe_builder.py:49-56: radial_zernikes, intensity, feret, texture,
+    radial_distribution, zernike; sizeshape on the masks): with the reference importable the seam keeps the branches that
+    have a kernel and hands the others to the reference's own step built from the same parameters."""
+    from aliby_b200 import pipe
+
+    default = ("radial_zernikes", "intensity", "feret", "texture", "radial_distribution", "zernike")
+    kw = {"ncores": None, "cp_measure_kwargs": {"intensity": {"edge_measurements": False}}}
+    tree = {"None": {"None": ("sizeshape",)}, 1: {"max": default}, 0: {"max": default}}
+    ours, theirs = pipe._split_tree(tree, kw["cp_measure_kwargs"])
+    assert ours == {"None": {"None": ["sizeshape"]}, 1: {"max": ["intensity"]}, 0: {"max": ["intensity"]}}
+    rest = ["radial_zernikes", "feret", "texture", "radial_distribution", "zernike"]
+    assert theirs == {1: {"max": rest}, 0: {"max": rest}}
+    # without the kwargs the edge features of `intensity` are wanted: no kernel, the whole feature goes to the reference
+    assert pipe._split_tree(tree)[1][1]["max"] == list(default)
+    seen = {}
+
+    def fake_reference_init_step(step_name, parameters, other_steps, why):
+        seen["step"], seen["tree"], seen["kwargs"] = step_name, parameters["tree"], parameters["kwargs"]
+        return lambda masks, pixels, **kw_: ((("ref-item",),), ["ref-result"])
+
+    monkeypatch.setattr(pipe, "_reference_init_step", fake_reference_init_step)
+    step = pipe.init_step("extract_nuclei", {"tree": tree, "kwargs": kw})
+    assert seen == {"step": "extract_nuclei", "tree": theirs, "kwargs": kw} and step.__name__ == "split_step"
+    # a tree the kernels cover completely never asks for the reference
+    monkeypatch.setattr(pipe, "_reference_init_step", lambda *a, **k: (_ for _ in ()).throw(AssertionError("not needed")))
+    whole = pipe.init_step("extract_nuclei", {"tree": ours, "kwargs": kw})
+    assert whole.func.__name__ == "process_tree_masks" and whole.keywords["tree"] == ours
+
+
 def test_ctypes_mirrors_match_the_c_header(tmp_path):
     """Field offsets / sizes of the ctypes mirrors == what a C compiler lays out for include/aliby_b200.h."""
     import shutil

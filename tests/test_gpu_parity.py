@@ -873,6 +873,13 @@ def test_extractmulti_colocalisation(ab):
     for c in table.column_names:
         x, y = table.column(c).to_pylist(), plain.column(c).to_pylist()
         assert all((p == q) or (p != p and q != q) for p, q in zip(x, y)), c
+    # the dense fast entry names and fills the same columns
+    fast_table = ab.extract_table(tree, labels, pixels)
+    arrow = fast_table.to_arrow()
+    assert arrow.column_names == table.column_names
+    for c in table.column_names:
+        x, y = table.column(c).to_pylist(), arrow.column(c).to_pylist()
+        assert all((p == q) or (p != p and q != q) for p, q in zip(x, y)), c
     # a Z stack (max), several tiles, uint8, a different threshold, a subset of the features
     kw = {"manders_fold": {"thr": 40}}
     tiles = [synth.make_field(930 + t, (96, 128), 2, 6, n_z=3, semi_axes=(3, 12)) for t in range(3)]

@@ -43,6 +43,10 @@ int abx_validate(const abx_extract_args* a) {
     if (a->row_stride < 1 || a->row_stride >= (1LL << 25))
       return abx_set_error(ABX_ERR_INVALID, "pixel row stride %lld outside [1, 2^25)", (long long)a->row_stride);
     if (a->pixel_dtype == ABX_U16 && a->Z > 65536) return abx_set_error(ABX_ERR_INVALID, "Z too large for 32-bit sums");
+    if ((a->request_feature_union & (int)(ABX_F_CPQ | ABX_F_CPMAD)) && a->pixel_dtype != ABX_U8 && a->pixel_dtype != ABX_U16)
+      return abx_set_error(ABX_ERR_UNSUPPORTED,
+                           "cp_measure intensity statistics have a kernel for uint8/uint16 pixels only (pixel dtype %d); there is no "
+                           "CPU fallback", a->pixel_dtype);
   }
   if (a->n_pairs < 0) return abx_set_error(ABX_ERR_INVALID, "negative count");
   if (a->n_pairs > 0) {
@@ -247,7 +251,10 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   }
   if (hp) cudaEventRecord(hp->join, hp->stream);
   mark(3);
-  if ((rc = launch_object_stats(args, ws, st))) return rc;  // the rest (large objects, background)
+  // the rest (large objects, background) — every object when cp_measure rank statistics are wanted in a layout the sweep
+  // kernel cannot address (the gather kernel has none; this one reads with plain loads, any layout, any reduction)
+  const bool cp_all = !sweep && (args->request_feature_union & (int)(ABX_F_CPQ | ABX_F_CPMAD)) != 0;
+  if ((rc = launch_object_stats(args, ws, st, cp_all))) return rc;
   if ((rc = launch_big_background(args, ws, st))) return rc;  // backgrounds of large planes: streaming histogram
   if ((rc = launch_object_float(args, ws, st))) return rc;  // floating-point requests (float pixels, `div`)
   if (args->n_pairs > 0) {  // two-image features: they start from the minima / maxima of both requests

@@ -135,7 +135,7 @@ int launch_object_sweep(const abx_extract_args* a, const Workspace& ws, cudaStre
 bool abx_sweep_ok(const abx_extract_args* a);
 int launch_object_stats_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool todo);
 int launch_object_edt_warp(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
-int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
+int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool all_objects);
 int launch_shape_edt(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_float(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);
 int launch_object_pair(const abx_extract_args* a, const Workspace& ws, cudaStream_t st);  // after every statistics kernel

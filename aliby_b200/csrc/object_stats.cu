@@ -41,6 +41,7 @@ struct Smem {
   u64 t_below_sum[4];
   u32 r_key[4], r_rank[4], r_cnt[4];
   u64 r_sum[4];
+  u64 redpos[kWarps];  // (max value << 32) | ~position: the first maximum in row-major order
 };
 static_assert(kWarps == 4, "one warp per selection target during refinement");
 
@@ -148,14 +149,20 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
                     const i64* __restrict__ tile_offset, i64 chan_stride, i64 z_stride, i64 px_row_stride, int Z,
                     const abx_request* __restrict__ requests, int n_requests,
                     const abx_object_rec* __restrict__ recs, ChanStats* __restrict__ out,
-                    const int* __restrict__ work_list, const u32* __restrict__ work_count, int big_background) {
+                    const int* __restrict__ work_list, const u32* __restrict__ work_count, int big_background,
+                    int all_objects, u32* __restrict__ err) {
   __shared__ Smem s;
   const u32 lane = lane_id(), warp = threadIdx.x >> 5;
   constexpr u32 kWrapMask = (sizeof(PX) == 1) ? 0xFFu : 0xFFFFu;
 
-  const u32 n_work = *work_count;  // objects handed over by the warp-per-object kernel
+  // objects handed over by the plan / warp-per-object kernel; or EVERY object: cp_measure rank statistics in a layout
+  // the sweep kernel cannot address (this kernel reads with plain loads and recomputes the whole record)
+  const u32 n_work = all_objects ? (u32)n_total : *work_count;
+  if (all_objects && blockIdx.x == 0 && threadIdx.x == 0)
+    for (int q = 0; q < n_requests; ++q)  // the float kernel has no rank statistics: status bit 1
+      if ((requests[q].features & (ABX_F_CPQ | ABX_F_CPMAD)) && requests[q].reduction == ABX_RED_DIV) atomicOr(err, 2u);
   for (u32 wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-    const int obj = work_list[wi];
+    const int obj = all_objects ? (int)wi : work_list[wi];
     __syncthreads();  // previous object's smem is dead
     if (threadIdx.x == 0) {
       const bool bg = obj >= n_objects;
@@ -200,8 +207,10 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
       // ---- sweep 1: moments, extrema, compaction ----
       u64 a_sum = 0, a_sq = 0, a_wrap = 0, a_m10 = 0, a_m01 = 0, a_m20 = 0, a_m02 = 0;
       u32 a_min = 0xFFFFFFFFu, a_max = 0;
+      u64 a_pos = 0;  // (value << 32) | ~((row << 16) | col): its maximum is the first maximum in row-major order
       sweep_window(w, [&](bool hit, u32 x, u32 r, u32 c) {
         if (hit) {
+          a_pos = max(a_pos, ((u64)x << 32) | (u64)(0xFFFFFFFFu - (((r - w.rmin) << 16) | (c - w.cmin))));
           a_sum += x;
           const u64 xx = (u64)x * (u64)x;
           a_sq += xx;
@@ -230,13 +239,19 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
         for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
         a_min = __reduce_min_sync(0xFFFFFFFFu, a_min);
         a_max = __reduce_max_sync(0xFFFFFFFFu, a_max);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a_pos = max(a_pos, __shfl_xor_sync(0xFFFFFFFFu, a_pos, o));
         if (lane == 0) {
 #pragma unroll
           for (int k = 0; k < 7; ++k) s.red[warp][k] = v[k];
           s.redmin[warp] = a_min; s.redmax[warp] = a_max;
+          s.redpos[warp] = a_pos;
         }
       }
       __syncthreads();
+      u64 pos = 0;
+      for (int ww = 0; ww < kWarps; ++ww) pos = max(pos, s.redpos[ww]);
+      const u32 first_max_pos = 0xFFFFFFFFu - (u32)pos;
       u64 tot[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) { tot[k] = 0; for (int ww = 0; ww < kWarps; ++ww) tot[k] += s.red[ww][k]; }
@@ -247,67 +262,72 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
       cs.sum = tot[0]; cs.sumsq = tot[1]; cs.wrapsq = tot[2];
       cs.m10 = tot[3]; cs.m01 = tot[4]; cs.m20 = tot[5]; cs.m02 = tot[6];
       cs.vmin = vmin; cs.vmax = vmax; cs.med_lo = cs.med_hi = 0; cs.top2p5_sum = cs.top5_sum = 0;
+      cs.q[0] = cs.q[1] = cs.q[2] = cs.q[3] = cs.q[4] = cs.q[5] = 0; cs.mad_lo = cs.mad_hi = 0; cs.maxpos = 0; cs.pad_ = 0;
 
-      if (feats & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) {
-        // ---- sweep 2: range-adaptive histogram ----
-        const u32 range = vmax - vmin;
+      // ---- order statistics: range-adaptive histogram of xf(x) in [lo, hi], four ranks at a time ----
+      //   histogram of (xf(x) - lo) >> s with s chosen so that the range fits 1024 bins (s = 0: exact), then 8 more bits
+      //   per sweep inside the (up to four) target bins.  Leaves the exact-level prefix data in s.t_*; returns s.
+      auto select4 = [&](const u32 (&rk)[4], auto xf, u32 lo, u32 hi, u32 (&value)[4]) -> int {
+        const u32 range = hi - lo;
         int s0 = 0;
         while ((range >> s0) >= (u32)kBins) ++s0;
         const u32 nb = (range >> s0) + 1;
+        __syncthreads();  // the histogram and the targets of an earlier selection have been consumed
         for (u32 b = threadIdx.x; b < nb; b += kThreads) s.hist[b] = 0;
         __syncthreads();
-        for_each_value(w, s, compact, n, [&](u32 x) { atomicAdd(&s.hist[(x - vmin) >> s0], 1u); });
+        for_each_value(w, s, compact, n, [&](u32 x) { atomicAdd(&s.hist[(xf(x) - lo) >> s0], 1u); });
         __syncthreads();
+        if (warp == 0) warp_find_rank(s.hist, nb, lo, rk, 4, s.t_key, s.t_rank, s.t_below_cnt, s.t_below_sum);
+        __syncthreads();
+        int cur = s0;
+        while (cur > 0) {
+          const int nxt = cur > 8 ? cur - 8 : 0;
+          const u32 nsub = 1u << (cur - nxt);
+          const u32 k0 = s.t_key[0], k1 = s.t_key[1], k2 = s.t_key[2], k3 = s.t_key[3];
+          __syncthreads();  // everyone has read the keys and finished with hist
+          for (u32 b = threadIdx.x; b < 4u * 256u; b += kThreads) s.hist[b] = 0;
+          __syncthreads();
+          for_each_value(w, s, compact, n, [&](u32 x) {
+            const u32 d = xf(x) - lo;
+            const u32 hi_bits = d >> cur;
+            const u32 sb = (d >> nxt) & (nsub - 1u);
+            if (hi_bits == k0) atomicAdd(&s.hist[sb], 1u);
+            if (hi_bits == k1) atomicAdd(&s.hist[256 + sb], 1u);
+            if (hi_bits == k2) atomicAdd(&s.hist[512 + sb], 1u);
+            if (hi_bits == k3) atomicAdd(&s.hist[768 + sb], 1u);
+          });
+          __syncthreads();
+          {  // warp j refines target j (kWarps == 4)
+            const u32 j = warp;
+            const u32 want = s.t_rank[j];
+            const u32 oldkey = s.t_key[j];
+            warp_find_rank(s.hist + 256 * j, nsub, 0u, &want, 1, &s.r_key[j], &s.r_rank[j], &s.r_cnt[j], &s.r_sum[j]);
+            __syncwarp();
+            if (lane == 0) {
+              s.t_key[j] = (oldkey << (cur - nxt)) | s.r_key[j];
+              s.t_rank[j] = s.r_rank[j];
+            }
+          }
+          __syncthreads();
+          cur = nxt;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) value[j] = lo + s.t_key[j];
+        return s0;
+      };
+      const auto identity = [](u32 x) { return x; };
+
+      if (feats & (ABX_F_MEDIAN | ABX_F_TOP2P5 | ABX_F_TOP5)) {
         const u32 k2p5 = (u32)ceil((double)n * 0.025);  // int(np.ceil(n * 0.025)), cell.py:110-111
         const u32 k5 = min(n, 5u);
         const u32 ranks[4] = {(n - 1) / 2, n / 2, n - k2p5, n - k5};
-        if (warp == 0) {
-          warp_find_rank(s.hist, nb, vmin, ranks, 4, s.t_key, s.t_rank, s.t_below_cnt, s.t_below_sum);
-        }
-        __syncthreads();
         u32 value[4];
         u64 below_sum[2];  // sum of the values ranked below targets 2 and 3
+        const int s0 = select4(ranks, identity, vmin, vmax, value);
         if (s0 == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) value[j] = vmin + s.t_key[j];
           below_sum[0] = s.t_below_sum[2] + (u64)s.t_rank[2] * value[2];
           below_sum[1] = s.t_below_sum[3] + (u64)s.t_rank[3] * value[3];
         } else {
-          // ---- refinement: 8 more bits per sweep inside the four target bins ----
-          int cur = s0;
-          while (cur > 0) {
-            const int nxt = cur > 8 ? cur - 8 : 0;
-            const u32 nsub = 1u << (cur - nxt);
-            const u32 k0 = s.t_key[0], k1 = s.t_key[1], k2 = s.t_key[2], k3 = s.t_key[3];
-            __syncthreads();  // everyone has read the keys and finished with hist
-            for (u32 b = threadIdx.x; b < 4u * 256u; b += kThreads) s.hist[b] = 0;
-            __syncthreads();
-            for_each_value(w, s, compact, n, [&](u32 x) {
-              const u32 d = x - vmin;
-              const u32 hi = d >> cur;
-              const u32 sb = (d >> nxt) & (nsub - 1u);
-              if (hi == k0) atomicAdd(&s.hist[sb], 1u);
-              if (hi == k1) atomicAdd(&s.hist[256 + sb], 1u);
-              if (hi == k2) atomicAdd(&s.hist[512 + sb], 1u);
-              if (hi == k3) atomicAdd(&s.hist[768 + sb], 1u);
-            });
-            __syncthreads();
-            {  // warp j refines target j (kWarps == 4)
-              const u32 j = warp;
-              const u32 want = s.t_rank[j];
-              const u32 oldkey = s.t_key[j];
-              warp_find_rank(s.hist + 256 * j, nsub, 0u, &want, 1, &s.r_key[j], &s.r_rank[j], &s.r_cnt[j], &s.r_sum[j]);
-              __syncwarp();
-              if (lane == 0) {
-                s.t_key[j] = (oldkey << (cur - nxt)) | s.r_key[j];
-                s.t_rank[j] = s.r_rank[j];
-              }
-            }
-            __syncthreads();
-            cur = nxt;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) value[j] = vmin + s.t_key[j];
           // ---- exact sums below the two top-k thresholds ----
           u64 sb2 = 0, sb3 = 0;
           u32 cb2 = 0, cb3 = 0;
@@ -334,6 +354,34 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
         cs.top2p5_sum = cs.sum - below_sum[0];
         cs.top5_sum = cs.sum - below_sum[1];
       }
+      if (feats & (ABX_F_CPQ | ABX_F_CPMAD)) {
+        // ---- cp_measure `intensity` (the same records object_sweep.cu writes for window-sized objects): the order
+        // statistics i = floor(n f) and i + 1 for f = 1/4, 1/2, 3/4; the same pair of floor(|2 v - 2 median| / 2); the
+        // position of the first maximum ----
+        const u32 last = n - 1u;
+        const u32 i1 = n >> 2, i2 = n >> 1, i3 = (u32)((3ull * n) >> 2);
+        const u32 rb1[4] = {i1, min(i1 + 1u, last), i2, min(i2 + 1u, last)};
+        const u32 rb2[4] = {i3, min(i3 + 1u, last), i3, min(i3 + 1u, last)};
+        u32 v1[4], v2[4];
+        select4(rb1, identity, vmin, vmax, v1);
+        select4(rb2, identity, vmin, vmax, v2);
+        cs.q[0] = v1[0]; cs.q[1] = v1[1]; cs.q[2] = v1[2]; cs.q[3] = v1[3]; cs.q[4] = v2[0]; cs.q[5] = v2[1];
+        cs.mad_lo = cs.mad_hi = 0;
+        if (feats & ABX_F_CPMAD) {
+          // twice the median (an integer): f = 1/2 exactly when n is odd
+          const u64 med2 = ((n & 1u) && i2 < last) ? (u64)v1[2] + v1[3] : 2ull * v1[2];
+          const auto absdev = [med2](u32 x) {
+            const i64 d = 2ll * (i64)x - (i64)med2;
+            return (u32)((d < 0 ? -d : d) >> 1);
+          };
+          const u32 rmad[4] = {i2, min(i2 + 1u, last), i2, min(i2 + 1u, last)};
+          u32 vm[4];
+          select4(rmad, absdev, 0u, max(absdev(vmin), absdev(vmax)), vm);
+          cs.mad_lo = vm[0];
+          cs.mad_hi = vm[1] | ((u32)(med2 & 1ull) << 31);
+        }
+        cs.maxpos = first_max_pos;
+      }
       if (threadIdx.x == 0) *dst = cs;
       __syncthreads();  // smem reused by the next request
     }
@@ -342,7 +390,7 @@ object_stats_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i
 
 }  // namespace
 
-int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
+int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool all_objects) {
   if (a->n_requests == 0) return ABX_OK;
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0) return ABX_OK;
@@ -352,7 +400,8 @@ int launch_object_stats(const abx_extract_args* a, const Workspace& ws, cudaStre
       static_cast<const uint16_t*>(a->labels), a->label_plane_stride, a->label_row_stride, a->plane_tile,         \
       a->plane_base, a->n_planes, a->n_objects, n_total, static_cast<const PX*>(a->pixels),                       \
       reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride, a->row_stride, a->Z, a->requests, \
-      a->n_requests, ws.recs, ws.chan, ws.stats_list, ws.list_counts, (int)abx_big_background(a))
+      a->n_requests, ws.recs, ws.chan, ws.stats_list, ws.list_counts, (int)abx_big_background(a),           \
+      all_objects ? 1 : 0, ws.err)
   if (a->pixel_dtype == ABX_U16) ABX_LAUNCH_OS(uint16_t);
   else if (a->pixel_dtype == ABX_U8) ABX_LAUNCH_OS(uint8_t);
   else return ABX_OK;  // float pixels: every request belongs to object_float.cu

@@ -92,6 +92,7 @@ struct PlanArgs {
   u32* counts;      // Workspace::list_counts
   // cp_measure features
   int cp_requests;        // some request wants ABX_F_CPQ / ABX_F_CPMAD: only the sweep kernel computes those
+  const abx_request* requests;  // as the statistics kernels see them (zreduce.cu marks what it leaves to the gather pass as DIV)
   int want_moments;       // need_edt bit 2: second coordinate moments of every object, from its bitmap
   const u64* bitmaps;
   MaskMoments* mom;
@@ -111,6 +112,11 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
   const bool is_bg = i >= a.n_objects;
   const int h = (int)(rec.rmax - rec.rmin) + 1, w = (int)(rec.cmax - rec.cmin) + 1;
   const bool windowed = live && rec.n > 0 && !is_bg && h <= kSide && w <= kSide;
+  // cp_measure rank statistics exist in the sweep kernel and in the CTA-per-object kernel only: a request that goes to
+  // the float kernel (`div`) or to the gather pass on the sum planes of a Z stack (`add`) has none -> status bit 1
+  if (i == 0 && a.cp_requests)
+    for (int q = 0; q < a.n_requests; ++q)
+      if ((a.requests[q].features & (ABX_F_CPQ | ABX_F_CPMAD)) && a.requests[q].reduction == ABX_RED_DIV) atomicOr(a.err, 2u);
   // ---- statistics ----
   if (a.sweep) {
     bool take = false, too_wide = false;
@@ -139,7 +145,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
       }
     }
     append(take, rec.n > kBigFirst, i, a.order_stats, a.n_total, a.counts + kCntOrderBig, a.counts + kCntOrderSmall);
-    const bool hand = live && rec.n > 0 && !windowed;
+    // windows above 64 x 64 and backgrounds: the CTA-per-object kernel (object_stats.cu).  It also takes the (rare)
+    // window that starts in front of the buffer when cp_measure statistics are wanted: the gather kernel has none.
+    const bool hand = live && rec.n > 0 && (!windowed || (too_wide && a.cp_requests));
     {
       const u32 m = __ballot_sync(kFull, hand);
       u32 b = 0;
@@ -147,11 +155,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanArgs a) {
       b = __shfl_sync(kFull, b, 0);
       if (hand) a.stats_list[b + (u32)__popc(m & ((1u << lane_id()) - 1u))] = i;
     }
-    if (too_wide) {
+    if (too_wide && !a.cp_requests) {
       const u32 b = atomicAdd(a.counts + kCntLeftover, (u32)a.n_requests);  // rare: no aggregation
       for (int q = 0; q < a.n_requests; ++q) a.pair_list[b + q] = i * a.n_requests + q;
     }
-    if (a.cp_requests && ((hand && !is_bg) || too_wide)) atomicOr(a.err, 2u);  // status bit 1: cp statistics not served
   }
   // ---- second moments of the pixel coordinates (cp_measure sizeshape), relative to the bounding box origin ----
   if (a.want_moments && live && !is_bg) {
@@ -1008,10 +1015,6 @@ bool abx_sweep_ok(const abx_extract_args* a) {
 int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st, bool sweep) {
   const int n_total = a->n_objects + (a->with_background ? a->n_planes : 0);
   if (n_total == 0 || (!sweep && !a->need_edt)) return ABX_OK;
-  if (!sweep && (a->request_feature_union & (int)(ABX_F_CPQ | ABX_F_CPMAD)))
-    return abx_set_error(ABX_ERR_UNSUPPORTED,
-                         "cp_measure intensity statistics need uint8/uint16 pixels in a TMA-addressable layout (16-byte aligned rows, Z = 1 or a max "
-                         "reduction); there is no CPU fallback");
   PlanArgs p;
   p.recs = ws.recs;
   p.plane_base = a->plane_base;
@@ -1035,6 +1038,7 @@ int launch_plan(const abx_extract_args* a, const Workspace& ws, cudaStream_t st,
   p.edt_list = ws.edt_list;
   p.counts = ws.list_counts;
   p.cp_requests = (a->request_feature_union & (int)(ABX_F_CPQ | ABX_F_CPMAD)) != 0;
+  p.requests = a->requests;
   p.want_moments = (a->need_edt & 4) != 0;
   p.bitmaps = ws.bitmaps;
   p.mom = ws.mom;

@@ -349,9 +349,8 @@ def raise_on_status(word: int) -> None:
         )
     if int(word) & 2:
         raise NotImplementedError(
-            "cp_measure 'intensity' met an object the sweep kernel does not serve (a bounding box above 64 x 64 pixels, or a "
-            "pixel layout the TMA unit cannot address): its quartiles / MAD / maximum position have no CUDA kernel and "
-            "there is no CPU fallback"
+            "cp_measure 'intensity' was requested under the `div` reducer or the `add` reducer of a Z stack: the kernels "
+            "that serve those have no quartiles / MAD / maximum position and there is no CPU fallback"
         )
     if int(word) & 4:
         raise NotImplementedError(
@@ -482,8 +481,14 @@ def run_planes(
     a.request_feature_union = nat.F_HAS_DIV if any(r[1] == nat.RED_DIV for r in plan.requests) else 0
     for r in plan.requests:
         a.request_feature_union |= int(r[2]) | int(r[3])
-    if a.request_feature_union & (nat.F_CPQ | nat.F_CPMAD) and a.pixel_dtype not in (nat.U8, nat.U16):
-        raise NotImplementedError("cp_measure 'intensity' has a CUDA kernel for uint8/uint16 pixels only; there is no CPU fallback")
+    if a.request_feature_union & (nat.F_CPQ | nat.F_CPMAD):
+        if a.pixel_dtype not in (nat.U8, nat.U16):
+            raise NotImplementedError("cp_measure 'intensity' has a CUDA kernel for uint8/uint16 pixels only; there is no CPU fallback")
+        for r in plan.requests:
+            if int(r[2]) & (nat.F_CPQ | nat.F_CPMAD) and (r[1] == nat.RED_DIV or (r[1] == nat.RED_ADD and a.Z > 1)):
+                raise NotImplementedError(
+                    "cp_measure 'intensity' of a Z stack has a CUDA kernel for the `max` reduction only (`add` sums and "
+                    "`div` quotients take kernels without its rank statistics); there is no CPU fallback")
     if plan.requests:  # extent of the pixel buffer behind data_ptr(), for the TMA description of it
         a.pixel_elems = (pixels.untyped_storage().nbytes() // pixels.element_size()) - pixels.storage_offset()
     pairs_t = plan.device_pairs(device)

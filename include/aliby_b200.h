@@ -93,8 +93,10 @@ typedef enum abx_metric {
   /* cp_measure `intensity` (loaders.py:71-73,135-150; CellProfiler MeasureObjectIntensity without the edge features).
    * Integrated / Mean / Std / Min / Max are ABX_M_TOTAL / MEAN / STD / MIN / MAX.  Quartiles, median and MAD follow
    * CellProfiler's rank rule (i = floor(n f), linear interpolation to i + 1), not np.median.  Positions are 0-based
-   * plane coordinates.  Needs a pixel request; computed by the sweep kernel only (window <= 64 x 64, TMA-addressable
-   * layout): anything else sets status bit 1. */
+   * plane coordinates.  Needs a pixel request of uint8 / uint16 pixels (ABX_ERR_UNSUPPORTED otherwise).  Objects of any
+   * size and any layout: the sweep kernel for windows <= 64 x 64 in a TMA-addressable layout, the CTA-per-object kernel
+   * for everything else.  A request under the `div` reducer, or under `add` on the reduced planes of a Z stack, is served
+   * by kernels without these statistics: status bit 1. */
   ABX_M_CP_LOWER_QUARTILE = 32,
   ABX_M_CP_MEDIAN = 33,
   ABX_M_CP_UPPER_QUARTILE = 34,
@@ -227,8 +229,8 @@ typedef struct abx_extract_args {
    * the table (copy it back together with the table).  Bit 0: a label above its plane's n_labels
    * (plane_base[p + 1] - plane_base[p]) was met — those pixels belong to no row of the table and the background
    * statistics of that plane are not meaningful; the caller passed a stale or wrong plane_base.  Bit 1: an
-   * ABX_M_CP_* intensity column was requested for an object that the sweep kernel does not serve (window above
-   * 64 x 64, or a chunked window with a wide value range): that cell of the table is not meaningful.  Bit 2: an
+   * ABX_M_CP_* rank statistic (quartiles, MAD, maximum position) was requested of a request that a kernel without them
+   * serves — the `div` reducer, or the `add` reducer of a Z stack: those cells are not meaningful.  Bit 2: an
    * ABX_M_CO_* column met an object with values of 65536 or more (a Z-add of a stack): that cell is NaN. */
   uint32_t* status;
   /* optional (ABI 4): pairs of requests for the ABX_M_CO_* columns */

@@ -801,13 +801,33 @@ def test_cp_measure_intensity_and_sizeshape(ab):
         ab.process_tree_masks(tree, labels, pixels, ab.extract_tree)
     with pytest.raises(KeyError, match="radial_zernikes"):
         ab.process_tree_masks({0: {"max": ("radial_zernikes",)}}, labels, pixels, ab.extract_tree)
-    # an object above the 64 x 64 window has no kernel for the rank statistics: the call says so instead of returning them
+    # objects above the 64 x 64 window (the CTA-per-object kernel): narrow and full value ranges, odd and even areas, a
+    # whole-plane object; plus sizeshape of the same masks
     wide = np.zeros((160, 200), np.uint16)
     wide[20:100, 30:130] = 1
-    with pytest.raises(NotImplementedError, match="64 x 64"):
-        ab.process_tree_masks({0: {"max": ("intensity",)}}, wide, pixels[:, :, :, :160, :200], ab.extract_tree, cp_measure_kwargs=kw)
-    items_w, got_w = ab.process_tree_masks({"None": {"None": ("sizeshape",)}}, wide, pixels[:, :, :, :160, :200], ab.extract_tree)
-    _check_cp(items_w, got_w, _cpm_reference({"None": {"None": ("sizeshape",)}}, wide, pixels[:, :, :, :160, :200], {}))
+    wide[100:159, 3:190] = 2
+    wide[101, 5] = 0  # (an odd area)
+    wide[4:12, 150:199] = 4  # id 3 absent
+    tree_w = {"None": {"None": ("sizeshape",)}, 0: {"max": ("intensity",)}, 1: {"max": ("intensity", "median")}}
+    for px in (pixels[:, :, :, :160, :200], rng.integers(0, 65536, size=(1, 2, 1, 160, 200)).astype(np.uint16),
+               rng.integers(0, 256, size=(1, 2, 1, 160, 200)).astype(np.uint8)):
+        items_w, got_w = ab.process_tree_masks(tree_w, wide, px, ab.extract_tree, cp_measure_kwargs=kw)
+        want_w = _cpm_reference({"None": {"None": ("sizeshape",)}, 0: {"max": ("intensity",)}, 1: {"max": ("intensity",)}}, wide, px, kw)
+        dict_w = [(it, g) for it, g in zip(items_w, got_w) if isinstance(g, dict)]
+        _check_cp([it for it, _ in dict_w], [g for _, g in dict_w], want_w)
+    whole = np.ones((96, 128), np.uint16)
+    px_whole = rng.integers(0, 4000, size=(1, 1, 1, 96, 128)).astype(np.uint16)
+    items_p, got_p = ab.process_tree_masks({0: {"max": ("intensity",)}}, whole, px_whole, ab.extract_tree, cp_measure_kwargs=kw)
+    _check_cp(items_p, got_p, _cpm_reference({0: {"max": ("intensity",)}}, whole, px_whole, kw))
+    # rank statistics of a Z stack exist for the `max` reduction only: `add` says so instead of returning them
+    stack = rng.integers(0, 3000, size=(1, 1, 3, 96, 128)).astype(np.uint16)
+    items_z, got_z = ab.process_tree_masks({0: {"max": ("intensity",)}}, whole, stack, ab.extract_tree, cp_measure_kwargs=kw)
+    _check_cp(items_z, got_z, _cpm_reference({0: {"max": ("intensity",)}}, whole, stack, kw))
+    with pytest.raises(NotImplementedError, match="add"):
+        ab.process_tree_masks({0: {"add": ("intensity",)}}, whole, stack, ab.extract_tree, cp_measure_kwargs=kw)
+    px_z, lab_z = synth.make_field(4900, (128, 192), 2, 12, n_z=3, semi_axes=(3, 14))  # window-sized cells of a Z stack
+    items_z, got_z = ab.process_tree_masks({1: {"max": ("intensity",)}}, lab_z, px_z, ab.extract_tree, cp_measure_kwargs=kw)
+    _check_cp(items_z, got_z, _cpm_reference({1: {"max": ("intensity",)}}, lab_z, px_z, kw))
 
 
 def _colocalisation_reference(tree, masks, pixels, cp_kwargs=None):

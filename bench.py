@@ -72,6 +72,16 @@ def _make(seed):
     from aliby_b200 import synth
 
     px, lab = synth.make_field(seed, FIELD, N_CHANNELS, N_OBJECTS)
+    if os.environ.get("ABX_RELABEL") == "raster":  # experiment: ids in raster order of the objects' first pixel
+        n = int(lab.max())
+        first = np.full(n + 1, lab.size, dtype=np.int64)
+        flat = lab.ravel()
+        idx = np.flatnonzero(flat)
+        np.minimum.at(first, flat[idx], idx)
+        order = np.argsort(first[1:], kind="stable")
+        lut = np.zeros(n + 1, dtype=lab.dtype)
+        lut[order + 1] = np.arange(1, n + 1, dtype=lab.dtype)
+        lab = lut[lab]
     return px[0], lab
 
 

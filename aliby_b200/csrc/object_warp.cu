@@ -3,10 +3,10 @@
 // object_stats_warp covers, for one object, everything the reference computes with |instructions| full-plane passes
 // (src/extraction/extract.py:346-359): the intensity statistics of every (channel, Z-reduction) request
 // (cell.py:43-157,232-265; distributors.py:19-21 fused into the load; tile crop of tiler.py:309-366 fused through the
-// tile offset).  It is the twin of object_stats_tma (object_tma.cu, TMA-staged windows) and runs
+// tile offset).  It is the twin of object_sweep (object_sweep.cu, TMA-staged windows) and runs
 //   (a) for whole launches whose layout TMA cannot address (unaligned bases / row strides, planes narrower than 64,
 //       Z stacks whose rows are not 16-byte multiples),
-//   (b) as one work item per (object, request) for the few objects object_stats_tma leaves over,
+//   (b) as one work item per (object, request) for the few objects object_sweep leaves over,
 //   (c) on the uint32 sum planes of Z-add requests (zreduce.cu).
 //
 //   phase M  label window -> compact list of the object's pixel offsets ((r << 6) | c, row-major) from warp ballots:

@@ -1,4 +1,4 @@
-// Device helpers shared by the warp-per-object kernels (object_warp.cu, object_tma.cu).  Include inside the
+// Device helpers shared by the warp-per-object kernels (object_warp.cu, object_sweep.cu, object_edt.cu, object_pair.cu).  Include inside the
 // translation unit's anonymous namespace after common.cuh.
 #pragma once
 

@@ -933,6 +933,51 @@ def test_extractmulti_colocalisation(ab):
     _check_colocalisation(items3, got3, _colocalisation_reference(tree3, lab, small))
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_cp_measure_and_pairs(ab, seed):
+    """Randomised planes for the cp_measure features and the two-image features: odd plane sizes (rows that are not
+    16-byte multiples: the CTA-per-object kernel serves every object), aligned ones (the sweep kernel), blocks, rings and
+    ellipses up to 150 px, salt-and-pepper ids, id gaps, several tiles, uint8 / uint16, narrow and full value ranges,
+    Z in {1, 2, 3} under `max`."""
+    from aliby_b200 import synth
+
+    rng = np.random.default_rng(9100 + seed)
+    aligned = seed % 2 == 0
+    H = int(rng.integers(64, 180))
+    W = 16 * int(rng.integers(5, 14)) if aligned else int(rng.integers(65, 230))
+    n_tiles = int(rng.integers(1, 4))
+    Z = 1 if seed < 4 else int(rng.integers(2, 4))
+    dtype = np.uint8 if seed % 4 == 1 else np.uint16
+    top = np.iinfo(dtype).max
+    masks = []
+    for _ in range(n_tiles):
+        lab = synth.ellipse_labels(rng, (H, W), int(rng.integers(0, 8)), semi_axes=(3, 28)).astype(np.uint16)
+        next_id = int(lab.max()) + 1
+        for _ in range(int(rng.integers(1, 6))):
+            h, w = int(rng.integers(1, min(H, 150))), int(rng.integers(1, min(W, 150)))
+            r, c = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+            lab[r : r + h, c : c + w] = next_id
+            if h > 8 and w > 8 and rng.random() < 0.4:
+                lab[r + 3 : r + h - 3, c + 3 : c + w - 3] = 0
+            next_id += int(rng.integers(1, 3))
+        speck = rng.random((H, W)) < 0.01
+        lab[speck] = rng.integers(1, next_id + 2, size=int(speck.sum()))
+        masks.append(lab)
+    if seed % 3 == 0:
+        base = rng.integers(0, max(2, top // 2), size=(n_tiles, 3, 1, 1, 1))
+        pixels = np.clip(base + rng.poisson(30, size=(n_tiles, 3, Z, H, W)), 0, top).astype(dtype)
+    else:
+        pixels = rng.integers(0, top + 1, size=(n_tiles, 3, Z, H, W)).astype(dtype)
+    kw = {"intensity": {"edge_measurements": False}, "manders_fold": {"thr": int(rng.integers(5, 60))}}
+    tree = {"None": {"None": ("sizeshape",)}, 2: {"max": ("intensity",)}, 0: {"max": ("intensity",)}}
+    m = masks if n_tiles > 1 else masks[0]
+    items, got = ab.process_tree_masks(tree, m, pixels, ab.extract_tree, cp_measure_kwargs=kw)
+    _check_cp(items, got, _cpm_reference(tree, m, pixels, kw))
+    multi = {(0, 1): {"None": {"max": ["pearson", "rwc"]}}, (2, 1): {"None": {"max": ["manders_fold", "overlap"]}}}
+    items, got = ab.process_tree_masks(multi, m, pixels, ab.extract_tree_multi, cp_measure_kwargs=kw)
+    _check_colocalisation(items, got, _colocalisation_reference(multi, m, pixels, kw))
+
+
 def test_extractmulti_step_splits_with_the_reference(ab, monkeypatch):
     """``init_step('extractmulti_*')`` (pipe.py:65-66): the branches with a kernel run on the GPU, the others (costes)
     go to the reference's step, and the concatenated result pivots into one table with every requested column."""

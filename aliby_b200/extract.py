@@ -439,8 +439,25 @@ def _results_from_dense(plan, dense, row_of_item, inst_of_item):
             return dense[row_of_item][:, cols].ravel().tolist()
         return dense[row_of_item, cols[inst_of_item]].tolist()
     if inst_of_item is None:
-        n_inst = len(plan.inst_cols)
-        row_of_item, inst_of_item = np.repeat(row_of_item, n_inst), np.tile(np.arange(n_inst), len(row_of_item))
+        # object-major product with dict- or tuple-valued metrics: one column block per instruction, cut into per-object
+        # values by C-level iteration (a (k, 1) view iterates into k arrays of length 1), then interleaved object-major
+        n_inst, n_obj = len(plan.inst_cols), len(row_of_item)
+        per_inst = []
+        for c, keys in zip(plan.inst_cols, plan.inst_keys):
+            if not len(c):
+                per_inst.append([None] * n_obj)  # (an instruction that failed to compile: plan.error was raised before)
+                continue
+            block = dense[row_of_item][:, list(c)]
+            if keys is not None:
+                per_inst.append([dict(zip(keys, sub)) for sub in block.reshape(n_obj, len(c), 1)])
+            elif len(c) == 1:
+                per_inst.append(block[:, 0].tolist())
+            else:
+                per_inst.append([tuple(v) for v in block.tolist()])
+        out = [None] * (n_obj * n_inst)
+        for i, vals in enumerate(per_inst):
+            out[i::n_inst] = vals
+        return out
     out = []
     for r, i in zip(row_of_item, inst_of_item):
         c, keys = plan.inst_cols[i], plan.inst_keys[i]

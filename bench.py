@@ -352,23 +352,28 @@ def ours(args):
     out_buf, out, status = engine.alloc_table(n_objects, plan.n_columns, device)
 
     # The per-field label maxima (masks.max() of extract.py:279) are part of every step: abx_label_max on a side stream,
-    # read back through pinned memory; the maxima of step k + 1 are found while the kernels of step k run, so the
-    # launch stream never waits for the host.
+    # read back through pinned memory.  The maxima of step k + 2 are found while the kernels of step k run (two buffers
+    # in rotation), so the launch stream never waits for the host and the host may fall up to two steps behind the GPU
+    # (a hiccup of the launching thread — the clock sampler's NVML queries take driver locks — does not drain the queue).
     side = torch.cuda.Stream(device=device)
-    nmax_host = torch.zeros(F, dtype=torch.int32).pin_memory()
-    nmax_ready = torch.cuda.Event()
+    nmax_host = [torch.zeros(F, dtype=torch.int32).pin_memory() for _ in range(2)]
+    nmax_ready = [torch.cuda.Event() for _ in range(2)]
+    step_no = [0]
 
-    def launch_label_max():
+    def launch_label_max(slot):
         with torch.cuda.stream(side):
-            nmax_host.copy_(extract._label_max(lab_dev, device), non_blocking=True)
-            nmax_ready.record(side)
+            nmax_host[slot].copy_(extract._label_max(lab_dev, device), non_blocking=True)
+            nmax_ready[slot].record(side)
 
-    launch_label_max()
+    launch_label_max(0)
+    launch_label_max(1)
 
     def step(events=None):
-        nmax_ready.synchronize()
-        n_lab = nmax_host.numpy().astype(np.int64)
-        launch_label_max()
+        slot = step_no[0] & 1
+        step_no[0] += 1
+        nmax_ready[slot].synchronize()
+        n_lab = nmax_host[slot].numpy().astype(np.int64)
+        launch_label_max(slot)  # for the step after the next one
         engine.run_planes(plan, lab_dev, plane_tile, n_lab, px_dev, offs, H * W, H * W, W, N_CHANNELS, 1,
                           out=out, stage_events=events, status=status)
 
@@ -418,7 +423,8 @@ def ours(args):
             lib.abx_event_destroy(h)
     stage_ms /= args.steps
     engine.raise_on_status(int(status.cpu()[0]))
-    assert np.array_equal(nmax_host.numpy().astype(np.int64), n_labels)
+    torch.cuda.synchronize()
+    assert all(np.array_equal(h.numpy().astype(np.int64), n_labels) for h in nmax_host)
 
     # ---- e2e leg: public API, pinned host inputs, H2D + D2H inside the timed region ----
     masks_host = [lab_pin[i].numpy() for i in range(F)]

@@ -158,10 +158,11 @@ extern "C" int abx_label_scan(const abx_extract_args* args, abx_object_rec* reco
                            static_cast<cudaStream_t>(args->stream));
 }
 
-// One helper stream and a fork / join event pair per (host thread, device), created on first use and kept.
+// Two helper streams and their fork / join events per (host thread, device), created on first use and kept.
 struct Helper {
-  cudaStream_t stream;
-  cudaEvent_t fork, join;
+  cudaStream_t stream;   // the shape chain
+  cudaStream_t stream2;  // the per-plane backgrounds
+  cudaEvent_t fork, join, join2;
 };
 static Helper* helper_stream() {
   static thread_local Helper helpers[64];
@@ -171,8 +172,10 @@ static Helper* helper_stream() {
   if (!made[dev]) {
     Helper h;
     if (cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h.stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h.join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.join2, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       return nullptr;
     }
@@ -224,12 +227,27 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   // small one (a time point of a yeast position: a few hundred objects, every kernel a few microseconds) halves its
   // chain of dependent launches.  With stage events (a profiling run) the two chains stay in line on the caller's
   // stream so that each stage can be timed on its own.
-  Helper* hp = (edt && !ev) ? helper_stream() : nullptr;
-  if (hp) {
-    cudaEventRecord(hp->fork, st);
+  // The per-plane backgrounds (label 0: labels, pixels and the scan's counts only) are a third independent chain, on a
+  // second helper stream: for a time point of a trap position they are the longest kernel of the call.
+  Helper* hp = !ev ? helper_stream() : nullptr;
+  const bool side_edt = hp && edt;
+  // (a small call that is launched eagerly is bound by the host's launch calls, not by its kernels: the extra stream
+  // operations would cost it more than the overlap returns — 0.089 -> 0.112 ms per C3 time point; replayed from a
+  // graph the same call gains, 0.075 -> 0.058 ms.  So: while the caller is capturing, or when the call is large.)
+  cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+  if (hp && cudaStreamIsCapturing(st, &capture) != cudaSuccess) { cudaGetLastError(); capture = cudaStreamCaptureStatusNone; }
+  const bool side_bg = hp && abx_big_background(args) && args->n_planes > 0 &&
+                       (capture == cudaStreamCaptureStatusActive || args->n_objects > 4096);
+  if (side_edt || side_bg) cudaEventRecord(hp->fork, st);
+  if (side_edt) {
     cudaStreamWaitEvent(hp->stream, hp->fork, 0);
     if ((rc = launch_object_edt_warp(args, ws, hp->stream))) return rc;
     if ((rc = launch_shape_edt(args, ws, hp->stream))) return rc;
+  }
+  if (side_bg) {
+    cudaStreamWaitEvent(hp->stream2, hp->fork, 0);
+    if ((rc = launch_big_background(args, ws, hp->stream2))) return rc;
+    cudaEventRecord(hp->join2, hp->stream2);
   }
   if (sweep) {
     if ((rc = launch_object_sweep(&red, ws, st))) return rc;
@@ -238,32 +256,33 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   }
   if (zred && (rc = launch_object_stats_rest(args, ws, st))) return rc;  // the Z-add requests, from their uint32 sum planes
   mark(2);
-  if (!hp && edt && (rc = launch_object_edt_warp(args, ws, st))) return rc;
-  // the few (object, request) pairs the sweep kernel left over (windows too wide at their alignment, wide value ranges
-  // of chunked windows): the gather kernel, one warp per CTA — behind the shape kernels on the helper stream when
-  // there is one (their cost is a few warps' latency: off the caller's chain)
+  if (!side_edt && edt && (rc = launch_object_edt_warp(args, ws, st))) return rc;
+  // the few (object, request) pairs the sweep kernel left over (a window that starts in front of the buffer): the
+  // gather kernel, one warp per CTA — behind the shape kernels on the helper stream when there is one (their cost is a
+  // few warps' latency: off the caller's chain)
   if (sweep) {
-    if (hp) {
+    if (side_edt) {
       cudaEventRecord(hp->fork, st);  // the sweep kernel has written the pair list
       cudaStreamWaitEvent(hp->stream, hp->fork, 0);
     }
-    if ((rc = launch_object_stats_warp(&red, ws, hp ? hp->stream : st, true))) return rc;
+    if ((rc = launch_object_stats_warp(&red, ws, side_edt ? hp->stream : st, true))) return rc;
   }
-  if (hp) cudaEventRecord(hp->join, hp->stream);
+  if (side_edt) cudaEventRecord(hp->join, hp->stream);
   mark(3);
-  // the rest (large objects, background) — every object when cp_measure rank statistics are wanted in a layout the sweep
-  // kernel cannot address (the gather kernel has none; this one reads with plain loads, any layout, any reduction)
+  // the rest (large objects, Z-add backgrounds) — every object when cp_measure rank statistics are wanted in a layout the
+  // sweep kernel cannot address (the gather kernel has none; this one reads with plain loads, any layout, any reduction)
   const bool cp_all = !sweep && (args->request_feature_union & (int)(ABX_F_CPQ | ABX_F_CPMAD)) != 0;
   if ((rc = launch_object_stats(args, ws, st, cp_all))) return rc;
-  if ((rc = launch_big_background(args, ws, st))) return rc;  // backgrounds of large planes: streaming histogram
+  if (!side_bg && (rc = launch_big_background(args, ws, st))) return rc;  // per-plane backgrounds: tile or streaming histogram
   if ((rc = launch_object_float(args, ws, st))) return rc;  // floating-point requests (float pixels, `div`)
   if (args->n_pairs > 0) {  // two-image features: they start from the minima / maxima of both requests
-    if (hp) cudaStreamWaitEvent(st, hp->join, 0);  // (the left-over pairs of the sweep kernel ran on the helper stream)
+    if (side_edt) cudaStreamWaitEvent(st, hp->join, 0);  // (the left-over pairs of the sweep kernel ran on the helper stream)
     if ((rc = launch_object_pair(args, ws, st))) return rc;
   }
-  if (!hp && (rc = launch_shape_edt(args, ws, st))) return rc;
+  if (!side_edt && (rc = launch_shape_edt(args, ws, st))) return rc;
   mark(4);
-  if (hp) cudaStreamWaitEvent(st, hp->join, 0);
+  if (side_edt) cudaStreamWaitEvent(st, hp->join, 0);
+  if (side_bg) cudaStreamWaitEvent(st, hp->join2, 0);
   if ((rc = launch_finalize(args, ws, st))) return rc;  // (also copies the error flags to args->status)
   mark(5);
   return ABX_OK;

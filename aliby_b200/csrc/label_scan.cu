@@ -105,7 +105,8 @@ __device__ __forceinline__ u32 bitpos_sum8(u32 m) {  // sum of the positions of 
   return (u32)__popc(m & 0xAAu) + 2u * (u32)__popc(m & 0xCCu) + 4u * (u32)__popc(m & 0xF0u);
 }
 
-// Column-strip walker.  A warp owns a band of kBandRows rows x 256 columns; lane l walks DOWN the
+// Column-strip walker.  A warp owns a band of band_rows (32; 16 or 8 for small launches, so that a time point of a few
+// tiles still fills the GPU with short walks) rows x 256 columns; lane l walks DOWN the
 // 8-pixel strip [c0, c0 + 8): one 128-bit cp.async per row brings the strip into the lane's private
 // shared-memory slots (the 32 lanes of a row form one coalesced 512-byte request; kRowBatch rows per
 // group, two groups in flight), and the object the lane is inside of lives in registers: a row whose
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kScanThreads)
 label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __restrict__ labels, int n_planes, int H, int W,
                   i64 plane_stride, i64 row_stride, const int32_t* __restrict__ plane_base,
                   abx_object_rec* __restrict__ recs, int n_objects, int vec_ok, u32* err, u64* __restrict__ bitmaps,
-                  int count_background) {
+                  int count_background, int band_rows) {
   __shared__ __align__(128) uint4 stage_all[kScanWarps][2][kRowBatch][32];  // 8 KB per warp
   __shared__ __align__(8) u64 bars[kScanWarps][2];
   const u32 lane = lane_id();
@@ -135,7 +136,7 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
   const i64 gwarp = (i64)blockIdx.x * kScanWarps + warp;
   const i64 nwarps = (i64)gridDim.x * kScanWarps;
   const int col_groups = (W + 255) >> 8;
-  const int bands = (H + kBandRows - 1) / kBandRows;
+  const int bands = (H + band_rows - 1) / band_rows;
   const i64 total = (i64)n_planes * bands * col_groups;
   u32 parity0 = 0, parity1 = 0;  // phase of the two mbarriers (warp-uniform)
   if (kTma) {
@@ -155,7 +156,7 @@ label_scan_kernel(const __grid_constant__ CUtensorMap tmap, const uint16_t* __re
     const u32 c0 = (u32)cg * 256u + lane * 8u;
     if (!kTma && c0 >= (u32)W) continue;  // (TMA: the whole warp stays converged; such lanes read zeros)
     const bool full = vec_ok && c0 + 8u <= (u32)W;  // aligned 128-bit copies are legal for this strip
-    const int r_begin = band * kBandRows, r_end = min(H, r_begin + kBandRows);
+    const int r_begin = band * band_rows, r_end = min(H, r_begin + band_rows);
     const uint16_t* src = labels + (i64)p * plane_stride + c0;
     const int base = plane_base[p];
     const u32 n_labels = (u32)(plane_base[p + 1] - base);
@@ -332,7 +333,11 @@ int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err,
   init_records_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(recs, a->n_objects, a->n_planes, a->H, a->W, err,
                                                                           reinterpret_cast<uint4*>(bitmaps), n_words, sqrt_tab,
                                                                           sqrt_tab ? n_sqrt : 0);
-  const i64 units = (i64)a->n_planes * ((a->H + kBandRows - 1) / kBandRows) * ((a->W + 255) / 256);
+  // rows per warp: 32, or fewer (a multiple of the 8-row load batch) while the launch has less than one unit per resident warp
+  int band_rows = kBandRows;
+  auto n_units = [&](int br) { return (i64)a->n_planes * ((a->H + br - 1) / br) * ((a->W + 255) / 256); };
+  while (band_rows > kRowBatch && n_units(band_rows) < 148 * 7 * kScanWarps) band_rows /= 2;
+  const i64 units = n_units(band_rows);
   if (units == 0) return abx_check_cuda(cudaGetLastError(), "init_records");
   i64 blocks = (units + kScanWarps - 1) / kScanWarps;
   const i64 cap = 148 * 7;  // 7 CTAs of 4 warps per SM (shared memory); more units are walked in a grid-stride loop
@@ -345,7 +350,7 @@ int launch_label_scan(const abx_extract_args* a, abx_object_rec* recs, u32* err,
 #define ABX_SCAN(TMA, BITS)                                                                                              \
   label_scan_kernel<TMA, BITS><<<(int)blocks, kScanThreads, 0, st>>>(                                                     \
       tm, static_cast<const uint16_t*>(a->labels), a->n_planes, a->H, a->W, a->label_plane_stride, a->label_row_stride,  \
-      a->plane_base, recs, a->n_objects, vec_ok, err, bitmaps, a->with_background)
+      a->plane_base, recs, a->n_objects, vec_ok, err, bitmaps, a->with_background, band_rows)
   if (tma && bitmaps) ABX_SCAN(true, true);
   else if (tma) ABX_SCAN(true, false);
   else if (bitmaps) ABX_SCAN(false, true);

@@ -33,7 +33,7 @@
  * hot call — size the scratch with abx_extract_workspace_bytes().  All strides and
  * offsets are in ELEMENTS of the addressed array.  Calls are re-entrant across
  * streams and devices as long as every call in flight has its own workspace.  State the library keeps: the
- * thread-local error string, and per (host thread, device) one helper stream with two events (created on first use,
+ * thread-local error string, and per (host thread, device) two helper streams with three events (created on first use,
  * kept for the life of the thread) and the cached encodings of the last call's TMA descriptors.
  */
 #ifndef ALIBY_B200_H

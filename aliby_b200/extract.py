@@ -98,9 +98,10 @@ def _host_label_stack(planes: list[np.ndarray]) -> np.ndarray:
     if all(isinstance(p, np.ndarray) and p.dtype == np.uint16 and p.flags.c_contiguous for p in planes):
         if len(planes) == 1:
             return planes[0][None]
-        run = _contiguous_run(planes)
-        if run is not None:
-            return run
+        if planes[0].nbytes >= (1 << 19):  # (small tiles: stacking them costs less than checking their addresses)
+            run = _contiguous_run(planes)
+            if run is not None:
+                return run
     stack = np.stack(planes)
     if stack.dtype != np.uint16:
         if stack.size and (stack.min() < 0 or stack.max() > 65535):
@@ -595,7 +596,16 @@ def extract_tree(
 
     # label planes: one per tile, or one per (tile, stack) for overlapping masks
     planes, plane_tile, n_labels, plane_of = [], [], [], {}
-    for tile_i, m in enumerate(masks):
+    stack = getattr(tileid_instructions, "label_stack", None) if counts is not None and not overlap else None
+    if stack is not None and len(stack) == len(counts) == len(masks):
+        # process_tree_masks stacked every tile and counted its ids: nothing to look at again
+        plane_of = dict(zip(counts, range(len(counts))))
+        plane_tile = list(range(len(masks)))
+        n_labels = list(counts.values())
+        planes = stack
+    else:
+        stack = None
+    for tile_i, m in enumerate(masks if stack is None else ()):
         if not len(m):
             continue
         stacks = list(m) if overlap else [m]
@@ -613,10 +623,7 @@ def extract_tree(
                 n_labels.append(int(plane.max()) if plane.size else 0)
     n_labels = np.asarray(n_labels, dtype=np.int64)
     base = np.concatenate([[0], np.cumsum(n_labels)])
-    stack = getattr(tileid_instructions, "label_stack", None) if counts is not None and not overlap else None
-    if stack is not None and len(stack) != len(planes):
-        stack = None
-    dense = _run_dense(plan, planes if stack is None else stack, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels)
+    dense = _run_dense(plan, planes, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels)
 
     if counts is not None:
         # the objects are the ids 1..k of every plane in plane order: row = position, no per-object Python work

@@ -112,7 +112,7 @@ bg_select_kernel(const u32* __restrict__ hist, const abx_request* __restrict__ r
 // thread in flight) and parked in shared memory; their range then sizes the histogram — packed 16-bit counters, a plane
 // has at most 16 384 pixels — so that zeroing and scanning it cost what the value range costs, not 65 536 bins.
 constexpr int kTilePixels = (int)kBigBackground;  // 16 384
-constexpr int kChunkValues = 16384;               // values one histogram round covers
+constexpr int kChunkValues = 8192;                // values one histogram round covers (16 KB of packed counters)
 
 template <typename PX>
 __global__ void __launch_bounds__(kThreads)
@@ -120,10 +120,12 @@ bg_tile_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i64 la
                const int32_t* __restrict__ plane_tile, int H, int W, const PX* __restrict__ pixels,
                const i64* __restrict__ tile_offset, i64 chan_stride, i64 z_stride, i64 px_row_stride, int Z,
                const abx_request* __restrict__ requests, int n_requests, int n_objects,
-               const abx_object_rec* __restrict__ recs, ChanStats* __restrict__ out) {
+               const abx_object_rec* __restrict__ recs, ChanStats* __restrict__ out, int px_slots) {
+  // shared memory sized by the launch for the planes' pixel count (px_slots = H W rounded up to 16): a 96 x 96 tile
+  // takes 16 + 18 + 9 KB and five CTAs share an SM
   extern __shared__ __align__(16) u32 h32[];                                      // kChunkValues / 2 words
-  unsigned short* vals = reinterpret_cast<unsigned short*>(h32 + kChunkValues / 2);  // [kTilePixels]
-  unsigned char* isbg = reinterpret_cast<unsigned char*>(vals + kTilePixels);   // [kTilePixels]
+  unsigned short* vals = reinterpret_cast<unsigned short*>(h32 + kChunkValues / 2);  // [px_slots]
+  unsigned char* isbg = reinterpret_cast<unsigned char*>(vals + px_slots);      // [px_slots]
   __shared__ u32 part[kThreads];
   __shared__ u32 s_lo[kThreads / 32], s_hi[kThreads / 32];
   __shared__ u32 s_med[2], s_total;
@@ -148,6 +150,7 @@ bg_tile_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i64 la
   const int n_px = H * W;
   // ---- the background values, once ----
   u32 lo = 0xFFFFFFFFu, hi = 0;
+  const u32 inv_w = 0xFFFFFFFFu / (u32)W + 1u;  // row of pixel i = umulhi(i, inv_w): exact for i < 2^32 / W (n_px <= 16 384)
   for (int base = 0; base < n_px; base += kThreads * 8) {
     int idx[8];
     bool bg[8];
@@ -156,7 +159,7 @@ bg_tile_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i64 la
     for (int u = 0; u < 8; ++u) {
       idx[u] = base + u * kThreads + tid;
       const int i = idx[u] < n_px ? idx[u] : 0;
-      const int r = i / W, c = i - r * W;
+      const int r = (int)__umulhi((u32)i, inv_w), c = i - r * W;
       bg[u] = idx[u] < n_px && __ldg(lab + (i64)r * lab_row_stride + c) == 0;
       src[u] = px + (i64)r * px_row_stride + c;
     }
@@ -182,7 +185,7 @@ bg_tile_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i64 la
   for (int k = 0; k < kThreads / 32; ++k) { lo = min(lo, s_lo[k]); hi = max(hi, s_hi[k]); }
   const u32 ranks[2] = {(n - 1) / 2, n / 2};
   const u32 top_from = n - (n < 5u ? n : 5u);  // elements with rank >= top_from are the (up to) five largest
-  // The histogram covers kChunkValues values at a time (32 KB of packed counters: two CTAs per SM); wider ranges —
+  // The histogram covers kChunkValues values at a time (16 KB of packed counters); wider ranges —
   // rare for a background — take several rounds over the parked values, in value order, with a running rank.
   u32 acc0 = 0;  // background pixels below the current chunk (block-uniform)
   for (u32 cmin = lo & ~1u; cmin <= hi; cmin += (u32)kChunkValues) {
@@ -208,15 +211,22 @@ bg_tile_kernel(const uint16_t* __restrict__ labels, i64 lab_plane_stride, i64 la
       const int w = w0 + j;
       if (w < words) { const u32 v = h32[w]; cnt += (v & 0xFFFFu) + (v >> 16); }
     }
-    part[tid] = cnt;
-    __syncthreads();
-    if (tid == 0) {  // exclusive prefix over the partial counts; tiny
-      u32 acc = acc0;
-      for (int t = 0; t < kThreads; ++t) { const u32 c = part[t]; part[t] = acc; acc += c; }
-      s_total = acc;
+    // exclusive prefix over the 256 partial counts: warp scans, then the warps' totals
+    u32 incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((tid & 31) >= o) incl += t;
     }
+    if ((tid & 31) == 31) part[tid >> 5] = incl;
     __syncthreads();
-    const u32 below = part[tid];
+    u32 below = acc0 + incl - cnt, total = acc0;
+    for (int k = 0; k < kThreads / 32; ++k) {
+      const u32 t = part[k];
+      if (k < (tid >> 5)) below += t;
+      total += t;
+    }
+    if (tid == 0) s_total = total;
     if (cnt > 0 && ((ranks[0] >= below && ranks[0] < below + cnt) || (ranks[1] >= below && ranks[1] < below + cnt) ||
                     below + cnt > top_from)) {
       u32 acc = below;
@@ -269,12 +279,14 @@ size_t abx_big_background_bytes(const abx_extract_args* a) {
 
 template <typename PX>
 static int launch_tile_background(const abx_extract_args* a, const Workspace& ws, cudaStream_t st) {
-  constexpr size_t smem = (size_t)kChunkValues * 2 + (size_t)kTilePixels * 3;  // 16-bit counters | u16 values | flags
+  constexpr size_t smem_max = (size_t)kChunkValues * 2 + (size_t)kTilePixels * 3;  // 16-bit counters | u16 values | flags
+  const int px_slots = (a->H * a->W + 15) & ~15;
+  const size_t smem = (size_t)kChunkValues * 2 + (size_t)px_slots * 3;
   static thread_local bool done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(bg_tile_kernel<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bg_tile_kernel<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return abx_check_cuda(e, "bg_tile smem attribute");
     done[dev] = true;
   }
@@ -282,7 +294,7 @@ static int launch_tile_background(const abx_extract_args* a, const Workspace& ws
   bg_tile_kernel<PX><<<dim3(a->n_planes, a->n_requests), kThreads, smem, st>>>(
       static_cast<const uint16_t*>(a->labels), a->label_plane_stride, a->label_row_stride, a->plane_tile, a->H, a->W,
       static_cast<const PX*>(a->pixels), reinterpret_cast<const i64*>(a->tile_offset), a->chan_stride, a->z_stride,
-      a->row_stride, a->Z, a->requests, a->n_requests, a->n_objects, ws.recs, ws.chan);
+      a->row_stride, a->Z, a->requests, a->n_requests, a->n_objects, ws.recs, ws.chan, px_slots);
   return abx_check_cuda(cudaGetLastError(), "bg_tile");
 }
 

@@ -192,6 +192,7 @@ def compile_tree(tree: dict, cp_measure_kwargs=None) -> Plan:
 
 
 _plan_cache: dict = {}
+_plan_cache_lock = __import__("threading").Lock()
 
 
 def compile_cached(instructions: list, cp_measure_kwargs=None) -> Plan:
@@ -203,9 +204,11 @@ def compile_cached(instructions: list, cp_measure_kwargs=None) -> Plan:
     except TypeError:  # an unhashable instruction: compile it for the error message it deserves
         return compile_instructions(instructions, cp_measure_kwargs)
     if plan is None:
-        if len(_plan_cache) >= 64:
-            _plan_cache.pop(next(iter(_plan_cache)))
-        plan = _plan_cache[key] = compile_instructions(instructions, cp_measure_kwargs)
+        plan = compile_instructions(instructions, cp_measure_kwargs)
+        with _plan_cache_lock:  # (two threads may both compile a new tree; the cache keeps one of the plans)
+            if len(_plan_cache) >= 64:
+                _plan_cache.pop(next(iter(_plan_cache)))
+            plan = _plan_cache.setdefault(key, plan)
     return plan
 
 

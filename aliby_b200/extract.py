@@ -122,6 +122,7 @@ _GRAPH_MAX_OBJECTS = 8192   # above this the launches are no longer what the cal
 _GRAPH_AFTER_CALLS = 2      # eager calls with the same shapes before a graph is captured
 _graph_seen: dict = {}
 _graph_cache: dict = {}
+_graph_lock = __import__("threading").Lock()
 
 
 def _graphs_enabled() -> bool:
@@ -142,9 +143,13 @@ def _graphed(key, build):
     _graph_seen[key] = seen
     if seen <= _GRAPH_AFTER_CALLS:
         return None
-    while len(_graph_cache) >= 8:
-        _graph_cache.pop(next(iter(_graph_cache)))
-    g = _graph_cache[key] = build()
+    g = build()
+    with _graph_lock:  # (entries are per thread, the dictionaries are shared)
+        while len(_graph_cache) >= 8:
+            _graph_cache.pop(next(iter(_graph_cache)))
+        if len(_graph_seen) > 256:
+            _graph_seen.clear()
+        _graph_cache[key] = g
     return g
 
 
@@ -184,7 +189,7 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
         key = (str(device), tuple(plan.instructions), (P, H, W), tuple(np.asarray(plane_tile).tolist()), layout)
         cur = _graph_cache.get((__import__("threading").get_ident(), *key))
         if cur is not None and cur.cap < int(n_labels.max()):  # more labels than captured: a larger instance
-            _graph_cache.pop((__import__("threading").get_ident(), *key))
+            _graph_cache.pop((__import__("threading").get_ident(), *key), None)
             cur = None
         g = cur or _graphed(key, lambda: engine.GraphedExtract(
             plan, P, H, W, plane_tile, layout[0], getattr(torch, layout[1]), offs, layout[3], layout[4], layout[5],

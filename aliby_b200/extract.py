@@ -200,7 +200,8 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
             n_cells = g.P * g.cap * plan.n_columns
             engine.raise_on_status(host[n_cells:].view(torch.int32)[0])
             return host[:n_cells].view(g.P * g.cap, plan.n_columns).numpy()[g.rows(n_labels)]
-    labels_dev = torch.from_numpy(host_labels).to(device, non_blocking=True)
+    labels_dev = torch.empty(host_labels.shape, dtype=torch.uint16, device=device)
+    engine.host_to_device(labels_dev, host_labels, slot="labels")
     if isinstance(pixels, TileView):
         px_dev, offs, cs, zs, rs, C_, Z_ = pixels.addressing(device)
     else:
@@ -211,7 +212,9 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
                         f"pixel dtype {pixels.dtype} has no CUDA kernel in aliby_b200 "
                         "(uint8/uint16/float32/float64) and there is no CPU fallback"
                     )
-                px_dev = torch.from_numpy(np.ascontiguousarray(pixels)).to(device, non_blocking=True)
+                px_host = np.ascontiguousarray(pixels)
+                px_dev = torch.empty(px_host.shape, dtype=getattr(torch, str(px_host.dtype)), device=device)
+                engine.host_to_device(px_dev, px_host)
             else:
                 px_dev = torch.empty(0, dtype=torch.uint16, device=device)
         else:

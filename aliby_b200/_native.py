@@ -95,6 +95,7 @@ EXPORTS = (
     "abx_label_max",
     "abx_crop_tiles",
     "abx_crop_tiles_padded",
+    "abx_host_is_pinned",
     "abx_event_create",
     "abx_event_destroy",
     "abx_event_elapsed_ms",
@@ -205,6 +206,7 @@ def lib() -> C.CDLL:
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
     ]
+    handle.abx_host_is_pinned.argtypes = [C.c_void_p]
     handle.abx_event_create.argtypes = [C.POINTER(C.c_void_p)]
     handle.abx_event_destroy.argtypes = [C.c_void_p]
     handle.abx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]

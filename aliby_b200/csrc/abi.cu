@@ -288,6 +288,16 @@ extern "C" int abx_extract(const abx_extract_args* args) {
   return ABX_OK;
 }
 
+extern "C" int abx_host_is_pinned(const void* ptr) {
+  cudaPointerAttributes attr;
+  const cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return abx_check_cuda(e, "cudaPointerGetAttributes");
+  }
+  return attr.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 extern "C" int abx_event_create(void** event) {
   if (!event) return abx_set_error(ABX_ERR_INVALID, "event is NULL");
   cudaEvent_t e;

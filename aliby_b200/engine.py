@@ -551,8 +551,9 @@ def host_to_device(dst, src, slot: str = "pixels"):
 
     t = src if isinstance(src, torch.Tensor) else torch.from_numpy(src)
     nbytes = t.numel() * t.element_size()
-    if (t.is_pinned() or nbytes < _UPLOAD_MIN_BYTES or nbytes > _UPLOAD_MAX_BYTES or not t.is_contiguous()
-            or not dst.is_contiguous()):
+    # (the driver knows whether the memory is page-locked; a tensor made from a NumPy view of a pinned buffer does not)
+    if (nbytes < _UPLOAD_MIN_BYTES or nbytes > _UPLOAD_MAX_BYTES or not t.is_contiguous() or not dst.is_contiguous()
+            or nat.lib().abx_host_is_pinned(t.data_ptr()) != 0):
         dst.copy_(t, non_blocking=True)
         return
     key = (slot, t.dtype, str(dst.device))

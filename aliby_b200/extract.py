@@ -326,10 +326,10 @@ def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
         planes = [_host_u16(masks[t]) for t in keep]
         run = _contiguous_run(planes)
         if run is not None:  # the planes are slices of one array: one copy instead of one per plane
-            lab.copy_(torch.from_numpy(run), non_blocking=True)
+            engine.host_to_device(lab, run, slot="labels")
         else:
             for j, plane in enumerate(planes):
-                lab[j].copy_(torch.from_numpy(plane), non_blocking=True)
+                engine.host_to_device(lab[j], plane, slot="labels")
         ev_lab = torch.cuda.Event()
         ev_lab.record(cps)
         for tiles in chunks:
@@ -337,7 +337,7 @@ def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
                 consecutive = tiles == list(range(tiles[0], tiles[0] + len(tiles)))
                 src = pixels[tiles[0] : tiles[0] + len(tiles)] if consecutive else pixels[tiles]
                 px = torch.empty(src.shape, dtype=getattr(torch, str(src.dtype)), device=device)
-                px.copy_(torch.from_numpy(np.ascontiguousarray(src)), non_blocking=True)
+                engine.host_to_device(px, np.ascontiguousarray(src))
             else:
                 px = torch.empty(0, dtype=torch.uint16, device=device)
             ev = torch.cuda.Event()

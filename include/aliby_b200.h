@@ -270,6 +270,11 @@ int abx_crop_tiles_padded(const void* frame, int32_t dtype, int32_t C, int32_t Z
                           const int32_t* tile_origin /* [n_tiles][2] */, int32_t n_tiles, int32_t h, int32_t w,
                           void* out, void* stream);
 
+/* 1 when `ptr` points into page-locked (pinned or registered) host memory, 0 for pageable host memory, < 0 on error.
+ * The host side uses it to decide between a direct asynchronous copy and staging through its own pinned buffers (a
+ * NumPy view of a pinned allocation is pinned whatever its wrapper reports). */
+int abx_host_is_pinned(const void* ptr);
+
 /* Timing events for abx_extract_args.stage_events (thin wrappers over cudaEvent_t). */
 int abx_event_create(void** event);
 int abx_event_destroy(void* event);

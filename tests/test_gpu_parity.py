@@ -978,6 +978,27 @@ def test_fuzz_cp_measure_and_pairs(ab, seed):
     _check_colocalisation(items, got, _colocalisation_reference(multi, m, pixels, kw))
 
 
+def test_host_uploads_pinned_and_pageable(ab):
+    """engine.host_to_device: page-locked memory is recognised through the driver (a NumPy view of a pinned tensor is
+    pinned, a fresh array is not) and both routes — direct asynchronous copy, staging by threads — deliver the bytes."""
+    import torch
+
+    from aliby_b200 import _native as nat
+    from aliby_b200 import engine
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    pageable = rng.integers(0, 65536, size=(3, 1500, 1501), dtype=np.uint16)  # 13.5 MB: several staging chunks
+    pinned = torch.from_numpy(pageable).pin_memory().numpy()
+    assert nat.lib().abx_host_is_pinned(pinned.ctypes.data) == 1 and nat.lib().abx_host_is_pinned(pinned[1:].ctypes.data) == 1
+    assert nat.lib().abx_host_is_pinned(pageable.ctypes.data) == 0
+    for src in (pageable, pinned, pageable[:, :64], pageable[1]):
+        dst = torch.empty(src.shape, dtype=torch.uint16, device=dev)
+        for _ in range(2):  # the second round reuses the staging buffer
+            engine.host_to_device(dst, np.ascontiguousarray(src))
+        assert np.array_equal(dst.cpu().numpy(), src)
+
+
 def test_extractmulti_step_splits_with_the_reference(ab, monkeypatch):
     """``init_step('extractmulti_*')`` (pipe.py:65-66): the branches with a kernel run on the GPU, the others (costes)
     go to the reference's step, and the concatenated result pivots into one table with every requested column."""

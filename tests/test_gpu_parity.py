@@ -978,6 +978,21 @@ def test_fuzz_cp_measure_and_pairs(ab, seed):
     _check_colocalisation(items, got, _colocalisation_reference(multi, m, pixels, kw))
 
 
+def test_extractmulti_many_channels(ab):
+    """Nine channels: more requests than the per-object kernel stages (8), so every pair takes the CTA-per-pair kernel;
+    narrow values, so its rank tables are small — the route that no other test takes."""
+    from aliby_b200 import synth
+
+    rng = np.random.default_rng(4242)
+    _, labels = synth.make_field(611, (160, 192), 1, 14, semi_axes=(3, 20))
+    base = rng.integers(100, 3000, size=(1, 9, 1, 1, 1))
+    pixels = (base + rng.poisson(25, size=(1, 9, 1, 160, 192))).astype(np.uint16)
+    pixels[0, 3] = pixels[0, 2] + rng.integers(0, 3, size=(1, 160, 192)).astype(np.uint16)  # nearly identical channels
+    tree = {(a, b): {"None": {"max": ["pearson", "rwc", "manders_fold"]}} for a, b in ((0, 8), (2, 3), (7, 1), (4, 5), (6, 0))}
+    items, got = ab.process_tree_masks(tree, labels, pixels, ab.extract_tree_multi)
+    _check_colocalisation(items, got, _colocalisation_reference(tree, labels, pixels))
+
+
 def test_host_uploads_pinned_and_pageable(ab):
     """engine.host_to_device: page-locked memory is recognised through the driver (a NumPy view of a pinned tensor is
     pinned, a fresh array is not) and both routes — direct asynchronous copy, staging by threads — deliver the bytes."""

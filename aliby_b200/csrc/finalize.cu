@@ -150,13 +150,17 @@ __device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const
     }
     switch (cd.metric) {
       case ABX_M_AREA: v = n; break;
-      case ABX_M_CENTROID_X: v = (double)r.sum_col / n; break;  // 0/0 -> NaN like NumPy
-      case ABX_M_CENTROID_Y: v = (double)r.sum_row / n; break;
+      // (an absent label is 0 / 0 = NaN in NumPy: said outright, the special-value subroutine of the fp64 division is long)
+      case ABX_M_CENTROID_X: if (r.n) v = (double)r.sum_col / n; break;
+      case ABX_M_CENTROID_Y: if (r.n) v = (double)r.sum_row / n; break;
       case ABX_M_SPHERICAL_VOLUME: {
         const double rad = sqrt(n / 3.141592653589793);
         v = (4.0 * 3.141592653589793 * (rad * rad * rad)) / 3.0;
       } break;
-      case ABX_M_ECCENTRICITY: v = sqrt(major * major - minor * minor) / major; break;
+      // (a round cell, major == minor, is sqrt(0) / major = +0: said outright for the same reason; 0 / 0 stays NaN)
+      case ABX_M_ECCENTRICITY:
+        if (major > 0.0) v = major == minor ? 0.0 : sqrt(major * major - minor * minor) / major;
+        break;
       case ABX_M_VOLUME: v = (4.0 * 3.141592653589793 * (minor * minor) * major) / 3.0; break;
       case ABX_M_CONICAL_VOLUME: v = 4.0 * shape[obj].sum_nn; break;
       case ABX_M_MINOR_AXIS: v = minor; break;
@@ -190,7 +194,7 @@ __device__ double finalize_cell(const abx_object_rec& r, int obj, int col, const
       case ABX_M_STD:
         if (r.n) {
           const unsigned __int128 num = (unsigned __int128)r.n * c.sumsq - (unsigned __int128)c.sum * c.sum;
-          v = sqrt(u128_to_double(num) / (n * n));
+          v = num == 0 ? 0.0 : sqrt(u128_to_double(num) / (n * n));  // (a constant cell: +0)
         }
         break;
       case ABX_M_MEDIAN: if (r.n) v = ((double)c.med_lo + (double)c.med_hi) / 2.0; break;

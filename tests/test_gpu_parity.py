@@ -437,6 +437,29 @@ def test_config_c3_trap_position_real_geometry(ab):
         check_items(items, got, as_float_pairs(want)[0])
 
 
+def test_many_tiles_in_one_call_backgrounds_on_their_own_stream(ab):
+    """Sixty time points x 40 tiles in ONE call (the batched form of C3: more than 4 096 objects, so the per-plane
+    backgrounds run on the second helper stream next to the statistics and the shape chain) against the oracle."""
+    from aliby_b200 import synth
+    from oracle import fast, port
+
+    T = 60
+    frames, centres, labels = synth.make_trap_position(31, n_tp=T, n_channels=2, frame=(700, 720), n_tiles=40, tile_size=96)
+    tree = {"None": {"None": ["area", "eccentricity"]}, 0: {"max": ["mean", "median", "imBackground", "background_max5"]},
+            1: {"max": ["std", "imBackground"]}}
+    masks = [labels[t, i] for t in range(T) for i in range(40)]
+    crops = np.concatenate([port.crop_tiles(frames[t], centres, (96, 96), (), t) for t in range(T)])
+    assert sum(int(m.max()) for m in masks) > 4096
+    table = ab.extract_table(tree, masks, crops)
+    o_items, want = fast.run_tree(tree, masks, crops)
+    wa = as_float_pairs(want)[0].reshape(len(table.objects), -1)
+    names = ["/".join(str(x) for x in i[1]) + "/" + i[1][-1] for i in o_items[: wa.shape[1]]]
+    assert names == table.names
+    loose = np.array([n.endswith("std") for n in names])
+    assert_same(table.values[:, ~loose], wa[:, ~loose], 0.0, "exact metrics")
+    assert_same(table.values[:, loose], wa[:, loose], RTOL_LOOSE, "fp64 metrics")
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_fuzz_random_label_planes(ab, seed):
     """Randomised planes that stress the scan and the window classes: salt-and-pepper labels (several ids inside

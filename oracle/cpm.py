@@ -7,7 +7,9 @@ installed here; the reference's tests pin no value at that boundary (SURVEY.md 8
 CellProfiler definitions that cp_measure wraps — MeasureObjectIntensity and MeasureObjectSizeShape — for one binary
 mask at a time, the way ``wrap_cp_measure_features`` calls them (``fun(mask.astype(uint16), pixels, **kw)`` ->
 ``{feature: ndarray of length 1}``).  Parity of the CUDA path with THIS file is self-defined; it is not parity with
-cp_measure.
+cp_measure.  What can be checked here is checked: ``tests/test_oracle_golden.py::test_cpm_oracle_against_scipy_ndimage``
+holds this file against the ``scipy.ndimage`` label functions CellProfiler itself calls (sum, mean, standard_deviation,
+minimum, maximum, maximum_position, center_of_mass), against ``numpy.corrcoef`` and ``scipy.stats.rankdata(dense)``.
 
 Conventions taken from CellProfiler:
 

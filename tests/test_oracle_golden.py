@@ -146,3 +146,64 @@ def test_fast_equals_port_on_c1_sample():
     _, a = port.run_tree(tree, labels, pixels)
     _, b = fast.run_tree(tree, labels, pixels)
     assert_same(as_float_pairs(b)[0], as_float_pairs(a)[0], 1e-12, "fast vs port")
+
+
+def test_cpm_oracle_against_scipy_ndimage():
+    """oracle/cpm.py is unpinned against cp_measure itself (its source is absent), but CellProfiler's
+    MeasureObjectIntensity / MeasureColocalization obtain their per-object sums, extrema, positions and deviations from
+    ``scipy.ndimage`` label functions — which ARE here: the restatement must agree with them on a labelled image, and
+    its rank rule with a direct sort."""
+    from scipy import ndimage
+
+    from oracle import cpm
+
+    rng = np.random.default_rng(11)
+    labels = np.zeros((60, 70), np.int32)
+    labels[5:25, 8:30] = 1
+    labels[30:55, 10:22] = 2
+    labels[28:40, 40:66] = 3
+    labels[12, 50] = 4
+    img = rng.integers(0, 4000, size=labels.shape).astype(np.uint16)
+    img2 = (img // 2 + rng.integers(0, 500, size=labels.shape)).astype(np.uint16)
+    idx = np.arange(1, 5)
+    f = img.astype(np.float64)
+    total, mean = ndimage.sum(f, labels, idx), ndimage.mean(f, labels, idx)
+    std, lo, hi = ndimage.standard_deviation(f, labels, idx), ndimage.minimum(f, labels, idx), ndimage.maximum(f, labels, idx)
+    maxpos = ndimage.maximum_position(f, labels, idx)
+    com = ndimage.center_of_mass(f, labels, idx)
+    geo = ndimage.center_of_mass(np.ones_like(f), labels, idx)
+    med = ndimage.median(f, labels, idx)
+    for k in idx:
+        got = {key: float(v[0]) for key, v in cpm.get_intensity(labels == k, img).items()}
+        assert got["Intensity_IntegratedIntensity"] == total[k - 1] and got["Intensity_MinIntensity"] == lo[k - 1]
+        assert got["Intensity_MaxIntensity"] == hi[k - 1]
+        assert abs(got["Intensity_MeanIntensity"] - mean[k - 1]) < 1e-9 and abs(got["Intensity_StdIntensity"] - std[k - 1]) < 1e-9
+        assert (got["Location_MaxIntensity_Y"], got["Location_MaxIntensity_X"]) == tuple(float(x) for x in maxpos[k - 1])
+        assert abs(got["Location_CenterMassIntensity_Y"] - com[k - 1][0]) < 1e-9
+        assert abs(got["Location_CenterMassIntensity_X"] - com[k - 1][1]) < 1e-9
+        want_disp = np.hypot(com[k - 1][0] - geo[k - 1][0], com[k - 1][1] - geo[k - 1][1])
+        assert abs(got["Intensity_MassDisplacement"] - want_disp) < 1e-9
+        # CellProfiler's rank rule against a direct sort; for an odd count it is the ordinary median shifted by half a step
+        v = np.sort(f[labels == k])
+        n = len(v)
+        for frac, key in ((0.25, "Intensity_LowerQuartileIntensity"), (0.5, "Intensity_MedianIntensity"),
+                          (0.75, "Intensity_UpperQuartileIntensity")):
+            q = n * frac
+            i = int(q)
+            want = v[i] * (1 - (q - i)) + v[i + 1] * (q - i) if i < n - 1 else v[min(i, n - 1)]
+            assert got[key] == want
+        if n % 2 == 0:
+            assert got["Intensity_MedianIntensity"] == v[n // 2] >= med[k - 1]  # upper of the two middle values
+        # two-image features: Pearson against numpy's own correlation, Manders against explicit sums
+        co = {key: float(x[0]) for key, x in cpm.get_correlation(img, img2, labels == k).items()}
+        a, b = f[labels == k], img2[labels == k].astype(np.float64)
+        if n > 1:
+            assert abs(co["Correlation_Pearson"] - np.corrcoef(a, b)[0, 1]) < 1e-9
+            both = (a >= 0.15 * a.max()) & (b >= 0.15 * b.max())
+            assert abs(co["Correlation_Manders_1"] - a[both].sum() / a[a >= 0.15 * a.max()].sum()) < 1e-12
+            from scipy.stats import rankdata
+
+            ra, rb = rankdata(a, method="dense") - 1, rankdata(b, method="dense") - 1
+            big_r = max(ra.max(), rb.max()) + 1
+            w = (big_r - np.abs(ra - rb)) / big_r
+            assert abs(co["Correlation_RWC_1"] - (a[both] * w[both]).sum() / a[a >= 0.15 * a.max()].sum()) < 1e-12

@@ -207,3 +207,18 @@ def test_cpm_oracle_against_scipy_ndimage():
             big_r = max(ra.max(), rb.max()) + 1
             w = (big_r - np.abs(ra - rb)) / big_r
             assert abs(co["Correlation_RWC_1"] - (a[both] * w[both]).sum() / a[a >= 0.15 * a.max()].sum()) < 1e-12
+        # size / shape: bounding box from ndimage.find_objects, centre from center_of_mass, axes from the eigenvalues of
+        # the coordinate covariance (numpy.linalg), radii from the distance transform of the padded mask
+        ss = {key: float(x[0]) for key, x in cpm.get_sizeshape(labels == k).items()}
+        sl = ndimage.find_objects((labels == k).astype(np.int32))[0]
+        assert (ss["AreaShape_BoundingBoxMinimum_Y"], ss["AreaShape_BoundingBoxMaximum_Y"]) == (sl[0].start, sl[0].stop)
+        assert (ss["AreaShape_BoundingBoxMinimum_X"], ss["AreaShape_BoundingBoxMaximum_X"]) == (sl[1].start, sl[1].stop)
+        assert ss["AreaShape_Area"] == n and abs(ss["AreaShape_Center_Y"] - geo[k - 1][0]) < 1e-9
+        rr, cc = np.nonzero(labels == k)
+        if n > 1:
+            lam = np.linalg.eigvalsh(np.cov(np.stack([rr, cc]).astype(np.float64), bias=True))
+            assert abs(ss["AreaShape_MajorAxisLength"] - 4 * np.sqrt(lam[1])) < 1e-9
+            assert abs(ss["AreaShape_MinorAxisLength"] - 4 * np.sqrt(max(lam[0], 0))) < 1e-9
+            assert abs(ss["AreaShape_Eccentricity"] - np.sqrt(1 - max(lam[0], 0) / lam[1])) < 1e-9
+        dist = ndimage.distance_transform_edt(np.pad(labels == k, 1))[1:-1, 1:-1][labels == k]
+        assert abs(ss["AreaShape_MaximumRadius"] - dist.max()) < 1e-12 and abs(ss["AreaShape_MeanRadius"] - dist.mean()) < 1e-12

@@ -407,7 +407,7 @@ def c5_sweep(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sharding.extract_sharded(tree, units[: world], lambda u: store.get(u, next(iter(store.values()))), gather=False)  # warm-up
+    sharding.extract_sharded(tree, units[: world], lambda u: store.get(u, next(iter(store.values()))))  # warm-up (with the gather)
     times = []
     out = None
     for _ in range(max(1, args.steps // 5)):

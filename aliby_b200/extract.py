@@ -366,7 +366,13 @@ def _pipelined_host_table(plan, masks, keep, pixels, device, chunk_bytes):
     cur.synchronize()
     for word in host[n_rows * n_cols :].view(torch.int32)[::2]:
         engine.raise_on_status(word)
-    return host[: n_rows * n_cols].view(n_rows, n_cols).numpy(), n_labels
+    values = host[: n_rows * n_cols].view(n_rows, n_cols).numpy()
+    if values.nbytes <= (8 << 20):
+        # a caller that keeps its tables (a plate sweep, one field per call) would keep the pinned staging block of every
+        # one of them, and every later call would pay a fresh cudaHostAlloc (3 ms per C2 field): small tables are handed
+        # over as pageable copies (0.1 ms), the block goes back to the host allocator's cache
+        values = values.copy()
+    return values, n_labels
 
 
 def extract_table(tree: dict, masks, pixels, device=None, plan: engine.Plan | None = None,

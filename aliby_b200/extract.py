@@ -153,9 +153,10 @@ def _graphed(key, build):
     return g
 
 
-def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
+def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None, strict_labels: bool = True):
     """planes: list of (Y, X) arrays, or the (P, Y, X) uint16 stack of them; pixels: (tiles, C, Z, Y, X) ndarray / tensor /
-    TileView."""
+    TileView.  ``strict_labels=False``: ids above a plane's ``n_labels`` are ignored instead of raising (the live overlap
+    path of the reference enumerates 1..k for k distinct ids and never looks at larger ones)."""
     import torch
 
     from .tile import TileView
@@ -198,7 +199,7 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
             g.run(host_labels, src)
             host = g.buf.cpu()
             n_cells = g.P * g.cap * plan.n_columns
-            engine.raise_on_status(host[n_cells:].view(torch.int32)[0])
+            engine.raise_on_status(int(host[n_cells:].view(torch.int32)[0]) & (~0 if strict_labels else ~1))
             return host[:n_cells].view(g.P * g.cap, plan.n_columns).numpy()[g.rows(n_labels)]
     labels_dev = torch.empty(host_labels.shape, dtype=torch.uint16, device=device)
     engine.host_to_device(labels_dev, host_labels, slot="labels")
@@ -225,7 +226,7 @@ def _run_dense(plan, planes, plane_tile, n_labels, pixels, device=None):
     buf, table, status = engine.alloc_table(n_objects, plan.n_columns, device)
     engine.run_planes(plan, labels_dev, plane_tile, n_labels, px_dev, offs, cs, zs, rs, C_, Z_, out=table, status=status)
     host = buf.cpu()  # one copy: the table and the call's error flags
-    engine.raise_on_status(host[n_objects * plan.n_columns :].view(torch.int32)[0])
+    engine.raise_on_status(int(host[n_objects * plan.n_columns :].view(torch.int32)[0]) & (~0 if strict_labels else ~1))
     return host[: n_objects * plan.n_columns].view(n_objects, plan.n_columns).numpy()
 
 
@@ -637,7 +638,9 @@ def extract_tree(
                 n_labels.append(int(plane.max()) if plane.size else 0)
     n_labels = np.asarray(n_labels, dtype=np.int64)
     base = np.concatenate([[0], np.cumsum(n_labels)])
-    dense = _run_dense(plan, planes, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels)
+    # (overlap without original ids: the reference enumerates 1..k of every stack and ignores larger ids, extract.py:478-500)
+    dense = _run_dense(plan, planes, np.asarray(plane_tile, dtype=np.int32), n_labels, pixels,
+                       strict_labels=not (overlap and inverse_mappings is None))
 
     if counts is not None:
         # the objects are the ids 1..k of every plane in plane order: row = position, no per-object Python work

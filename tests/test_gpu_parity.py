@@ -143,6 +143,22 @@ def test_golden_overlap(ab):
     assert_same(got, g["values"], 0.0, "overlap")
 
 
+def test_overlap_non_sequential_ids_like_the_reference(ab):
+    """The live overlap path with ids that are NOT sequential (values from the real reference, run in the build
+    container): for k distinct ids the reference enumerates 1..k and reads the plane of the id itself — id 1 absent (area
+    0, mean NaN), id 2 measured, id 5 never looked at; no error."""
+    from functools import partial
+
+    m = np.zeros((1, 12, 12), np.uint16)
+    m[0, 1:4, 1:4] = 2
+    m[0, 6:10, 5:9] = 5
+    px = np.arange(2 * 12 * 12, dtype=np.uint16).reshape(1, 2, 1, 12, 12)
+    tree = {"None": {"None": ["area"]}, 0: {"max": ["mean"]}}
+    items, got = ab.process_tree_masks_overlap(tree, [m], px, partial(ab.extract_tree, overlap=True))
+    assert [tuple(i[0]) for i in items] == [(0, 0, 1), (0, 0, 1), (0, 0, 2), (0, 0, 2)]
+    assert got[0] == 0.0 and got[1] != got[1] and got[2] == 9.0 and got[3] == 26.0
+
+
 # ---------------------------------------------------------------- oracle comparisons on synthetic fields
 def test_config_c1(ab):
     """BASELINE.json configs[0]: 2 channels x 1080^2, ~300 objects, intensity + sizeshape."""

@@ -1,0 +1,96 @@
+"""Randomised differential check of the oracle against the REAL reference (build container only) — TEST INFRASTRUCTURE.
+
+    python oracle/diff_reference.py [n_cases]
+
+``tests/golden/*.npz`` pin the oracle on fixed cases; this script throws random small planes at both — odd sizes, 1-pixel
+cells, id gaps, touching cells, cells on the border, constant / zero / saturated cells, uint8 and uint16, Z stacks under
+max and add, several tiles — runs ``extraction.extract.process_tree_masks`` of ``/root/reference/src`` and
+``oracle.port.run_tree`` / ``oracle.fast.run_tree`` on the same inputs and compares every value (bit-exact for what
+NumPy derives from integers, 1e-12 for fp64 sums).  ``/root/reference`` does not exist on the GPU box: nothing in
+``tests/`` runs this; its last result is recorded in DESIGN.md §5."""
+
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import make_golden as mg  # noqa: E402
+
+SHAPE = ["area", "centroid_x", "centroid_y", "eccentricity", "volume", "conical_volume", "spherical_volume", "min_maj_approximation"]
+INTENSITY = ["mean", "std", "median", "total", "total_squared", "max2p5pc", "max5px_median", "moment_of_inertia", "ratio"]
+
+
+def random_case(rng):
+    H, W = int(rng.integers(9, 60)), int(rng.integers(9, 70))
+    n_tiles = int(rng.integers(1, 4))
+    Z = int(rng.integers(1, 4))
+    dtype = np.uint8 if rng.random() < 0.3 else np.uint16
+    top = np.iinfo(dtype).max
+    masks = []
+    for _ in range(n_tiles):
+        lab = np.zeros((H, W), np.uint16)
+        nid = 1
+        for _ in range(int(rng.integers(0, 7))):
+            h, w = int(rng.integers(1, max(2, H // 2))), int(rng.integers(1, max(2, W // 2)))
+            r, c = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+            yy, xx = np.mgrid[0:h, 0:w]
+            blob = ((yy - (h - 1) / 2) / max(1, h / 2)) ** 2 + ((xx - (w - 1) / 2) / max(1, w / 2)) ** 2 <= 1.0 if rng.random() < 0.6 else np.ones((h, w), bool)
+            lab[r : r + h, c : c + w][blob] = nid
+            nid += int(rng.integers(1, 3))
+        masks.append(lab)
+    kind = rng.integers(0, 3)
+    if kind == 0:
+        px = rng.integers(0, top + 1, size=(n_tiles, 2, Z, H, W)).astype(dtype)
+    elif kind == 1:
+        px = np.clip(rng.integers(0, top // 2 + 1) + rng.poisson(20, size=(n_tiles, 2, Z, H, W)), 0, top).astype(dtype)
+    else:
+        px = np.full((n_tiles, 2, Z, H, W), rng.choice([0, 7, top]), dtype=dtype)
+    tree = {"None": {"None": list(SHAPE)}, 0: {"max": list(INTENSITY)}, 1: {"add": ["mean", "median", "total", "std", "max2p5pc"]}}
+    return tree, masks, px
+
+
+def same(a, b, tol):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    if a.shape != b.shape:
+        return False
+    nan = np.isnan(a)
+    return bool(np.array_equal(nan, np.isnan(b)) and np.all(np.abs(a[~nan] - b[~nan]) <= tol * np.maximum(1.0, np.abs(b[~nan]))))
+
+
+def main(n_cases: int = 40) -> int:
+    mg.install_shims()
+    sys.path.insert(0, mg.REF)
+    warnings.filterwarnings("ignore")
+    from extraction import extract as ref
+
+    from oracle import fast, port
+
+    rng = np.random.default_rng(20260)
+    exact = {"area", "centroid_x", "centroid_y", "eccentricity", "volume", "min_maj_approximation", "mean", "median", "total",
+             "total_squared", "max2p5pc", "max5px_median", "ratio"}
+    n_values = 0
+    for case in range(n_cases):
+        tree, masks, px = random_case(rng)
+        m = masks if len(masks) > 1 else masks[0]
+        r_items, r_res = ref.process_tree_masks(tree, m, px, ref.extract_tree)
+        for name, impl in (("port", port), ("fast", fast)):
+            o_items, o_res = impl.run_tree(tree, m, px)
+            assert len(o_items) == len(r_items), (case, name, len(o_items), len(r_items))
+            for (ri, rr), (oi, orr) in zip(zip(r_items, r_res), zip(o_items, o_res)):
+                assert tuple(ri[0]) == tuple(oi[0]) and tuple(ri[1]) == tuple(oi[1]), (case, name, ri, oi)
+                tol = 0.0 if ri[1][2] in exact else 1e-12
+                assert same(rr, orr, tol), (case, name, ri, rr, orr)
+                n_values += 1
+    print(f"{n_cases} random cases, {n_values} values: oracle.port and oracle.fast agree with the reference")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(int(sys.argv[1]) if len(sys.argv) > 1 else 40))

@@ -89,6 +89,59 @@ def main(n_cases: int = 40) -> int:
                 assert same(rr, orr, tol), (case, name, ri, rr, orr)
                 n_values += 1
     print(f"{n_cases} random cases, {n_values} values: oracle.port and oracle.fast agree with the reference")
+    # ---- tile windows and the out-of-frame padding (tiles.py:109-166, tiler.py:601-650) ----
+    import ast
+
+    src = open(os.path.join(mg.REF, "aliby/tile/tiler.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "if_out_of_bounds_pad")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "tiler.py", "exec"), ns)
+    from aliby.tile.tiles import TileLocations
+
+    n_crops = 0
+    for case in range(n_cases):
+        H, W = int(rng.integers(20, 90)), int(rng.integers(20, 90))
+        size = int(rng.choice([8, 11, 16, 17]))
+        frame = rng.integers(0, 4000, size=(int(rng.integers(1, 4)), H, W)).astype(np.uint16 if rng.random() < 0.7 else np.uint8)
+        centres = [(int(rng.integers(-2, H + 3)), int(rng.integers(-2, W + 3))) for _ in range(int(rng.integers(1, 6)))]
+        drifts = [[0.0, 0.0]] + [[float(rng.normal(0, 2)), float(rng.normal(0, 2))] for _ in range(int(rng.integers(0, 3)))]
+        locs = TileLocations(centres, tile_size=size, max_size=(H, W), drifts=drifts)
+        for tp in range(len(drifts)):
+            for i, tile in enumerate(locs):
+                want = ns["if_out_of_bounds_pad"](frame, tile.as_range(tp))
+                got = port.crop_with_padding(frame, port.tile_window(centres[i], (size, size), drifts, tp))
+                assert want.shape == got.shape and want.dtype == got.dtype, (case, tp, i, want.shape, got.shape, want.dtype, got.dtype)
+                assert np.array_equal(want, got, equal_nan=True), (case, tp, i)
+                n_crops += 1
+    print(f"{n_crops} tile crops (drifts, windows that leave the frame, NaN tiles): oracle.port agrees with the reference")
+    # ---- the long -> wide pivot of the HOST side (aliby_b200.extract.format_extraction, generic path) ----
+    from aliby_b200 import extract as ours
+
+    n_tables = 0
+    for case in range(n_cases):
+        objs = [(int(t), int(k)) for t in range(int(rng.integers(1, 4))) for k in range(1, int(rng.integers(1, 6)))]
+        insts = [("None", "None", "area"), (0, "max", "mean"), (1, "add", "median"), (0, "max", "intensity"), ((0, 1), "None", "max", "pearson")]
+        insts = [insts[j] for j in rng.permutation(len(insts))[: int(rng.integers(1, len(insts) + 1))]]
+        items, results = [], []
+        for o in objs:
+            for inst in insts:
+                if rng.random() < 0.1:
+                    continue  # a ragged product: missing cells become nulls
+                items.append((o, inst))
+                if inst[-1] in ("intensity", "pearson"):
+                    results.append({f"K_{j}": np.array([float(rng.normal())]) for j in range(int(rng.integers(1, 4)))})
+                else:
+                    results.append(float(rng.normal()) if rng.random() < 0.9 else float("nan"))
+        if not items:
+            continue
+        a = ref.format_extraction((tuple(items), list(results)))
+        b = ours.format_extraction((tuple(items), list(results)))
+        assert a.column_names == b.column_names and a.schema == b.schema, (case, a.schema, b.schema)
+        for c in a.column_names:
+            x, y = a.column(c).to_pylist(), b.column(c).to_pylist()
+            assert len(x) == len(y) and all((p == q) or (p is not None and q is not None and p != p and q != q) for p, q in zip(x, y)), (case, c)
+        n_tables += 1
+    print(f"{n_tables} random (instructions, results) lists: aliby_b200.extract.format_extraction builds the reference's table")
     return 0
 
 

@@ -142,6 +142,48 @@ def main(n_cases: int = 40) -> int:
             assert len(x) == len(y) and all((p == q) or (p is not None and q is not None and p != p and q != q) for p, q in zip(x, y)), (case, c)
         n_tables += 1
     print(f"{n_tables} random (instructions, results) lists: aliby_b200.extract.format_extraction builds the reference's table")
+    # ---- profile assembly over time points and steps (pipe_core.py:453-512) ----
+    import pyarrow
+
+    from aliby_b200 import pipe as our_pipe
+
+    src = open(os.path.join(mg.REF, "aliby/pipe_core.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_profiles_from_state")
+    ns = {"numpy": np, "np": np, "pyarrow": pyarrow, "pa": pyarrow, "format_extraction": ref.format_extraction}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "pipe_core.py", "exec"), ns)
+    n_states = 0
+    for case in range(n_cases):
+        steps = ["extract_nuclei"] + (["extract_cell"] if rng.random() < 0.6 else []) + (["extractmulti_nuclei"] if rng.random() < 0.6 else [])
+        insts = {"extract": [("None", "None", "area"), (0, "max", "mean"), (1, "max", "median")],
+                 "extractmulti": [((0, 1), "None", "max", "pearson")]}
+        n_tp = int(rng.integers(1, 5))
+        # (the join of extract with extractmulti is keyed by tp / tile / object / label: the same objects on both sides)
+        objs_of = {(obj, tp): ([] if rng.random() < 0.2 else [(int(t), int(k)) for t in range(2) for k in range(1, int(rng.integers(2, 5)))])
+                   for obj in ("nuclei", "cell") for tp in range(n_tp)}
+        state = {"data": {s_: [] for s_ in steps}}
+        for s_ in steps:
+            prefix, obj = s_.split("_")
+            for tp in range(n_tp):
+                items, results = [], []
+                for o in objs_of[(obj, tp)]:
+                    for inst in insts[prefix]:
+                        items.append((o, inst))
+                        results.append({"Correlation_Pearson": np.array([float(rng.normal())])} if prefix == "extractmulti" else float(rng.normal()))
+                state["data"][s_].append((tuple(items), results))
+        pipeline = {"steps": {"tile": {}, **{s_: {} for s_ in steps}}}
+        a = ns["get_profiles_from_state"](state, pipeline)
+        b = our_pipe.get_profiles_from_state(state, pipeline)
+        assert a.column_names == b.column_names and a.schema == b.schema, (case, a.schema, b.schema)
+        key_cols = [c for c in a.column_names if c.startswith("metadata_")]
+
+        def keyed(t):
+            rows = t.to_pylist()
+            return {tuple(r[k] for k in key_cols): tuple((c, None if r[c] is None else round(r[c], 12)) for c in t.column_names if c not in key_cols)
+                    for r in rows}
+
+        assert a.num_rows == b.num_rows and keyed(a) == keyed(b), case
+        n_states += 1
+    print(f"{n_states} random pipeline states: aliby_b200.pipe.get_profiles_from_state builds the reference's profile table")
     return 0
 
 
